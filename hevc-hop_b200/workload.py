@@ -1,0 +1,132 @@
+"""Synthetic PU batches for the stand-alone HOP candidate-search microbench (BASELINE.json configs[2],
+SURVEY.md §8d) and for parity tests.
+
+Every PU gets its own little "causal neighbourhood": a plane of (2*SR + W + 8) x (SR + H + 8) int16
+samples cut from the synthetic lenslet image, with the PU's own position at (SR, SR).  Samples at
+x >= SR and y >= SR (the PU itself and everything right/below it) are NOT_VALID (-1), exactly the
+staircase the SS reference has while a CU is being coded.  The search window, gate offsets and cost
+state are what TEncSearch::xSetSearchRange / xMotionEstimation produce for a 2Nx2N PU at a CU origin
+(TEncSearch.cpp:6224-6259, 4555-4560).
+"""
+import math
+
+import numpy as np
+
+from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
+from .lenslet import lenslet_luma
+
+SEARCH_RANGE = 128
+PROBE_PAD = 8
+
+
+def lambda_motion_sad(qp=32):
+    """m_uiLambdaMotionSAD for an intra(SS) slice at `qp`: TEncSlice.cpp:385-395 + TComRdCost.cpp:167-173."""
+    lam = 0.57 * 2.0 ** ((qp - 12) / 3.0)
+    return int(math.floor(65536.0 * math.sqrt(lam)))
+
+
+def plane_dims(cols, rows, sr=SEARCH_RANGE):
+    return 2 * sr + cols + PROBE_PAD, sr + rows + PROBE_PAD
+
+
+class PuBatch:
+    """org/ref sample buffers + K1 and K2 job arrays for `n` PUs of one shape."""
+
+    def __init__(self, cols, rows, n, seed=0, bit_depth=8, qp=32, sr=SEARCH_RANGE, use_had=1,
+                 n_start=1, threshold=0xFFFFFFFE, source=None):
+        self.cols, self.rows, self.n, self.sr = cols, rows, n, sr
+        pw, ph = plane_dims(cols, rows, sr)
+        self.pw, self.ph = pw, ph
+        rng = np.random.default_rng(seed)
+        if source is None:
+            # one big lenslet picture, planes are random crops of it (cheap for thousands of PUs)
+            side = max(1024, 2 * pw)
+            source = lenslet_luma(side, side, seed=seed, bit_depth=bit_depth).astype(np.int16)
+        sh, sw = source.shape
+        ref = np.empty((n, ph, pw), dtype=np.int16)
+        org = np.empty((n, rows, cols), dtype=np.int16)
+        ys = rng.integers(0, sh - ph, size=n)
+        xs = rng.integers(0, sw - pw, size=n)
+        for i in range(n):
+            crop = source[ys[i]:ys[i] + ph, xs[i]:xs[i] + pw]
+            org[i] = crop[sr:sr + rows, sr:sr + cols]
+            ref[i] = crop
+        ref[:, sr:, sr:] = -1
+        self.org = org.reshape(-1)
+        self.ref = ref.reshape(-1)
+        lam = lambda_motion_sad(qp)
+
+        sj = np.zeros(n, dtype=SEARCH_JOB_DT)
+        idx = np.arange(n, dtype=np.int64)
+        sj["org_off"] = idx * (rows * cols)
+        sj["ref_off"] = idx * (ph * pw) + sr * pw + sr
+        sj["org_stride"] = cols
+        sj["ref_stride"] = pw
+        sj["cols"], sj["rows"] = cols, rows
+        sj["rng_left"], sj["rng_right"] = -sr, sr
+        sj["rng_top"], sj["rng_bottom"] = -sr, -4            # min(bottom, -offY-4), offY = 0
+        sj["offset_x"], sj["offset_y"] = -cols - 4, -rows - 4
+        sj["is_ss"], sj["fast_enc"], sj["bit_depth"] = 1, 1, bit_depth
+        sj["cost"]["lambda_cost"] = lam
+        sj["cost"]["cost_scale"] = 2
+        # AMVP-like predictor: a quarter-pel vector pointing into the causal area
+        sj["cost"]["pred"]["hor"] = (rng.integers(-sr // 2, sr // 2, size=n) * 4).astype(np.int16)
+        sj["cost"]["pred"]["ver"] = (rng.integers(-sr, 0, size=n) * 4).astype(np.int16)
+        self.search_jobs = sj
+
+        gj = np.zeros(n, dtype=GT_JOB_DT)
+        for k in ("org_off", "ref_off", "org_stride", "ref_stride", "cols", "rows", "bit_depth"):
+            gj[k] = sj[k]
+        # start vector: somewhere in the fully coded rows above the PU, 2W x 2H window inside the plane
+        hy_lo = -sr + rows // 2
+        hy_hi = max(hy_lo, -rows - rows // 2 - 4)
+        hx = rng.integers(-sr + cols // 2, sr - cols // 2 + 1, size=n)
+        hy = rng.integers(hy_lo, hy_hi + 1, size=n)
+        gj["ss_cand"]["hor"] = hx.astype(np.int16)
+        gj["ss_cand"]["ver"] = hy.astype(np.int16)
+        gj["num_pred"] = 2                                     # fillMvpCand always returns AMVP_MAX_NUM_CANDS
+        if n_start > 1:
+            for k in range(min(n_start - 1, 2)):
+                ax = rng.integers(-sr + cols // 2, sr - cols // 2 + 1, size=n) * 4 + rng.integers(0, 4, size=n)
+                ay = rng.integers(hy_lo, hy_hi + 1, size=n) * 4 + rng.integers(0, 4, size=n)
+                gj["amvp"][:, k]["hor"] = ax.astype(np.int16)
+                gj["amvp"][:, k]["ver"] = ay.astype(np.int16)
+        gj["threshold"] = threshold
+        gj["use_had"] = use_had
+        gj["cost"]["lambda_cost"] = lam
+        gj["cost"]["cost_scale"] = 0
+        gj["cost"]["pred"] = sj["cost"]["pred"]
+        self.gt_jobs = gj
+
+    def passes(self):
+        return gt_passes(self.cols, self.rows)
+
+
+def gt_passes(cols, rows):
+    """Diamond passes per start vector: j0 = window, window/2, ... > 1, at most 6 (TEncSearch.cpp:5181)."""
+    j0 = (min(cols, rows) >> 1) * 2
+    p = 0
+    while j0 > 1 and p < 6:
+        p += 1
+        j0 //= 2
+    return p
+
+
+CANDIDATES_PER_PASS = 56   # affine corner sets among the 620 diamond combinations
+
+
+def dist_jobs(cols, rows, n, seed=0, bit_depth=8, func=HOP_DF_HADS, sub_shift=0):
+    """n independent (org, cur) block pairs of one shape for the K3 stand-alone distortion kernels."""
+    rng = np.random.default_rng(seed)
+    maxv = (1 << bit_depth) - 1
+    org = rng.integers(0, maxv + 1, size=(n, rows, cols)).astype(np.int16)
+    cur = np.clip(org + rng.integers(-40, 41, size=org.shape), -1, maxv).astype(np.int16)
+    jobs = np.zeros(n, dtype=DIST_JOB_DT)
+    idx = np.arange(n, dtype=np.int64)
+    jobs["org_off"] = idx * rows * cols
+    jobs["cur_off"] = idx * rows * cols
+    jobs["org_stride"] = cols
+    jobs["cur_stride"] = cols
+    jobs["cols"], jobs["rows"] = cols, rows
+    jobs["func"], jobs["sub_shift"], jobs["bit_depth"] = func, sub_shift, bit_depth
+    return jobs, org.reshape(-1), cur.reshape(-1)

@@ -1,0 +1,200 @@
+/*
+ * hop_gpu.h -- C ABI of libhopgpu, the B200 (sm_100a) implementation of the HEVC-HOP encoder hot path.
+ *
+ * The library replaces, inside an otherwise unchanged HM-15/HEVC-HOP encoder, the bodies of
+ *
+ *   TEncSearch::xPatternSearch      source/Lib/TLibEncoder/TEncSearch.cpp:6262-6371   (K1, SS full search)
+ *   TEncSearch::xPatternSearchGT    source/Lib/TLibEncoder/TEncSearch.cpp:4686-5467   (K2, HOP/GT diamond search)
+ *   TComRdCost::m_afpDistortFunc[]  source/Lib/TLibCommon/TComRdCost.cpp:177-221      (K3, SAD / HADs table)
+ *   TEncCu::xCopyYuv2SSRef          source/Lib/TLibEncoder/TEncCu.cpp:1677-1715       (K4, SS reference update)
+ *   + TComPicYuv::extendPicBorder   source/Lib/TLibCommon/TComPicYuv.cpp:236-274
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/torch types cross this line.
+ *   - `Pel` of the reference is int16_t (TypeDef.h:300); NOT_VALID samples are -1 (CommonDef.h:126).
+ *   - every function returns HOP_OK (0) or a negative HopStatus; there is no CPU fallback: when no
+ *     CUDA device / kernel image is usable the call fails with HOP_ERR_CUDA (hop_last_error() has text).
+ *   - the reference has no error returns (Void + exit()); the host shim (hop_shim.h) turns a non-zero
+ *     status into fprintf(stderr)+exit(EXIT_FAILURE), as the reference does for its own fatal errors.
+ *   - host entry points copy in/out and never retain host pointers; `_dev` entry points take device
+ *     pointers plus a CUstream/cudaStream_t passed as void* (NULL = the context's own stream).
+ *   - a context is used by one host thread at a time (the reference encoder is single threaded).
+ */
+#ifndef HOP_GPU_H
+#define HOP_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOP_ABI_VERSION 1
+
+typedef enum HopStatus {
+  HOP_OK            = 0,
+  HOP_ERR_ARG       = -1,  /* bad argument (NULL, size out of range, unsupported block shape) */
+  HOP_ERR_CUDA      = -2,  /* CUDA runtime / launch failure, or no sm_100 device               */
+  HOP_ERR_NOMEM     = -3,
+  HOP_ERR_STATE     = -4   /* call order violated (e.g. search before hop_ref_reset)            */
+} HopStatus;
+
+#define HOP_MAX_UINT   0xFFFFFFFFu   /* MAX_UINT, CommonDef.h */
+#define HOP_NOT_VALID  (-1)          /* NOT_VALID, CommonDef.h:126 */
+#define HOP_MAX_PU     64            /* largest PU edge (CTU 64) */
+#define HOP_MAX_PRED   3             /* AMVP_MAX_NUM_CANDS_MEM, CommonDef.h */
+
+/* TComMv (TComMv.h): two Shorts. */
+typedef struct HopMv { int16_t hor, ver; } HopMv;
+
+/* Motion-cost state of TComRdCost read by getCost()/getBits() (TComRdCost.h:128-136, 185-202). */
+typedef struct HopCostState {
+  uint32_t lambda_cost;   /* m_uiCost, i.e. m_uiLambdaMotionSAD after getMotionCost(1,0)  */
+  int32_t  cost_scale;    /* m_iCostScale: 2 inside xPatternSearch, 0 inside xPatternSearchGT */
+  HopMv    pred;          /* m_mvPredictor (quarter-pel)                                   */
+} HopCostState;
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 -- one xPatternSearch call (TEncSearch.cpp:6262-6371).
+ * `org`/`ref` are sample offsets into the two buffers handed to the batch call; ref_off addresses
+ * piRefY, i.e. the PU's own position in the SS reference plane.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HopSearchJob {
+  int64_t  org_off;        /* pcPatternKey->getROIY()                          */
+  int64_t  ref_off;        /* piRefY                                           */
+  int32_t  org_stride;     /* pcPatternKey->getPatternLStride()                */
+  int32_t  ref_stride;     /* iRefStride                                       */
+  int32_t  cols, rows;     /* getROIYWidth/Height: 4..64, see hop_shape_supported */
+  int32_t  rng_left, rng_top, rng_right, rng_bottom;   /* pcMvSrchRngLT / RB (integer pel) */
+  int32_t  offset_x, offset_y;                         /* riOffsetX / riOffsetY            */
+  int32_t  is_ss;          /* isSSE: apply the causal gate + isValidPattern    */
+  int32_t  fast_enc;       /* m_pcEncCfg->getUseFastEnc(): rows>8 => iSubShift=1 (:6303-6309) */
+  int32_t  bit_depth;      /* g_bitDepthY                                      */
+  HopCostState cost;
+} HopSearchJob;
+
+typedef struct HopSearchResult {
+  int32_t  found;          /* isValid (:6356); 0 => sad == HOP_MAX_UINT, mv untouched by the shim */
+  HopMv    mv;             /* rcMv == ssBestCand[0] (IT_SS_NUMBER_OF_BEST_CAND 1)                 */
+  uint32_t sad;            /* ruiSAD = best - getCost(best)                                        */
+  uint32_t cost;           /* uiSadBest (SAD + motion cost) -- extra, for tests                    */
+} HopSearchResult;
+
+/* ---------------------------------------------------------------------------------------------
+ * K2 -- one xPatternSearchGT call, diamond branch (TEncSearch.cpp:4686-4790, 5093-5467) with the
+ * compile-time configuration the reference ships (TypeDef.h:207-240): IT_GT_AFFINE 1,
+ * IT_GT_SEARCH 2, IT_GT_GRID_SIZE 2, IT_MAX_NSS_Iteration 6, IT_Independent_Iterations 1,
+ * bilinear warp in IEEE binary64 (TComPrediction.cpp:807-832, 904-1030), W_GT 1, IT_GT_CODING 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HopGtJob {
+  int64_t  org_off;
+  int64_t  ref_off;
+  int32_t  org_stride;
+  int32_t  ref_stride;
+  int32_t  cols, rows;
+  HopMv    ss_cand;               /* bestSSCand[0], integer pel (:5116-5123)                       */
+  int32_t  num_pred;              /* AMVPInfo::iN (:5101)                                          */
+  HopMv    amvp[HOP_MAX_PRED];    /* AMVPInfo::m_acMvCand, raw quarter-pel (:5104, 5144-5153)      */
+  uint32_t threshold;             /* ruiCost on entry = cost to beat (:4769)                       */
+  int32_t  use_had;               /* m_pcEncCfg->getUseHADME() (:4772)                             */
+  int32_t  bit_depth;             /* g_bitDepthY                                                   */
+  HopCostState cost;              /* cost_scale is 0 here (:4619)                                  */
+} HopGtJob;
+
+typedef struct HopGtResult {
+  int32_t  gt_flag;        /* gtFlag (:5441/:5461)                                              */
+  HopMv    gt[4];          /* rcGT0..rcGT3 (:5448-5451), zero when !gt_flag                      */
+  uint32_t cost;           /* ruiCost on exit (unchanged threshold when !gt_flag)                */
+  HopMv    mv_int;         /* pcMvInt on exit (:5455); valid only when gt_flag                   */
+  int32_t  best_index;     /* extra, for tests: (start*8 + pass)*64 + candidate, or -1           */
+  uint32_t n_candidates;   /* extra: HOP candidates warped + scored by this call                */
+} HopGtResult;
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 -- one DistFunc call (TComRdCost.cpp:513-1010, 1366-1708).
+ * ------------------------------------------------------------------------------------------- */
+typedef enum HopDistFunc {
+  HOP_DF_SAD  = 8,    /* DF_SAD  (TypeDef.h DFunc): xGetSAD{,4,8,12,16,16N,24,32,48,64} by width */
+  HOP_DF_HADS = 22    /* DF_HADS: xGetHADs (8x8 / 4x4 / 2x2 tiles)                                */
+} HopDistFunc;
+
+typedef struct HopDistJob {
+  int64_t  org_off, cur_off;
+  int32_t  org_stride, cur_stride;
+  int32_t  cols, rows;
+  int32_t  func;           /* HopDistFunc */
+  int32_t  sub_shift;      /* DistParam::iSubShift (SAD only) */
+  int32_t  bit_depth;
+} HopDistJob;
+
+/* ---------------------------------------------------------------------------------------------
+ * Context: one per encoder instance = per GPU.  Owns a stream, scratch buffers and (optionally) the
+ * device mirror of the SS reference luma plane (TEncTop::m_cSSRef / TComPicYuv, margin 80).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HopCtx HopCtx;
+
+int         hop_abi_version(void);
+const char* hop_last_error(void);                 /* thread-local text of the last failure */
+int         hop_device_count(void);               /* number of CUDA devices, <0 on error    */
+
+int  hop_ctx_create(int device, HopCtx** out);
+void hop_ctx_destroy(HopCtx* ctx);
+int  hop_ctx_sync(HopCtx* ctx);
+void* hop_ctx_stream(HopCtx* ctx);                /* the context's cudaStream_t */
+
+/* 1 if (cols,rows) is a PU shape the kernels accept: both in {4,8,12,16,24,32,48,64}, not 4x4. */
+int  hop_shape_supported(int cols, int rows);
+
+/* SS reference mirror (K4).  pic_w/pic_h luma size, margin as TComPicYuv (80), stride = pic_w+2*margin. */
+int  hop_ref_create(HopCtx* ctx, int pic_w, int pic_h, int margin);
+int  hop_ref_reset(HopCtx* ctx, int value);       /* setPicPel(NOT_VALID), TComSlice.cpp:253 */
+/* copy a w x h block of reconstruction to (x,y) and re-extend the borders (TEncCu.cpp:1694-1696) */
+int  hop_ref_update(HopCtx* ctx, int x, int y, int w, int h, const int16_t* src, int src_stride);
+/* read back the whole plane incl. margins ((pic_h+2m) x stride samples) -- tests / debugging */
+int  hop_ref_download(HopCtx* ctx, int16_t* dst, size_t dst_samples);
+int  hop_ref_stride(HopCtx* ctx);
+/* device pointer of sample (0,0) of the mirror, for the _dev entry points */
+const int16_t* hop_ref_origin_dev(HopCtx* ctx);
+
+/* ---- host entry points (copy in, run, copy out, synchronous) -------------------------------
+ * `org`/`ref` are HOST buffers of org_samples / ref_samples int16 samples; job offsets index them.
+ * ref == NULL means "the context's SS reference mirror" (offsets are then relative to its sample
+ * (0,0) and may be negative into the margin). */
+int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs,
+                             const int16_t* org, size_t org_samples,
+                             const int16_t* ref, size_t ref_samples,
+                             HopSearchResult* out);
+int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs,
+                                const int16_t* org, size_t org_samples,
+                                const int16_t* ref, size_t ref_samples,
+                                HopGtResult* out);
+int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs,
+                   const int16_t* org, size_t org_samples,
+                   const int16_t* cur, size_t cur_samples,
+                   uint32_t* out);
+
+/* ---- device entry points (everything already resident in HBM, asynchronous on `stream`) ---- */
+int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,
+                                 const int16_t* d_org, const int16_t* d_ref,
+                                 HopSearchResult* d_out, void* stream);
+int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs,
+                                    const int16_t* d_org, const int16_t* d_ref,
+                                    HopGtResult* d_out, void* stream);
+int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs,
+                       const int16_t* d_org, const int16_t* d_cur,
+                       uint32_t* d_out, void* stream);
+
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+uint64_t hop_ctx_launch_count(HopCtx* ctx);
+
+/* ALU peak probes for the roofline: run a dependent-free instruction loop on every
+ * SM and return achieved Gop/s (lane-operations) for the named pipe.
+ * what: 0 = int32 IADD3, 1 = VABSDIFF4-accumulate (4 byte-SADs per lane-op), 2 = fp64 DADD,
+ *       3 = fp64 DMUL, 4 = fp64 DFMA, 5 = int32 LOP3/SHF mix. */
+int hop_probe_alu(HopCtx* ctx, int what, double* gops_out, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOP_GPU_H */

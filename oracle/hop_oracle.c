@@ -1,0 +1,405 @@
+/*
+ * hop_oracle.c -- CPU restatement of the HEVC-HOP hot path.  TEST INFRASTRUCTURE ONLY (see hop_oracle.h).
+ *
+ * Each function cites the reference lines (relative to /root/reference/source/Lib) it restates.
+ * Build: gcc -O2 -ffp-contract=off, x86-64 baseline (SSE2 doubles, no FMA) -- the warp is IEEE
+ * binary64 in the reference (build/linux/common/makefile.base:50,66: -O3, no -march) and must not be
+ * contracted.  Parity pin: tests/test_oracle_vs_ref.py and tests/golden/ compare this file with the
+ * compiled reference itself (oracle/_ref/libhopref.so).
+ */
+#include "hop_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+#define DIST_SHIFT(bit_depth) ((bit_depth) - 8)   /* DISTORTION_PRECISION_ADJUSTMENT, TypeDef.h:162-167 */
+
+/* ------------------------------------------------------------------------------------------------
+ * bit costs -- TLibCommon/TComRdCost.cpp:270-284, TComRdCost.h:185-216
+ * ---------------------------------------------------------------------------------------------- */
+uint32_t orc_component_bits(int32_t val)
+{
+  uint32_t length = 1;
+  uint32_t temp = (val <= 0) ? (uint32_t)((-val << 1) + 1) : (uint32_t)(val << 1);
+  while (temp != 1) { temp >>= 1; length += 2; }
+  return length;
+}
+
+uint32_t orc_get_bits(const HopCostState* cs, int32_t x, int32_t y)
+{
+  /* FIX203 branch, TComRdCost.h:196-199: (x << m_iCostScale) - m_mvPredictor */
+  return orc_component_bits((x << cs->cost_scale) - cs->pred.hor) +
+         orc_component_bits((y << cs->cost_scale) - cs->pred.ver);
+}
+
+uint32_t orc_get_cost_xy(const HopCostState* cs, int32_t x, int32_t y)
+{
+  return (cs->lambda_cost * orc_get_bits(cs, x, y)) >> 16;   /* UInt arithmetic, TComRdCost.h:187 */
+}
+
+uint32_t orc_get_cost_bits(const HopCostState* cs, uint32_t bits)
+{
+  return (cs->lambda_cost * bits) >> 16;                      /* TComRdCost.h:193 */
+}
+
+uint32_t orc_get_bits_gt(int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t x2, int32_t y2)
+{
+  /* IT_GT_CODING 0, IT_GT_AFFINE 1 (GT3 not coded), W_GT 1 -- TComRdCost.h:204-216 */
+  return 1u * (orc_component_bits(x0) + orc_component_bits(y0) + orc_component_bits(x1) +
+               orc_component_bits(y1) + orc_component_bits(x2) + orc_component_bits(y2));
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SAD -- TComRdCost.cpp:513-1010.  setDistParam (:298-329) picks xGetSAD4/8/16/32/64 through
+ * g_aucConvertToBit (powers of two), xGetSAD12/24/48 by explicit test, else the generic xGetSAD,
+ * which ignores iSubShift (:513-539).
+ * ---------------------------------------------------------------------------------------------- */
+static int sad_width_has_subshift(int cols)
+{
+  return cols == 4 || cols == 8 || cols == 16 || cols == 32 || cols == 64 ||
+         cols == 12 || cols == 24 || cols == 48;
+}
+
+uint32_t orc_sad(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                 int cols, int rows, int sub_shift, int bit_depth)
+{
+  uint32_t sum = 0;
+  if (!sad_width_has_subshift(cols)) sub_shift = 0;
+  int step = 1 << sub_shift;
+  for (int r = rows; r != 0; r -= step) {
+    for (int n = 0; n < cols; n++) sum += (uint32_t)abs((int)org[n] - (int)cur[n]);
+    org += org_stride * step;
+    cur += cur_stride * step;
+  }
+  sum <<= sub_shift;
+  return sum >> DIST_SHIFT(bit_depth);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Hadamard -- TComRdCost.cpp:1366-1575 (tiles), :1641-1708 (xGetHADs).  The reference's butterfly
+ * networks are full 2-D Walsh-Hadamard transforms; sum(|coeff|) does not depend on coefficient order
+ * or sign conventions, only on the per-tile rounding: 8x8 (sad+2)>>2, 4x4 (satd+1)>>1, 2x2 none.
+ * ---------------------------------------------------------------------------------------------- */
+static uint32_t had_tile(const int16_t* org, const int16_t* cur, int so, int sc, int n)
+{
+  int d[64];
+  for (int y = 0; y < n; y++)
+    for (int x = 0; x < n; x++) d[y * n + x] = (int)org[y * so + x] - (int)cur[y * sc + x];
+  for (int y = 0; y < n; y++)                 /* rows */
+    for (int len = 1; len < n; len <<= 1)
+      for (int i = 0; i < n; i += len << 1)
+        for (int j = i; j < i + len; j++) {
+          int a = d[y * n + j], b = d[y * n + j + len];
+          d[y * n + j] = a + b; d[y * n + j + len] = a - b;
+        }
+  for (int x = 0; x < n; x++)                 /* columns */
+    for (int len = 1; len < n; len <<= 1)
+      for (int i = 0; i < n; i += len << 1)
+        for (int j = i; j < i + len; j++) {
+          int a = d[j * n + x], b = d[(j + len) * n + x];
+          d[j * n + x] = a + b; d[(j + len) * n + x] = a - b;
+        }
+  int satd = 0;
+  for (int k = 0; k < n * n; k++) satd += abs(d[k]);
+  if (n == 8) return (uint32_t)((satd + 2) >> 2);
+  if (n == 4) return (uint32_t)((satd + 1) >> 1);
+  return (uint32_t)satd;
+}
+
+uint32_t orc_hads(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride,
+                  int cols, int rows, int bit_depth)
+{
+  uint32_t sum = 0;
+  int n;
+  if ((rows % 8 == 0) && (cols % 8 == 0)) n = 8;
+  else if ((rows % 4 == 0) && (cols % 4 == 0)) n = 4;
+  else if ((rows % 2 == 0) && (cols % 2 == 0)) n = 2;
+  else return HOP_MAX_UINT;  /* assert(false) in the reference */
+  for (int y = 0; y < rows; y += n)
+    for (int x = 0; x < cols; x += n)
+      sum += had_tile(org + y * org_stride + x, cur + y * cur_stride + x, org_stride, cur_stride, n);
+  return sum >> DIST_SHIFT(bit_depth);
+}
+
+uint32_t orc_dist(const HopDistJob* job, const int16_t* org, const int16_t* cur)
+{
+  const int16_t* o = org + job->org_off;
+  const int16_t* c = cur + job->cur_off;
+  if (job->func == HOP_DF_HADS)
+    return orc_hads(o, job->org_stride, c, job->cur_stride, job->cols, job->rows, job->bit_depth);
+  return orc_sad(o, job->org_stride, c, job->cur_stride, job->cols, job->rows, job->sub_shift,
+                 job->bit_depth);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 -- TLibEncoder/TEncSearch.cpp:6262-6371 (+ isValidPattern TComRdCost.cpp:444-458)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_pattern_search(const HopSearchJob* job, const int16_t* org_buf, const int16_t* ref_buf,
+                        HopSearchResult* out)
+{
+  const int16_t* org = org_buf + job->org_off;
+  const int16_t* ref_y = ref_buf + job->ref_off;
+  const int stride = job->ref_stride;
+  uint32_t sad_best = HOP_MAX_UINT;
+  int best_x = 0, best_y = 0;
+  int is_valid = 0;
+  int sub_shift = 0;
+  if (job->fast_enc && job->rows > 8) sub_shift = 1;          /* :6303-6309 */
+
+  ref_y += job->rng_top * stride;                              /* :6311 */
+  for (int y = job->rng_top; y <= job->rng_bottom; y++) {
+    for (int x = job->rng_left; x <= job->rng_right; x++) {
+      const int16_t* srch = ref_y + x;
+      uint32_t sad = orc_sad(org, job->org_stride, srch, stride, job->cols, job->rows, sub_shift,
+                             job->bit_depth);                   /* :6323, before the gates */
+      if (job->is_ss) {
+        if ((x >= job->offset_x) && (y > job->offset_y)) continue;            /* :6328 */
+        const int16_t* lb = srch + (job->rows + 4) * stride;                  /* isValidPattern */
+        const int16_t* rb = lb + (job->cols + 4);
+        if (!((*lb != HOP_NOT_VALID) && (*rb != HOP_NOT_VALID))) continue;    /* :6330 */
+      }
+      is_valid = 1;
+      sad += orc_get_cost_xy(&job->cost, x, y);                 /* :6336 */
+      if (sad < sad_best) { sad_best = sad; best_x = x; best_y = y; }         /* :6338-6349 */
+    }
+    ref_y += stride;
+  }
+  memset(out, 0, sizeof(*out));
+  if (!is_valid) {                                              /* :6356-6360 */
+    out->found = 0; out->sad = HOP_MAX_UINT; out->cost = HOP_MAX_UINT;
+    return;
+  }
+  out->found = 1;
+  out->mv.hor = (int16_t)best_x; out->mv.ver = (int16_t)best_y;
+  out->cost = sad_best;
+  out->sad = sad_best - orc_get_cost_xy(&job->cost, best_x, best_y);          /* :6365 */
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * warp -- TLibCommon/TComPrediction.cpp:807-832, 904-1030
+ * ---------------------------------------------------------------------------------------------- */
+void orc_calc_param_projective(const int32_t x[4], const int32_t y[4], double h[9], int width, int height)
+{
+  double H, W, dx[4], dy[4];
+  W = (double)width - 1.0;
+  H = (double)height - 1.0;
+  dx[1] = (double)x[1] - x[2];
+  dx[2] = (double)x[3] - x[2];
+  dx[3] = (double)x[0] - x[1] + x[2] - x[3];
+  dy[1] = (double)y[1] - y[2];
+  dy[2] = (double)y[3] - y[2];
+  dy[3] = (double)y[0] - y[1] + y[2] - y[3];
+  h[2] = ((dx[3] * dy[2] - dx[2] * dy[3]) / (dx[1] * dy[2] - dx[2] * dy[1])) / W;
+  h[5] = ((dx[1] * dy[3] - dx[3] * dy[1]) / (dx[1] * dy[2] - dx[2] * dy[1])) / H;
+  h[0] = (double)(x[1] - x[0]) / W + h[2] * x[1];
+  h[3] = (double)(x[3] - x[0]) / H + h[5] * x[3];
+  h[6] = (double)x[0];
+  h[1] = (double)(y[1] - y[0]) / W + h[2] * y[1];
+  h[4] = (double)(y[3] - y[0]) / H + h[5] * y[3];
+  h[7] = (double)y[0];
+  h[8] = 1.0;
+}
+
+void orc_projective_transform(const int16_t* ref, int16_t* aux_out, const double h[9],
+                              int W, int H, int stride, int nss_window)
+{
+  /* IT_GT_GRID_SIZE == 2, IT_GT_Interpolation_Filter == 0 */
+  const int G = 2;
+  int off_x = W / 2 - (W / G / 2);
+  int off_y = H / 2 - (H / G / 2);
+  for (int y = off_y; y < off_y + H / G; y++) {
+    for (int x = off_x; x < off_x + W / G; x++) {
+      double Fx = (h[0] * x + h[3] * y + h[6]) / (h[2] * x + h[5] * y + h[8]);
+      double Fy = (h[1] * x + h[4] * y + h[7]) / (h[2] * x + h[5] * y + h[8]);
+      int Y = (int)Fy - off_y;
+      int X = (int)Fx - off_x;
+      double q = (Fy - off_y - (double)Y);
+      double p = (Fx - off_x - (double)X);
+      if (Y < -nss_window / G) Y = -nss_window / G;
+      if (X < -nss_window / G) X = -nss_window / G;
+      if (Y > nss_window / G + H / G - 1) Y = nss_window / G + H / G - 1;
+      if (X > nss_window / G + W / G - 1) X = nss_window / G + W / G - 1;
+      if (Y + 1 > nss_window / G + H / G - 1) Y = nss_window / G + H / G - 2;
+      if (X + 1 > nss_window / G + W / G - 1) X = nss_window / G + W / G - 2;
+      const int16_t* pa = ref + Y * stride;
+      double aux = (1.0 - q) * ((1.0 - p) * (double)(pa[X]) + p * (double)(pa[X + 1]));
+      pa = ref + (Y + 1) * stride;
+      aux += q * ((1.0 - p) * (double)(pa[X]) + p * (double)(pa[X + 1]));
+      if (aux > 255) aux = 255;     /* hard-coded 8-bit clip, also for 10-bit input (:969-972) */
+      if (aux < 0) aux = 0;
+      aux_out[x - off_x] = (int16_t)(aux + 0.5);
+    }
+    aux_out += W / G;
+  }
+}
+
+void orc_stage_window(const int16_t* src, int src_stride, int16_t* dst, int w, int h, int bit_depth)
+{
+  /* filterCopy(isFirst) then filterCopy(isLast): TComInterpolationFilter.cpp:113-154.
+   * Short arithmetic kept literally; equals clamp(src, 0, 2^bd-1) for src in [-1, 2^bd-1]. */
+  int shift = 14 - bit_depth;                         /* IF_INTERNAL_PREC - bitDepth */
+  int16_t offset = (int16_t)(1 << 13);                /* IF_INTERNAL_OFFS */
+  int16_t offset_last = (int16_t)(offset + (shift ? (1 << (shift - 1)) : 0));
+  int16_t max_val = (int16_t)((1 << bit_depth) - 1);
+  for (int r = 0; r < h; r++) {
+    for (int c = 0; c < w; c++) {
+      int16_t v = (int16_t)(src[c] << shift);
+      v = (int16_t)(v - offset);
+      int16_t t = (int16_t)((v + offset_last) >> shift);
+      if (t < 0) t = 0;
+      if (t > max_val) t = max_val;
+      dst[c] = t;
+    }
+    src += src_stride;
+    dst += w;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 -- TLibEncoder/TEncSearch.cpp:4686-4790 (prologue), 5093-5467 (diamond branch)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_pattern_search_gt(const HopGtJob* job, const int16_t* org_buf, const int16_t* ref_buf,
+                           HopGtResult* out)
+{
+  const int cols = job->cols, rows = job->rows;
+  const int G = 2;                                   /* IT_GT_GRID_SIZE */
+  const int16_t* org = org_buf + job->org_off;
+  const int16_t* ref_y = ref_buf + job->ref_off;
+  const int ref_stride = job->ref_stride;
+  const int win_w = cols * 2, win_h = rows * 2;
+  int16_t* window = (int16_t*)malloc(sizeof(int16_t) * win_w * win_h);   /* m_filteredBlock[0][0] */
+  int16_t* aux = (int16_t*)malloc(sizeof(int16_t) * rows * cols);        /* piAux :4749 */
+  double proj[9];
+  int best_cx[4] = {0, 0, 0, 0}, best_cy[4] = {0, 0, 0, 0};              /* :4776 */
+  int cur_cx[4], cur_cy[4];
+  int best_nx[4], best_ny[4], cur_nx[4], cur_ny[4];
+  const int max_iter = 6;                                                 /* IT_MAX_NSS_Iteration */
+  int nss_window = ((rows < cols) ? rows : cols) >> 1;                    /* :4756 */
+  nss_window *= G;                                                        /* :4758 */
+  int last_step = nss_window >> max_iter;                                 /* :4763 */
+  if (last_step == 0) last_step = 1;
+  uint32_t dist, dist_best = job->threshold;                              /* :4769 */
+  int best_ss_x = 0, best_ss_y = 0;                                       /* :5096-5097 */
+  int best_index = -1;
+  uint32_t n_cand = 0;
+
+  int num_pred = job->num_pred;
+  for (int b = 0; b < 1 + num_pred; b++) {                                /* :5106-5110 */
+    int16_t Hor, Ver;
+    int i_offset;
+    if (b < 1) {
+      if (job->ss_cand.hor == 0 && job->ss_cand.ver == 0) continue;       /* :5116 */
+      Ver = job->ss_cand.ver; Hor = job->ss_cand.hor;
+      i_offset = job->ss_cand.hor - cols / 2 + (job->ss_cand.ver - rows / 2) * ref_stride;   /* :5120 */
+      Ver = (int16_t)(Ver << 2); Hor = (int16_t)(Hor << 2);               /* :5122-5123 */
+    } else {
+      HopMv e = job->amvp[b - 1];
+      if (e.hor == 0 && e.ver == 0) continue;                             /* :5144 */
+      Ver = e.ver; Hor = e.hor;
+      Ver = (int16_t)(Ver >> 2); Hor = (int16_t)(Hor >> 2);               /* :5148-5149 */
+      i_offset = Hor - cols / 2 + (Ver - rows / 2) * ref_stride;          /* :5150 */
+      Ver = (int16_t)(Ver << 2); Hor = (int16_t)(Hor << 2);               /* :5152-5153 */
+    }
+    /* :5161-5165 -> m_filteredBlock[0][0] = clamped copy of the 2W x 2H window */
+    orc_stage_window(ref_y + i_offset, ref_stride, window, win_w, win_h, job->bit_depth);
+    const int16_t* ref_srch = window + (cols / 2) + (rows / 2) * win_w;   /* :5177 */
+
+    int iter = 1;
+    int pass = 0;
+    for (int j0 = nss_window; (j0 > 1) && (iter <= max_iter); j0 /= 2, pass++) {   /* :5181 */
+      iter++;
+      if (j0 == nss_window) {                                             /* :5183-5203 */
+        cur_nx[0] = best_nx[0] = 0;            cur_ny[0] = best_ny[0] = 0;
+        cur_nx[1] = best_nx[1] = cols * G - 1; cur_ny[1] = best_ny[1] = 0;
+        cur_nx[2] = best_nx[2] = cols * G - 1; cur_ny[2] = best_ny[2] = rows * G - 1;
+        cur_nx[3] = best_nx[3] = 0;            cur_ny[3] = best_ny[3] = rows * G - 1;
+      } else {                                                            /* :5204-5214 */
+        for (int k = 0; k < 4; k++) { cur_nx[k] = best_nx[k]; cur_ny[k] = best_ny[k]; }
+      }
+      const int s = j0 / 2;
+      int cand = 0;   /* index among the affine candidates of this pass, in loop order */
+      /* 8 nested loops, each (s, 0, -s), outermost y0 .. innermost x3; per corner only the diamond
+       * points (x==0 || y==0) are visited (:5217-5287) */
+      for (int y0 = s; y0 >= -s; y0 -= s) { cur_cy[0] = cur_ny[0] + y0;
+      for (int x0 = s; x0 >= -s; x0 -= s) { if (!(y0 == 0 || x0 == 0)) continue; cur_cx[0] = cur_nx[0] + x0;
+      for (int y1 = s; y1 >= -s; y1 -= s) { cur_cy[1] = cur_ny[1] + y1;
+      for (int x1 = s; x1 >= -s; x1 -= s) { if (!(y1 == 0 || x1 == 0)) continue; cur_cx[1] = cur_nx[1] + x1;
+      for (int y2 = s; y2 >= -s; y2 -= s) { cur_cy[2] = cur_ny[2] + y2;
+      for (int x2 = s; x2 >= -s; x2 -= s) { if (!(y2 == 0 || x2 == 0)) continue; cur_cx[2] = cur_nx[2] + x2;
+      for (int y3 = s; y3 >= -s; y3 -= s) { cur_cy[3] = cur_ny[3] + y3;
+      for (int x3 = s; x3 >= -s; x3 -= s) { if (!(y3 == 0 || x3 == 0)) continue; cur_cx[3] = cur_nx[3] + x3;
+        if (x0 == x1 && x0 == x2 && x0 == x3 && y0 == y1 && y0 == y2 && y0 == y3) continue;  /* :5289 */
+        orc_calc_param_projective(cur_cx, cur_cy, proj, cols * G, rows * G);                 /* :5316 */
+        if (!(proj[2] == 0.0 && proj[5] == 0.0)) continue;                                   /* :5323 */
+        orc_projective_transform(ref_srch, aux, proj, cols * G, rows * G, win_w, nss_window); /* :5336 */
+        if (job->use_had) dist = orc_hads(org, job->org_stride, aux, cols, cols, rows, job->bit_depth);
+        else dist = orc_sad(org, job->org_stride, aux, cols, cols, rows, 0, job->bit_depth);  /* :5344 */
+        dist += orc_get_cost_xy(&job->cost, Hor, Ver);                                       /* :5345 */
+        dist += orc_get_cost_bits(&job->cost, orc_get_bits_gt(                               /* :5346-5358 */
+            cur_cx[0] / last_step, cur_cy[0] / last_step,
+            (cur_cx[1] - cols * G + 1) / last_step, cur_cy[1] / last_step,
+            (cur_cx[2] - cols * G + 1) / last_step, (cur_cy[2] - rows * G + 1) / last_step));
+        n_cand++;
+        if (dist < dist_best) {                                                              /* :5361-5384 */
+          dist_best = dist;
+          for (int k = 0; k < 4; k++) {
+            best_cx[k] = cur_cx[k]; best_cy[k] = cur_cy[k];
+            best_nx[k] = cur_cx[k]; best_ny[k] = cur_cy[k];
+          }
+          best_ss_x = Hor; best_ss_y = Ver;
+          best_index = (b * 8 + pass) * 64 + cand;
+        }
+        cand++;
+      }}}}}}}}
+    }
+  }
+  free(window); free(aux);
+
+  memset(out, 0, sizeof(*out));
+  out->n_candidates = n_cand;
+  out->best_index = -1;
+  out->cost = job->threshold;
+  int any = 0;
+  for (int k = 0; k < 4; k++) any |= (best_cx[k] != 0) | (best_cy[k] != 0);
+  if (any) {                                                                                 /* :5436-5459 */
+    out->gt_flag = 1;
+    out->gt[0].hor = (int16_t)(best_cx[0] / last_step);                 out->gt[0].ver = (int16_t)(best_cy[0] / last_step);
+    out->gt[1].hor = (int16_t)((best_cx[1] - cols * G + 1) / last_step); out->gt[1].ver = (int16_t)(best_cy[1] / last_step);
+    out->gt[2].hor = (int16_t)((best_cx[2] - cols * G + 1) / last_step); out->gt[2].ver = (int16_t)((best_cy[2] - rows * G + 1) / last_step);
+    out->gt[3].hor = (int16_t)(best_cx[3] / last_step);                 out->gt[3].ver = (int16_t)((best_cy[3] - rows * G + 1) / last_step);
+    out->cost = dist_best;
+    out->mv_int.hor = (int16_t)(best_ss_x >> 2);
+    out->mv_int.ver = (int16_t)(best_ss_y >> 2);
+    out->best_index = best_index;
+  }
+}
+
+void orc_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* org, const int16_t* ref,
+                              HopSearchResult* out)
+{
+  for (int i = 0; i < n; i++) orc_pattern_search(&jobs[i], org, ref, &out[i]);
+}
+
+void orc_pattern_search_gt_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref,
+                                 HopGtResult* out)
+{
+  for (int i = 0; i < n; i++) orc_pattern_search_gt(&jobs[i], org, ref, &out[i]);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K4 -- TLibCommon/TComPicYuv.cpp:247-274 (xExtendPicCompBorder, luma)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_extend_border(int16_t* origin, int stride, int pic_w, int pic_h, int margin)
+{
+  int16_t* pi = origin;
+  for (int y = 0; y < pic_h; y++) {
+    for (int x = 0; x < margin; x++) {
+      pi[-margin + x] = pi[0];
+      pi[pic_w + x] = pi[pic_w - 1];
+    }
+    pi += stride;
+  }
+  pi -= (stride + margin);
+  for (int y = 0; y < margin; y++) memcpy(pi + (y + 1) * stride, pi, sizeof(int16_t) * (pic_w + (margin << 1)));
+  pi -= ((pic_h - 1) * stride);
+  for (int y = 0; y < margin; y++) memcpy(pi - (y + 1) * stride, pi, sizeof(int16_t) * (pic_w + (margin << 1)));
+}

@@ -1,0 +1,190 @@
+/*
+ * ref_harness.cpp -- C entry points into the UNMODIFIED reference (TEST INFRASTRUCTURE ONLY).
+ *
+ * Linked against the reference's own objects (compiled by oracle/Makefile straight from
+ * /root/reference/source with the reference's flags) into oracle/_ref/libhopref.so.  It subclasses
+ * TEncSearch so that the protected members xPatternSearch / xPatternSearchGT
+ * (TLibEncoder/TEncSearch.h:471-517) can be driven with synthetic inputs, and exposes the DistFunc
+ * table of TComRdCost and TComPicYuv::extendPicBorder.  Nothing of the reference is re-implemented
+ * here: every result below is computed by reference code.
+ *
+ * Used (a) to pin oracle/hop_oracle.c and to generate tests/golden/, (b) as the "reference" CPU
+ * baseline of bench.py.  The job/result structs are those of include/hop_gpu.h.
+ */
+#include "TLibEncoder/TEncSearch.h"
+#include "TLibEncoder/TEncCfg.h"
+#include "TLibCommon/TComRdCost.h"
+#include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/TComPattern.h"
+#include "TLibCommon/TComPicYuv.h"
+#include "TLibCommon/TComRom.h"
+
+#include "../include/hop_gpu.h"
+#include <string.h>
+
+namespace {
+
+class RefSearch : public TEncSearch
+{
+public:
+  TEncCfg     cfg;
+  TComRdCost  rd;
+  TComDataCU  cu;      // only getCUMvField(REF_PIC_LIST_0)->getAMVPInfo() is read (TEncSearch.cpp:5100)
+  TComPattern pattern;
+
+  RefSearch()
+  {
+    m_pcEncCfg = &cfg;
+    m_pcRdCost = &rd;
+    rd.init();                  // TComRdCost.cpp:177-233, fills m_afpDistortFunc
+    initTempBuff();             // TComPrediction.cpp:81, allocates m_filteredBlock*
+    m_cDistParam.bApplyWeight = false;   // what setWpScalingDistParam leaves for SS slices
+  }
+
+  void setCost(const HopCostState& cs)
+  {
+    // getMotionCost(1,0) copies m_uiLambdaMotionSAD to m_uiCost; setLambda derives it from a double.
+    // m_uiLambdaMotionSAD is private, so drive it through the public pair with an exact inverse:
+    // floor(65536*sqrt(l)) must equal lambda_cost -> search the double that does.
+    double s = ((double)cs.lambda_cost + 0.5) / 65536.0;
+    rd.setLambda(s * s);
+    rd.getMotionCost(true, 0);
+    TComMv pred(cs.pred.hor, cs.pred.ver);
+    rd.setPredictor(pred);
+    rd.setCostScale(cs.cost_scale);
+  }
+
+  void patternSearch(const HopSearchJob* j, const int16_t* org, const int16_t* ref, HopSearchResult* out)
+  {
+    g_bitDepthY = j->bit_depth;
+    cfg.setUseFastEnc(j->fast_enc != 0);
+    setCost(j->cost);
+    pattern.initPattern((Pel*)org + j->org_off, NULL, NULL, j->cols, j->rows, j->org_stride, 0, 0);
+    TComMv lt(j->rng_left, j->rng_top), rb(j->rng_right, j->rng_bottom);
+    TComMv mv(0x7fff, 0x7fff);
+    TComMv ssBest[1]; ssBest[0].set(0x7fff, 0x7fff);
+    UInt sad = 0;
+    xPatternSearch(&pattern, (Pel*)ref + j->ref_off, j->ref_stride, &lt, &rb, mv, sad,
+                   j->offset_x, j->offset_y, ssBest, j->is_ss != 0);
+    memset(out, 0, sizeof(*out));
+    out->sad = sad;
+    if (sad == MAX_UINT && mv.getHor() == 0x7fff) { out->found = 0; out->cost = MAX_UINT; return; }
+    out->found = 1;
+    out->mv.hor = mv.getHor(); out->mv.ver = mv.getVer();
+    out->cost = sad + rd.getCost(mv.getHor(), mv.getVer());
+    // ssBestCand[0] must equal rcMv (IT_SS_NUMBER_OF_BEST_CAND 1); flag a mismatch loudly
+    if (ssBest[0].getHor() != mv.getHor() || ssBest[0].getVer() != mv.getVer()) out->found = -1;
+  }
+
+  void patternSearchGT(const HopGtJob* j, const int16_t* org, const int16_t* ref, HopGtResult* out)
+  {
+    g_bitDepthY = j->bit_depth;
+    cfg.setUseHADME(j->use_had != 0);
+    setCost(j->cost);
+    pattern.initPattern((Pel*)org + j->org_off, NULL, NULL, j->cols, j->rows, j->org_stride, 0, 0);
+    AMVPInfo* amvp = cu.getCUMvField(REF_PIC_LIST_0)->getAMVPInfo();
+    amvp->iN = j->num_pred;
+    for (int i = 0; i < HOP_MAX_PRED; i++) amvp->m_acMvCand[i].set(j->amvp[i].hor, j->amvp[i].ver);
+    TComMv ssBest[1]; ssBest[0].set(j->ss_cand.hor, j->ss_cand.ver);
+    // pcMvInt / half / quarter only feed the prologue's scratch interpolation in the diamond branch
+    TComMv mvInt(j->ss_cand.hor, j->ss_cand.ver), mvHalf(0, 0), mvQter(0, 0);
+    TComMv gt0, gt1, gt2, gt3;
+    Bool gtFlag = false;
+    UInt cost = j->threshold;
+    xPatternSearchGT(&cu, &pattern, (Pel*)ref + j->ref_off, j->ref_stride, &mvInt, &mvHalf, &mvQter,
+                     &gt0, &gt1, &gt2, &gt3, gtFlag, cost, false, ssBest);
+    memset(out, 0, sizeof(*out));
+    out->gt_flag = gtFlag ? 1 : 0;
+    out->gt[0].hor = gt0.getHor(); out->gt[0].ver = gt0.getVer();
+    out->gt[1].hor = gt1.getHor(); out->gt[1].ver = gt1.getVer();
+    out->gt[2].hor = gt2.getHor(); out->gt[2].ver = gt2.getVer();
+    out->gt[3].hor = gt3.getHor(); out->gt[3].ver = gt3.getVer();
+    out->cost = cost;
+    if (gtFlag) { out->mv_int.hor = mvInt.getHor(); out->mv_int.ver = mvInt.getVer(); }
+    out->best_index = -2;      // not observable from outside the reference
+    out->n_candidates = 0;
+  }
+
+  // protected members of TComPrediction (TComPrediction.h:106,110), re-exported
+  void calcParam(Int* x, Int* y, Double* h, Int w, Int hh) { calcParamProjective(x, y, h, w, hh); }
+  void warp(Pel* r, Pel* aux, Double* h, Int W, Int H, Int stride, Int nss) { ProjectiveTransform(r, aux, h, W, H, stride, nss); }
+
+  uint32_t dist(const HopDistJob* j, const int16_t* org, const int16_t* cur)
+  {
+    DistParam dp;
+    pattern.initPattern((Pel*)org + j->org_off, NULL, NULL, j->cols, j->rows, j->org_stride, 0, 0);
+    if (j->func == HOP_DF_HADS)
+      rd.setDistParam(&pattern, (Pel*)cur + j->cur_off, j->cur_stride, 1, dp, true);   // TComRdCost.cpp:332
+    else
+      rd.setDistParam(&pattern, (Pel*)cur + j->cur_off, j->cur_stride, dp);            // TComRdCost.cpp:298
+    dp.iSubShift = (j->func == HOP_DF_HADS) ? 0 : j->sub_shift;
+    dp.bitDepth = j->bit_depth;
+    dp.bApplyWeight = false;
+    dp.uiComp = 0;
+    return dp.DistFunc(&dp);
+  }
+};
+
+RefSearch* g_ref = NULL;
+RefSearch* ref()
+{
+  if (!g_ref) {
+    g_uiMaxCUWidth = 64; g_uiMaxCUHeight = 64; g_uiMaxCUDepth = 4; g_uiAddCUDepth = 1;
+    g_bitDepthY = 8; g_bitDepthC = 8;
+    initROM();
+    g_ref = new RefSearch();
+  }
+  return g_ref;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ref_pattern_search(const HopSearchJob* job, const int16_t* org, const int16_t* refbuf, HopSearchResult* out)
+{ ref()->patternSearch(job, org, refbuf, out); }
+
+void ref_pattern_search_gt(const HopGtJob* job, const int16_t* org, const int16_t* refbuf, HopGtResult* out)
+{ ref()->patternSearchGT(job, org, refbuf, out); }
+
+uint32_t ref_dist(const HopDistJob* job, const int16_t* org, const int16_t* cur)
+{ return ref()->dist(job, org, cur); }
+
+void ref_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* org, const int16_t* refbuf, HopSearchResult* out)
+{ for (int i = 0; i < n; i++) ref()->patternSearch(&jobs[i], org, refbuf, &out[i]); }
+
+void ref_pattern_search_gt_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* refbuf, HopGtResult* out)
+{ for (int i = 0; i < n; i++) ref()->patternSearchGT(&jobs[i], org, refbuf, &out[i]); }
+
+/* TComRdCost::xGetComponentBits is private; getBitsGT (public, TComRdCost.h:204) exposes it. */
+uint32_t ref_bits_gt(int x0, int y0, int x1, int y1, int x2, int y2)
+{ return ref()->rd.getBitsGT(x0, y0, x1, y1, x2, y2, 0, 0); }
+
+uint32_t ref_get_cost_xy(const HopCostState* cs, int x, int y)
+{ ref()->setCost(*cs); return ref()->rd.getCost(x, y); }
+
+/* TComPrediction::calcParamProjective / ProjectiveTransform are public members of TComPrediction */
+void ref_calc_param_projective(const int32_t x[4], const int32_t y[4], double h[9], int width, int height)
+{ ref()->calcParam((Int*)x, (Int*)y, h, width, height); }
+
+void ref_projective_transform(const int16_t* refsrch, int16_t* aux, const double h[9], int W, int H, int stride, int nss_window)
+{ ref()->warp((Pel*)refsrch, aux, (Double*)h, W, H, stride, nss_window); }
+
+/* TComPicYuv::extendPicBorder on a luma plane: `plane` is (pic_h+2m) x (pic_w+2m) incl. margins (in/out) */
+int ref_extend_border(int16_t* plane, int pic_w, int pic_h)
+{
+  ref();
+  TComPicYuv pic;
+  pic.create(pic_w, pic_h, 64, 64, 4);
+  int m = pic.getLumaMargin();
+  int stride = pic.getStride();
+  size_t n = (size_t)stride * (pic_h + 2 * m);
+  memcpy(pic.getBufY(), plane, n * sizeof(int16_t));
+  pic.setBorderExtension(false);
+  pic.extendPicBorder();
+  memcpy(plane, pic.getBufY(), n * sizeof(int16_t));
+  pic.destroy();
+  return m;
+}
+
+}  // extern "C"
