@@ -125,7 +125,7 @@ ABI = [
     ("hop_pattern_search_gt_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_dist_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
-    ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     ("hop_dist_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_ctx_launch_count", C.c_uint64, [_P]),
     ("hop_probe_alu", C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -243,8 +243,9 @@ class HopContext:
     def pattern_search_dev(self, n, d_jobs, d_org, d_ref, d_out, stream=None):
         self._check(self.lib.hop_pattern_search_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out, stream))
 
-    def pattern_search_gt_dev(self, n, d_jobs, d_org, d_ref, d_out, stream=None):
-        self._check(self.lib.hop_pattern_search_gt_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out, stream))
+    def pattern_search_gt_dev(self, n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream=None):
+        self._check(self.lib.hop_pattern_search_gt_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out,
+                                                             max_cols, max_rows, stream))
 
     def dist_dev(self, n, d_jobs, d_org, d_cur, d_out, stream=None):
         self._check(self.lib.hop_dist_batch_dev(self.h, n, d_jobs, d_org, d_cur, d_out, stream))

@@ -1,0 +1,410 @@
+// hop_api.cu -- the C ABI of libhopgpu (include/hop_gpu.h): contexts, scratch management, the host
+// (copy-in / run / copy-out) and device (HBM-resident) entry points, the SS reference mirror and the
+// ALU probes.  No CPU fallback exists anywhere in this file: every path ends in a kernel launch or in
+// an error status.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hop_internal.h"
+
+using namespace hop;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int status, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(HOP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+struct Scratch {
+  void*  p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct HopCtx {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  int          sm_count = 0;
+  uint64_t     launches = 0;
+  Scratch      jobs, org, ref, out, keys, sink;
+  // SS reference mirror
+  int16_t*     plane = nullptr;
+  int          pic_w = 0, pic_h = 0, margin = 0, stride = 0;
+  bool         plane_valid = false;
+};
+
+namespace {
+
+int ensure(HopCtx* ctx, Scratch& s, size_t bytes)
+{
+  if (bytes <= s.cap) return HOP_OK;
+  if (s.p) CU(cudaFree(s.p));
+  s.p = nullptr; s.cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMalloc(&s.p, cap);
+  if (e != cudaSuccess) return fail(HOP_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+  s.cap = cap;
+  (void)ctx;
+  return HOP_OK;
+}
+
+int bind(HopCtx* ctx)
+{
+  if (!ctx) return fail(HOP_ERR_ARG, "NULL context");
+  CU(cudaSetDevice(ctx->device));
+  return HOP_OK;
+}
+
+int shape_ok(int cols, int rows)
+{
+  auto ok = [](int v) { return v == 4 || v == 8 || v == 12 || v == 16 || v == 24 || v == 32 || v == 48 || v == 64; };
+  return ok(cols) && ok(rows) && !(cols == 4 && rows == 4);
+}
+
+bool g_table_ready[64] = {false};
+
+}  // namespace
+
+extern "C" {
+
+int hop_abi_version(void) { return HOP_ABI_VERSION; }
+const char* hop_last_error(void) { return g_err; }
+
+int hop_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(HOP_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int hop_shape_supported(int cols, int rows) { return shape_ok(cols, rows); }
+
+int hop_ctx_create(int device, HopCtx** out)
+{
+  if (!out) return fail(HOP_ERR_ARG, "out == NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(HOP_ERR_CUDA, "no CUDA device (%s); libhopgpu has no CPU fallback",
+                e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(HOP_ERR_ARG, "device %d out of range (%d devices)", device, n);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(HOP_ERR_CUDA, "device %d is sm_%d%d; libhopgpu carries sm_100a code only", device, prop.major, prop.minor);
+  HopCtx* ctx = new (std::nothrow) HopCtx();
+  if (!ctx) return fail(HOP_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete ctx; return fail(HOP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  if (device < 64 && !g_table_ready[device]) {
+    int8_t table[GT_CANDS][8];
+    int count = 0;
+    gt_build_offset_table(table, &count);
+    if (count != GT_CANDS) { delete ctx; return fail(HOP_ERR_STATE, "GT offset table has %d entries, expected %d", count, GT_CANDS); }
+    e = gt_upload_offset_table(table);
+    if (e != cudaSuccess) { delete ctx; return fail(HOP_ERR_CUDA, "offset table upload: %s", cudaGetErrorString(e)); }
+    g_table_ready[device] = true;
+  }
+  *out = ctx;
+  return HOP_OK;
+}
+
+void hop_ctx_destroy(HopCtx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->sink};
+  for (Scratch* s : all) if (s->p) cudaFree(s->p);
+  if (ctx->plane) cudaFree(ctx->plane);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int hop_ctx_sync(HopCtx* ctx)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+void* hop_ctx_stream(HopCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t hop_ctx_launch_count(HopCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// SS reference mirror (K4)
+// ---------------------------------------------------------------------------------------------
+int hop_ref_create(HopCtx* ctx, int pic_w, int pic_h, int margin)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (pic_w <= 0 || pic_h <= 0 || margin < 0) return fail(HOP_ERR_ARG, "bad picture geometry %dx%d margin %d", pic_w, pic_h, margin);
+  if (ctx->plane) { CU(cudaFree(ctx->plane)); ctx->plane = nullptr; }
+  ctx->pic_w = pic_w; ctx->pic_h = pic_h; ctx->margin = margin; ctx->stride = pic_w + 2 * margin;
+  size_t samples = (size_t)ctx->stride * (pic_h + 2 * margin);
+  cudaError_t e = cudaMalloc((void**)&ctx->plane, samples * sizeof(int16_t));
+  if (e != cudaSuccess) return fail(HOP_ERR_NOMEM, "cudaMalloc(plane %zu samples): %s", samples, cudaGetErrorString(e));
+  ctx->plane_valid = false;
+  return HOP_OK;
+}
+
+int hop_ref_reset(HopCtx* ctx, int value)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (!ctx->plane) return fail(HOP_ERR_STATE, "hop_ref_reset before hop_ref_create");
+  size_t samples = (size_t)ctx->stride * (ctx->pic_h + 2 * ctx->margin);
+  int l = 0;
+  CU(ref_fill_launch(ctx->plane, samples, value, ctx->stream, &l));
+  ctx->launches += l;
+  ctx->plane_valid = true;
+  return HOP_OK;
+}
+
+int hop_ref_update(HopCtx* ctx, int x, int y, int w, int h, const int16_t* src, int src_stride)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "hop_ref_update before hop_ref_create/hop_ref_reset");
+  if (!src || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > ctx->pic_w || y + h > ctx->pic_h || src_stride < w)
+    return fail(HOP_ERR_ARG, "block (%d,%d %dx%d) outside the %dx%d picture", x, y, w, h, ctx->pic_w, ctx->pic_h);
+  int16_t* origin = ctx->plane + (size_t)ctx->margin * ctx->stride + ctx->margin;
+  // pageable source: the copy is staged by the runtime before the call returns, so `src` is not retained
+  CU(cudaMemcpy2DAsync(origin + (size_t)y * ctx->stride + x, ctx->stride * sizeof(int16_t), src,
+                       src_stride * sizeof(int16_t), w * sizeof(int16_t), h, cudaMemcpyHostToDevice, ctx->stream));
+  int l = 0;
+  CU(ref_extend_launch(origin, ctx->stride, ctx->pic_w, ctx->pic_h, ctx->margin, x, y, w, h, ctx->stream, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+int hop_ref_download(HopCtx* ctx, int16_t* dst, size_t dst_samples)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (!ctx->plane) return fail(HOP_ERR_STATE, "no reference plane");
+  size_t samples = (size_t)ctx->stride * (ctx->pic_h + 2 * ctx->margin);
+  if (!dst || dst_samples < samples) return fail(HOP_ERR_ARG, "destination too small (%zu < %zu)", dst_samples, samples);
+  CU(cudaMemcpyAsync(dst, ctx->plane, samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+int hop_ref_stride(HopCtx* ctx) { return ctx ? ctx->stride : 0; }
+
+const int16_t* hop_ref_origin_dev(HopCtx* ctx)
+{
+  if (!ctx || !ctx->plane) return nullptr;
+  return ctx->plane + (size_t)ctx->margin * ctx->stride + ctx->margin;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device entry points
+// ---------------------------------------------------------------------------------------------
+int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org,
+                                 const int16_t* d_ref, HopSearchResult* d_out, void* stream)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!d_jobs || !d_org || !d_ref || !d_out))) return fail(HOP_ERR_ARG, "NULL device buffer");
+  if (n == 0) return HOP_OK;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  st = ensure(ctx, ctx->keys, sizeof(unsigned long long) * (size_t)n);
+  if (st) return st;
+  // enough CTAs to cover the machine a few times: a single in-encoder call spreads one PU's window
+  // over many SMs, a large batch needs no extra split
+  int slices = (4 * ctx->sm_count + n - 1) / n;
+  int l = 0;
+  CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, slices, s, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org,
+                                    const int16_t* d_ref, HopGtResult* d_out, int max_cols, int max_rows,
+                                    void* stream)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!d_jobs || !d_org || !d_ref || !d_out))) return fail(HOP_ERR_ARG, "NULL device buffer");
+  if (max_cols < 4 || max_cols > HOP_MAX_PU || max_rows < 4 || max_rows > HOP_MAX_PU)
+    return fail(HOP_ERR_ARG, "shape bound %dx%d out of range", max_cols, max_rows);
+  if (n == 0) return HOP_OK;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int l = 0;
+  CU(gt_launch(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, s, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs, const int16_t* d_org,
+                       const int16_t* d_cur, uint32_t* d_out, void* stream)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!d_jobs || !d_org || !d_cur || !d_out))) return fail(HOP_ERR_ARG, "NULL device buffer");
+  if (n == 0) return HOP_OK;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int l = 0;
+  CU(dist_launch(n, d_jobs, d_org, d_cur, d_out, s, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host entry points: copy in, run, copy out
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// upload jobs + org (+ ref unless the mirror is used); returns the device pointers
+int stage_inputs(HopCtx* ctx, int n, const void* jobs, size_t job_size, const int16_t* org, size_t org_samples,
+                 const int16_t* ref, size_t ref_samples, size_t out_bytes, const int16_t** d_ref_out)
+{
+  int st;
+  if ((st = ensure(ctx, ctx->jobs, job_size * (size_t)n))) return st;
+  if ((st = ensure(ctx, ctx->org, org_samples * sizeof(int16_t)))) return st;
+  if ((st = ensure(ctx, ctx->out, out_bytes))) return st;
+  CU(cudaMemcpyAsync(ctx->jobs.p, jobs, job_size * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->org.p, org, org_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (ref) {
+    if ((st = ensure(ctx, ctx->ref, ref_samples * sizeof(int16_t)))) return st;
+    CU(cudaMemcpyAsync(ctx->ref.p, ref, ref_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    *d_ref_out = (const int16_t*)ctx->ref.p;
+  } else {
+    if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
+    *d_ref_out = hop_ref_origin_dev(ctx);
+  }
+  return HOP_OK;
+}
+
+}  // namespace
+
+int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs, const int16_t* org, size_t org_samples,
+                             const int16_t* ref, size_t ref_samples, HopSearchResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  for (int i = 0; i < n; i++) {
+    const HopSearchJob& j = jobs[i];
+    if (j.cols < 1 || j.cols > HOP_MAX_PU || j.rows < 1 || j.rows > HOP_MAX_PU || j.bit_depth < 8 || j.bit_depth > 14)
+      return fail(HOP_ERR_ARG, "job %d: unsupported block %dx%d / bit depth %d", i, j.cols, j.rows, j.bit_depth);
+  }
+  const int16_t* d_ref = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopSearchJob), org, org_samples, ref, ref_samples,
+                    sizeof(HopSearchResult) * (size_t)n, &d_ref);
+  if (st) return st;
+  st = hop_pattern_search_batch_dev(ctx, n, (const HopSearchJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref,
+                                    (HopSearchResult*)ctx->out.p, ctx->stream);
+  if (st) return st;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopSearchResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* org, size_t org_samples,
+                                const int16_t* ref, size_t ref_samples, HopGtResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  int max_cols = 4, max_rows = 4;
+  for (int i = 0; i < n; i++) {
+    const HopGtJob& j = jobs[i];
+    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 14 || j.num_pred < 0 || j.num_pred > HOP_MAX_PRED)
+      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / num_pred %d", i, j.cols, j.rows, j.bit_depth, j.num_pred);
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+  }
+  const int16_t* d_ref = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,
+                    sizeof(HopGtResult) * (size_t)n, &d_ref);
+  if (st) return st;
+  st = hop_pattern_search_gt_batch_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref,
+                                       (HopGtResult*)ctx->out.p, max_cols, max_rows, ctx->stream);
+  if (st) return st;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopGtResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs, const int16_t* org, size_t org_samples,
+                   const int16_t* cur, size_t cur_samples, uint32_t* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !cur || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  for (int i = 0; i < n; i++) {
+    const HopDistJob& j = jobs[i];
+    if (j.cols < 1 || j.rows < 1 || (j.func != HOP_DF_SAD && j.func != HOP_DF_HADS) || j.bit_depth < 8 || j.sub_shift < 0 || j.sub_shift > 3)
+      return fail(HOP_ERR_ARG, "job %d: bad distortion job", i);
+  }
+  const int16_t* d_cur = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopDistJob), org, org_samples, cur, cur_samples, sizeof(uint32_t) * (size_t)n, &d_cur);
+  if (st) return st;
+  st = hop_dist_batch_dev(ctx, n, (const HopDistJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_cur,
+                          (uint32_t*)ctx->out.p, ctx->stream);
+  if (st) return st;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ALU probes
+// ---------------------------------------------------------------------------------------------
+int hop_probe_alu(HopCtx* ctx, int what, double* gops_out, double* ms_out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (what < 0 || what > 5 || !gops_out) return fail(HOP_ERR_ARG, "bad probe id %d", what);
+  if ((st = ensure(ctx, ctx->sink, 64))) return st;
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+  double per = 0;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(probe_launch(what, blocks, threads, iters / 16, (unsigned*)ctx->sink.p, ctx->stream, &per));   // warm-up
+  CU(cudaEventRecord(e0, ctx->stream));
+  CU(probe_launch(what, blocks, threads, iters, (unsigned*)ctx->sink.p, ctx->stream, &per));
+  CU(cudaEventRecord(e1, ctx->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->launches += 2;
+  const double ops = (double)blocks * threads * (double)iters * per;
+  *gops_out = ops / (ms * 1e-3) / 1e9;
+  if (ms_out) *ms_out = ms;
+  return HOP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,34 @@
+// hop_internal.h -- declarations shared by the translation units of libhopgpu (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/hop_gpu.h"
+
+namespace hop {
+
+constexpr int GT_CANDS   = 56;    // affine corner sets per diamond pass
+constexpr int GT_THREADS = 128;   // K2 CTA size upper bound
+constexpr int K1_THREADS = 256;
+constexpr int K1_MAX_SLICES = 32; // CTAs cooperating on one PU's search window
+
+// K2
+void        gt_build_offset_table(int8_t table[GT_CANDS][8], int* count);
+cudaError_t gt_upload_offset_table(const int8_t table[GT_CANDS][8]);
+cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);
+// K1
+cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                          HopSearchResult* d_out, unsigned long long* d_keys, int slices,
+                          cudaStream_t stream, int* launches);
+// K3
+cudaError_t dist_launch(int n, const HopDistJob* d_jobs, const int16_t* d_org, const int16_t* d_cur,
+                        uint32_t* d_out, cudaStream_t stream, int* launches);
+// K4
+cudaError_t ref_fill_launch(int16_t* d_plane, size_t samples, int value, cudaStream_t stream, int* launches);
+cudaError_t ref_extend_launch(int16_t* d_origin, int stride, int pic_w, int pic_h, int margin,
+                              int x, int y, int w, int h, cudaStream_t stream, int* launches);
+// probes
+cudaError_t probe_launch(int what, int blocks, int threads, int iters, unsigned* d_sink,
+                         cudaStream_t stream, double* lane_ops_per_thread_iter);
+
+}  // namespace hop

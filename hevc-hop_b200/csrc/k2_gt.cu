@@ -1,0 +1,419 @@
+// k2_gt.cu -- K2: the HOP / geometric-transform candidate search (sm_100a).
+//
+// Replaces TEncSearch::xPatternSearchGT, diamond branch (TLibEncoder/TEncSearch.cpp:4686-4790,
+// 5093-5467) together with calcParamProjective / ProjectiveTransform
+// (TLibCommon/TComPrediction.cpp:807-832, 904-1030), xGetHADs / xCalcHADs4x4/8x8 and the SAD family
+// (TLibCommon/TComRdCost.cpp:513-1010, 1366-1708) and the bit-cost helpers.
+//
+// Parallel restatement:
+//   * one CTA per PU job; start vectors and diamond passes are walked sequentially inside the kernel
+//     (they are data dependent), the 56 affine corner sets of a pass are evaluated in parallel;
+//   * the 620 corner sets of a pass reduce to a fixed table of 56 offset patterns (in reference loop
+//     order) because the pass centres always form a parallelogram; every candidate is still put
+//     through the reference's own double-precision affine test;
+//   * a task = (candidate, HAD tile): one thread warps an 8x8 (or 4x4) tile into registers with the
+//     reference's IEEE binary64 operation sequence (no FMA contraction, __d*_rn intrinsics), takes the
+//     difference to the original block, runs the 2-D Walsh-Hadamard butterflies in registers and adds
+//     the rounded tile SATD to the candidate's accumulator in shared memory;
+//   * ordered argmin: candidates are scanned in loop order with strict '<' against the running best,
+//     which carries across passes and start vectors exactly as uiDistBest does.
+#include "hop_common.cuh"
+#include "hop_internal.h"
+
+namespace hop {
+
+__constant__ int8_t c_gt_offsets[GT_CANDS][8];   // x0,y0,x1,y1,x2,y2,x3,y3 in {-1,0,1}, loop order
+
+void gt_build_offset_table(int8_t table[GT_CANDS][8], int* count)
+{
+  // the 8 nested loops of TEncSearch.cpp:5217-5287, each running (s, 0, -s); diamond points only;
+  // translations skipped (:5289); affine <=> o0 - o1 + o2 - o3 == 0 (centres are parallelograms).
+  int n = 0;
+  const int v[3] = {1, 0, -1};
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { int y0 = v[a], x0 = v[b]; if (y0 && x0) continue;
+  for (int c = 0; c < 3; c++) for (int d = 0; d < 3; d++) { int y1 = v[c], x1 = v[d]; if (y1 && x1) continue;
+  for (int e = 0; e < 3; e++) for (int f = 0; f < 3; f++) { int y2 = v[e], x2 = v[f]; if (y2 && x2) continue;
+  for (int g = 0; g < 3; g++) for (int h = 0; h < 3; h++) { int y3 = v[g], x3 = v[h]; if (y3 && x3) continue;
+    if (x0 == x1 && x0 == x2 && x0 == x3 && y0 == y1 && y0 == y2 && y0 == y3) continue;
+    if (x0 - x1 + x2 - x3 != 0 || y0 - y1 + y2 - y3 != 0) continue;
+    if (n < GT_CANDS) {
+      int8_t* t = table[n];
+      t[0] = x0; t[1] = y0; t[2] = x1; t[3] = y1; t[4] = x2; t[5] = y2; t[6] = x3; t[7] = y3;
+    }
+    n++;
+  }}}}
+  *count = n;
+}
+
+cudaError_t gt_upload_offset_table(const int8_t table[GT_CANDS][8])
+{
+  return cudaMemcpyToSymbol(c_gt_offsets, table, sizeof(int8_t) * GT_CANDS * 8);
+}
+
+struct GtShared {
+  // per-pass candidate table (SoA, loop order)
+  double   h0[GT_CANDS], h3[GT_CANDS], h6[GT_CANDS];   // Fx = h0*x + h3*y + h6
+  double   h1[GT_CANDS], h4[GT_CANDS], h7[GT_CANDS];   // Fy = h1*x + h4*y + h7
+  uint32_t add_cost[GT_CANDS];                         // getCost(Hor,Ver) + getCost(getBitsGT(..))
+  uint32_t dist[GT_CANDS];                             // sum of tile SATDs / SADs
+  int32_t  valid[GT_CANDS];
+  int16_t  corner[GT_CANDS][8];
+  // search state
+  int32_t  centre[8];        // iBestNSSCenterX/Y[4] interleaved x,y
+  int32_t  best_corner[8];   // iBestCornerX/Y[4]
+  uint32_t dist_best;
+  int32_t  best_ss_x, best_ss_y;
+  int32_t  best_index;
+  uint32_t n_cand;
+};
+
+// ---- in-register Walsh-Hadamard tiles ---------------------------------------------------------
+template <int N> struct Tile;
+
+template <> struct Tile<8> {
+  int d[64];
+  __device__ __forceinline__ void row_transform(int r)
+  {
+    int* p = d + r * 8;
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) { int a = p[j], b = p[j + len]; p[j] = a + b; p[j + len] = a - b; }
+  }
+  __device__ __forceinline__ uint32_t satd()
+  {
+#pragma unroll
+    for (int x = 0; x < 8; x++)
+#pragma unroll
+      for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+        for (int i = 0; i < 8; i += len << 1)
+#pragma unroll
+          for (int j = i; j < i + len; j++) {
+            int a = d[j * 8 + x], b = d[(j + len) * 8 + x];
+            d[j * 8 + x] = a + b; d[(j + len) * 8 + x] = a - b;
+          }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 64; k++) s += abs(d[k]);
+    return (uint32_t)((s + 2) >> 2);           // xCalcHADs8x8, TComRdCost.cpp:1572
+  }
+  __device__ __forceinline__ uint32_t sad()
+  {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 64; k++) s += abs(d[k]);
+    return (uint32_t)s;
+  }
+};
+
+template <> struct Tile<4> {
+  int d[16];
+  __device__ __forceinline__ void row_transform(int r)
+  {
+    int* p = d + r * 4;
+#pragma unroll
+    for (int len = 1; len < 4; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 4; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) { int a = p[j], b = p[j + len]; p[j] = a + b; p[j + len] = a - b; }
+  }
+  __device__ __forceinline__ uint32_t satd()
+  {
+#pragma unroll
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+      for (int len = 1; len < 4; len <<= 1)
+#pragma unroll
+        for (int i = 0; i < 4; i += len << 1)
+#pragma unroll
+          for (int j = i; j < i + len; j++) {
+            int a = d[j * 4 + x], b = d[(j + len) * 4 + x];
+            d[j * 4 + x] = a + b; d[(j + len) * 4 + x] = a - b;
+          }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += abs(d[k]);
+    return (uint32_t)((s + 1) >> 1);           // xCalcHADs4x4, TComRdCost.cpp:1476
+  }
+  __device__ __forceinline__ uint32_t sad()
+  {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += abs(d[k]);
+    return (uint32_t)s;
+  }
+};
+
+// One warped sample: ProjectiveTransform body for the affine case (h2 == h5 == 0 => denominator is
+// exactly 1.0, so the reference's division returns its numerator unchanged), TComPrediction.cpp:925-972,1025.
+//   win  : clamped window samples, addressed win[(Y + w) * wstride + (X + w)]
+//   lim_x/lim_y : w + cols - 1 / w + rows - 1
+__device__ __forceinline__ int warp_sample(const int16_t* __restrict__ win, int wstride, int w,
+                                           double Fx, double Fy, int off_x, int off_y,
+                                           double off_xd, double off_yd, int lim_x, int lim_y)
+{
+  int Y = (int)Fy - off_y;                       // C truncation toward zero
+  int X = (int)Fx - off_x;
+  double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)Y);
+  double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)X);
+  if (Y < -w) Y = -w;
+  if (X < -w) X = -w;
+  if (Y > lim_y) Y = lim_y;
+  if (X > lim_x) X = lim_x;
+  if (Y + 1 > lim_y) Y = lim_y - 1;
+  if (X + 1 > lim_x) X = lim_x - 1;
+  const int16_t* r0 = win + (Y + w) * wstride + (X + w);
+  const int16_t* r1 = r0 + wstride;
+  double A = (double)r0[0], B = (double)r0[1], C = (double)r1[0], D = (double)r1[1];
+  double omp = __dsub_rn(1.0, p), omq = __dsub_rn(1.0, q);
+  double aux = __dmul_rn(omq, __dadd_rn(__dmul_rn(omp, A), __dmul_rn(p, B)));
+  aux = __dadd_rn(aux, __dmul_rn(q, __dadd_rn(__dmul_rn(omp, C), __dmul_rn(p, D))));
+  if (aux > 255.0) aux = 255.0;                  // hard-coded 8-bit clip (also for 10-bit input)
+  if (aux < 0.0) aux = 0.0;
+  return (int)__dadd_rn(aux, 0.5);               // (Pel)(aux + 0.5)
+}
+
+template <int N, bool HAD>
+__device__ __forceinline__ uint32_t eval_tile(const GtShared& sh, int c, int tx, int ty,
+                                              const int16_t* __restrict__ org, int org_stride,
+                                              const int16_t* __restrict__ win, int wstride, int w,
+                                              int cols, int rows)
+{
+  const int off_x = cols >> 1, off_y = rows >> 1;          // W/2 - W/4 with W = 2*cols
+  const double off_xd = (double)off_x, off_yd = (double)off_y;
+  const int lim_x = w + cols - 1, lim_y = w + rows - 1;
+  const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
+  const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  Tile<N> t;
+#pragma unroll
+  for (int r = 0; r < N; r++) {
+    const double yd = (double)(off_y + ty + r);
+    const double h3y = __dmul_rn(h3, yd), h4y = __dmul_rn(h4, yd);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double xd = (double)(off_x + tx + k);
+      // (h0*x + h3*y) + h6, left to right
+      double Fx = __dadd_rn(__dadd_rn(__dmul_rn(h0, xd), h3y), h6);
+      double Fy = __dadd_rn(__dadd_rn(__dmul_rn(h1, xd), h4y), h7);
+      int v = warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
+      t.d[r * N + k] = (int)org[(ty + r) * org_stride + tx + k] - v;
+    }
+    if (HAD) t.row_transform(r);
+  }
+  return HAD ? t.satd() : t.sad();
+}
+
+// ---- the kernel -------------------------------------------------------------------------------
+// dynamic shared memory: [GtShared][org rows*cols int16][window (cols+2w)*(rows+2w) int16]
+template <int N, bool HAD>
+__device__ __forceinline__ void run_tasks(GtShared& sh, const int16_t* s_org, const int16_t* s_win,
+                                          int wstride, int w, int cols, int rows)
+{
+  const int tiles_x = cols / N, ntiles = tiles_x * (rows / N);
+  const int ntask = ntiles * GT_CANDS;
+  for (int t = threadIdx.x; t < ntask; t += blockDim.x) {
+    const int c = t % GT_CANDS, tile = t / GT_CANDS;
+    if (!sh.valid[c]) continue;
+    const int tx = (tile % tiles_x) * N, ty = (tile / tiles_x) * N;
+    uint32_t v = eval_tile<N, HAD>(sh, c, tx, ty, s_org, cols, s_win, wstride, w, cols, rows);
+    atomicAdd(&sh.dist[c], v);
+  }
+}
+
+__global__ void __launch_bounds__(GT_THREADS)
+k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+             const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  const HopGtJob job = jobs[job_id];
+  const int cols = job.cols, rows = job.rows;
+  const int G = 2;                                              // IT_GT_GRID_SIZE
+  const int nss_window = ((rows < cols ? rows : cols) >> 1) * G;  // TEncSearch.cpp:4756-4758
+  const int w = nss_window / G;                                 // clamp radius inside ProjectiveTransform
+  int last_step = nss_window >> 6;                              // :4763 (IT_MAX_NSS_Iteration 6)
+  if (last_step == 0) last_step = 1;
+  const int win_w = cols + 2 * w, win_h = rows + 2 * w;
+  const int wstride = win_w | 1;                                // odd stride: fewer bank conflicts
+  int16_t* s_org = reinterpret_cast<int16_t*>(smem_raw + sizeof(GtShared));
+  int16_t* s_win = s_org + rows * cols;
+  const int16_t* org = org_buf + job.org_off;
+  const int16_t* ref_y = ref_buf + job.ref_off;
+  const int max_val = (1 << job.bit_depth) - 1;
+  const int dist_shift = job.bit_depth - 8;
+  const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
+
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+    s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 8; k++) sh.best_corner[k] = 0;
+    sh.dist_best = job.threshold;                               // :4769
+    sh.best_ss_x = 0; sh.best_ss_y = 0; sh.best_index = -1; sh.n_cand = 0;
+  }
+
+  const int n_start = 1 + job.num_pred;
+  for (int b = 0; b < n_start; b++) {                           // :5106-5110
+    int Hx, Hy;                                                 // integer-pel start vector
+    if (b == 0) {
+      if (job.ss_cand.hor == 0 && job.ss_cand.ver == 0) continue;   // :5116
+      Hx = job.ss_cand.hor; Hy = job.ss_cand.ver;
+    } else {
+      const HopMv e = job.amvp[b - 1];
+      if (e.hor == 0 && e.ver == 0) continue;                   // :5144
+      Hx = (int16_t)(e.hor >> 2); Hy = (int16_t)(e.ver >> 2);   // :5148-5149
+    }
+    const int Hor = (int16_t)(Hx << 2), Ver = (int16_t)(Hy << 2);   // Short, quarter-pel
+    __syncthreads();   // previous pass done with s_win
+    // window staging: samples [Hx - w, Hx + w + cols) x [Hy - w, Hy + w + rows) relative to the PU,
+    // clamped to [0, 2^bd - 1] (filterCopy first+last, TComInterpolationFilter.cpp:113-154)
+    for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
+      const int wy = i / win_w, wx = i % win_w;
+      int v = ref_y[(Hy - w + wy) * job.ref_stride + (Hx - w + wx)];
+      v = v < 0 ? 0 : (v > max_val ? max_val : v);
+      s_win[wy * wstride + wx] = (int16_t)v;
+    }
+    const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);        // :5345
+
+    int pass = 0;
+    for (int j0 = nss_window; j0 > 1 && pass < 6; j0 /= 2, pass++) {   // :5181
+      const int s = j0 / 2;
+      __syncthreads();
+      if (threadIdx.x < GT_CANDS) {
+        const int c = threadIdx.x;
+        int cx[4], cy[4];
+        if (pass == 0) {                                        // :5183-5203
+          cx[0] = 0; cy[0] = 0; cx[1] = cols * G - 1; cy[1] = 0;
+          cx[2] = cols * G - 1; cy[2] = rows * G - 1; cx[3] = 0; cy[3] = rows * G - 1;
+        } else {                                                // :5204-5214
+#pragma unroll
+          for (int k = 0; k < 4; k++) { cx[k] = sh.centre[2 * k]; cy[k] = sh.centre[2 * k + 1]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          cx[k] += s * c_gt_offsets[c][2 * k];
+          cy[k] += s * c_gt_offsets[c][2 * k + 1];
+        }
+        // calcParamProjective, TComPrediction.cpp:807-832, literally (IEEE binary64, no contraction)
+        const double Wd = __dsub_rn((double)(cols * G), 1.0), Hd = __dsub_rn((double)(rows * G), 1.0);
+        const double dx1 = __dsub_rn((double)cx[1], (double)cx[2]);
+        const double dx2 = __dsub_rn((double)cx[3], (double)cx[2]);
+        const double dx3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cx[0], (double)cx[1]), (double)cx[2]), (double)cx[3]);
+        const double dy1 = __dsub_rn((double)cy[1], (double)cy[2]);
+        const double dy2 = __dsub_rn((double)cy[3], (double)cy[2]);
+        const double dy3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cy[0], (double)cy[1]), (double)cy[2]), (double)cy[3]);
+        const double den = __dsub_rn(__dmul_rn(dx1, dy2), __dmul_rn(dx2, dy1));
+        const double h2 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx3, dy2), __dmul_rn(dx2, dy3)), den), Wd);
+        const double h5 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx1, dy3), __dmul_rn(dx3, dy1)), den), Hd);
+        const int ok = (h2 == 0.0 && h5 == 0.0) ? 1 : 0;        // :5323, NaN (den == 0) fails
+        sh.valid[c] = ok;
+        sh.dist[c] = 0;
+        if (ok) {
+          sh.h0[c] = __dadd_rn(__ddiv_rn((double)(cx[1] - cx[0]), Wd), __dmul_rn(h2, (double)cx[1]));
+          sh.h3[c] = __dadd_rn(__ddiv_rn((double)(cx[3] - cx[0]), Hd), __dmul_rn(h5, (double)cx[3]));
+          sh.h6[c] = (double)cx[0];
+          sh.h1[c] = __dadd_rn(__ddiv_rn((double)(cy[1] - cy[0]), Wd), __dmul_rn(h2, (double)cy[1]));
+          sh.h4[c] = __dadd_rn(__ddiv_rn((double)(cy[3] - cy[0]), Hd), __dmul_rn(h5, (double)cy[3]));
+          sh.h7[c] = (double)cy[0];
+          const uint32_t gb = gt_bits(cx[0] / last_step, cy[0] / last_step,
+                                      (cx[1] - cols * G + 1) / last_step, cy[1] / last_step,
+                                      (cx[2] - cols * G + 1) / last_step, (cy[2] - rows * G + 1) / last_step);
+          sh.add_cost[c] = mv_add + bits_cost(job.cost, gb);    // :5345-5358
+#pragma unroll
+          for (int k = 0; k < 4; k++) { sh.corner[c][2 * k] = (int16_t)cx[k]; sh.corner[c][2 * k + 1] = (int16_t)cy[k]; }
+        }
+      }
+      __syncthreads();
+      if (tile_n == 8) {
+        if (job.use_had) run_tasks<8, true>(sh, s_org, s_win, wstride, w, cols, rows);
+        else             run_tasks<8, false>(sh, s_org, s_win, wstride, w, cols, rows);
+      } else {
+        if (job.use_had) run_tasks<4, true>(sh, s_org, s_win, wstride, w, cols, rows);
+        else             run_tasks<4, false>(sh, s_org, s_win, wstride, w, cols, rows);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        // ordered argmin with the carried threshold: loop order, strict '<' (:5361)
+        uint32_t best = sh.dist_best;
+        int best_c = -1;
+        uint32_t n = 0;
+        for (int c = 0; c < GT_CANDS; c++) {
+          if (!sh.valid[c]) continue;
+          n++;
+          const uint32_t d = (sh.dist[c] >> dist_shift) + sh.add_cost[c];
+          if (d < best) { best = d; best_c = c; }
+        }
+        sh.n_cand += n;
+        if (best_c >= 0) {                                      // :5363-5383
+          sh.dist_best = best;
+          for (int k = 0; k < 8; k++) { sh.best_corner[k] = sh.corner[best_c][k]; sh.centre[k] = sh.corner[best_c][k]; }
+          sh.best_ss_x = Hor; sh.best_ss_y = Ver;
+          sh.best_index = (b * 8 + pass) * 64 + best_c;
+        } else if (pass == 0) {
+          // first pass of a start vector resets the best centres to the initial rectangle (:5183-5203)
+          sh.centre[0] = 0; sh.centre[1] = 0; sh.centre[2] = cols * G - 1; sh.centre[3] = 0;
+          sh.centre[4] = cols * G - 1; sh.centre[5] = rows * G - 1; sh.centre[6] = 0; sh.centre[7] = rows * G - 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    HopGtResult r;
+    r.gt_flag = 0;
+    for (int k = 0; k < 4; k++) { r.gt[k].hor = 0; r.gt[k].ver = 0; }
+    r.cost = job.threshold;
+    r.mv_int.hor = 0; r.mv_int.ver = 0;
+    r.best_index = -1;
+    r.n_candidates = sh.n_cand;
+    int any = 0;
+    for (int k = 0; k < 8; k++) any |= sh.best_corner[k];
+    if (any) {                                                  // :5436-5459
+      const int* bc = sh.best_corner;
+      r.gt_flag = 1;
+      r.gt[0].hor = (int16_t)(bc[0] / last_step);                  r.gt[0].ver = (int16_t)(bc[1] / last_step);
+      r.gt[1].hor = (int16_t)((bc[2] - cols * G + 1) / last_step); r.gt[1].ver = (int16_t)(bc[3] / last_step);
+      r.gt[2].hor = (int16_t)((bc[4] - cols * G + 1) / last_step); r.gt[2].ver = (int16_t)((bc[5] - rows * G + 1) / last_step);
+      r.gt[3].hor = (int16_t)(bc[6] / last_step);                  r.gt[3].ver = (int16_t)((bc[7] - rows * G + 1) / last_step);
+      r.cost = sh.dist_best;
+      r.mv_int.hor = (int16_t)(sh.best_ss_x >> 2);
+      r.mv_int.ver = (int16_t)(sh.best_ss_y >> 2);
+      r.best_index = sh.best_index;
+    }
+    out[job_id] = r;
+  }
+}
+
+size_t gt_smem_bytes(int max_cols, int max_rows)
+{
+  const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
+  const size_t win = (size_t)((max_cols + 2 * w) | 1) * (max_rows + 2 * w);
+  return sizeof(GtShared) + sizeof(int16_t) * ((size_t)max_cols * max_rows + win) + 16;
+}
+
+cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k2_gt_search, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gt_smem_bytes(HOP_MAX_PU, HOP_MAX_PU));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // CTA size: one thread per (candidate, tile) task of a pass, capped at GT_THREADS
+  const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
+  int threads = GT_CANDS * (max_cols / tile) * (max_rows / tile);
+  threads = threads > GT_THREADS ? GT_THREADS : ((threads + 31) / 32) * 32;
+  if (threads < 64) threads = 64;   // the candidate set-up uses GT_CANDS (56) threads
+  k2_gt_search<<<n, threads, gt_smem_bytes(max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out);
+  if (launches) (*launches)++;
+  return cudaGetLastError();
+}
+
+}  // namespace hop

@@ -1,9 +1,9 @@
 """Synthetic PU batches for the stand-alone HOP candidate-search microbench (BASELINE.json configs[2],
 SURVEY.md §8d) and for parity tests.
 
-Every PU gets its own little "causal neighbourhood": a plane of (2*SR + W + 8) x (SR + H + 8) int16
-samples cut from the synthetic lenslet image, with the PU's own position at (SR, SR).  Samples at
-x >= SR and y >= SR (the PU itself and everything right/below it) are NOT_VALID (-1), exactly the
+Every PU gets its own little "causal neighbourhood": a plane of (2*ox + W + 8) x (oy + H + 8) int16
+samples cut from the synthetic lenslet image, with the PU's own position at (ox, oy) =
+(max(SR, W), max(SR, 2H + 4)).  Samples at x >= ox and y >= oy (the PU itself and everything right/below it) are NOT_VALID (-1), exactly the
 staircase the SS reference has while a CU is being coded.  The search window, gate offsets and cost
 state are what TEncSearch::xSetSearchRange / xMotionEstimation produce for a 2Nx2N PU at a CU origin
 (TEncSearch.cpp:6224-6259, 4555-4560).
@@ -25,8 +25,15 @@ def lambda_motion_sad(qp=32):
     return int(math.floor(65536.0 * math.sqrt(lam)))
 
 
+def plane_origin(cols, rows, sr=SEARCH_RANGE):
+    """Position of the PU inside its private plane: far enough from the plane edges for the K1 search
+    range AND for the 2W x 2H window of any K2 start vector drawn by PuBatch."""
+    return max(sr, cols), max(sr, 2 * rows + 4)
+
+
 def plane_dims(cols, rows, sr=SEARCH_RANGE):
-    return 2 * sr + cols + PROBE_PAD, sr + rows + PROBE_PAD
+    ox, oy = plane_origin(cols, rows, sr)
+    return 2 * ox + cols + PROBE_PAD, oy + rows + PROBE_PAD
 
 
 class PuBatch:
@@ -36,7 +43,8 @@ class PuBatch:
                  n_start=1, threshold=0xFFFFFFFE, source=None):
         self.cols, self.rows, self.n, self.sr = cols, rows, n, sr
         pw, ph = plane_dims(cols, rows, sr)
-        self.pw, self.ph = pw, ph
+        ox, oy = plane_origin(cols, rows, sr)
+        self.pw, self.ph, self.ox, self.oy = pw, ph, ox, oy
         rng = np.random.default_rng(seed)
         if source is None:
             # one big lenslet picture, planes are random crops of it (cheap for thousands of PUs)
@@ -49,9 +57,9 @@ class PuBatch:
         xs = rng.integers(0, sw - pw, size=n)
         for i in range(n):
             crop = source[ys[i]:ys[i] + ph, xs[i]:xs[i] + pw]
-            org[i] = crop[sr:sr + rows, sr:sr + cols]
+            org[i] = crop[oy:oy + rows, ox:ox + cols]
             ref[i] = crop
-        ref[:, sr:, sr:] = -1
+        ref[:, oy:, ox:] = -1
         self.org = org.reshape(-1)
         self.ref = ref.reshape(-1)
         lam = lambda_motion_sad(qp)
@@ -59,7 +67,7 @@ class PuBatch:
         sj = np.zeros(n, dtype=SEARCH_JOB_DT)
         idx = np.arange(n, dtype=np.int64)
         sj["org_off"] = idx * (rows * cols)
-        sj["ref_off"] = idx * (ph * pw) + sr * pw + sr
+        sj["ref_off"] = idx * (ph * pw) + oy * pw + ox
         sj["org_stride"] = cols
         sj["ref_stride"] = pw
         sj["cols"], sj["rows"] = cols, rows
@@ -78,16 +86,17 @@ class PuBatch:
         for k in ("org_off", "ref_off", "org_stride", "ref_stride", "cols", "rows", "bit_depth"):
             gj[k] = sj[k]
         # start vector: somewhere in the fully coded rows above the PU, 2W x 2H window inside the plane
-        hy_lo = -sr + rows // 2
-        hy_hi = max(hy_lo, -rows - rows // 2 - 4)
-        hx = rng.integers(-sr + cols // 2, sr - cols // 2 + 1, size=n)
+        hy_lo = -oy + rows // 2
+        hy_hi = -rows - rows // 2 - 4
+        hx_lo, hx_hi = -ox + cols // 2, ox - cols // 2
+        hx = rng.integers(hx_lo, hx_hi + 1, size=n)
         hy = rng.integers(hy_lo, hy_hi + 1, size=n)
         gj["ss_cand"]["hor"] = hx.astype(np.int16)
         gj["ss_cand"]["ver"] = hy.astype(np.int16)
         gj["num_pred"] = 2                                     # fillMvpCand always returns AMVP_MAX_NUM_CANDS
         if n_start > 1:
             for k in range(min(n_start - 1, 2)):
-                ax = rng.integers(-sr + cols // 2, sr - cols // 2 + 1, size=n) * 4 + rng.integers(0, 4, size=n)
+                ax = rng.integers(hx_lo, hx_hi + 1, size=n) * 4 + rng.integers(0, 4, size=n)
                 ay = rng.integers(hy_lo, hy_hi + 1, size=n) * 4 + rng.integers(0, 4, size=n)
                 gj["amvp"][:, k]["hor"] = ax.astype(np.int16)
                 gj["amvp"][:, k]["ver"] = ay.astype(np.int16)

@@ -178,9 +178,10 @@ int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs,
 int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,
                                  const int16_t* d_org, const int16_t* d_ref,
                                  HopSearchResult* d_out, void* stream);
+/* max_cols/max_rows: upper bound of the PU shapes in d_jobs (sizes the shared-memory window and CTA) */
 int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs,
                                     const int16_t* d_org, const int16_t* d_ref,
-                                    HopGtResult* d_out, void* stream);
+                                    HopGtResult* d_out, int max_cols, int max_rows, void* stream);
 int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs,
                        const int16_t* d_org, const int16_t* d_cur,
                        uint32_t* d_out, void* stream);

@@ -1,0 +1,241 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (libhopgpu.so), against the oracle on
+the same seeded inputs (bit-exact: integer / index work), against the committed golden vectors of the
+compiled reference, and -- at full microbench sizes -- through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle
+import hevc_hop_b200 as hop
+from hevc_hop_b200.workload import PuBatch, dist_jobs, gt_passes
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+ALL_SHAPES = [(8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 8), (16, 8), (8, 16), (16, 4), (4, 16), (16, 12),
+              (12, 16), (32, 16), (16, 32), (32, 8), (8, 32), (32, 24), (24, 32), (64, 32), (32, 64), (64, 16),
+              (16, 64), (64, 48), (48, 64)]
+
+
+def gt_assert_equal(a, b, extras=True):
+    for k in ("gt_flag", "cost") + (("best_index", "n_candidates") if extras else ()):
+        assert (a[k] == b[k]).all(), (k, a[k], b[k])
+    assert a["gt"].tobytes() == b["gt"].tobytes()
+    assert a["mv_int"].tobytes() == b["mv_int"].tobytes()
+
+
+def test_library_loaded_and_device_is_blackwell(ctx):
+    assert ctx.lib.hop_abi_version() == 1
+    assert ctx.lib.hop_device_count() >= 1
+
+
+@pytest.mark.parametrize("shape", ALL_SHAPES)
+def test_k1_matches_oracle(ctx, shape):
+    c, r = shape
+    orc = _oracle.oracle()
+    b = PuBatch(c, r, 4, seed=c * 31 + r, sr=24)
+    got = ctx.pattern_search(b.search_jobs, b.org, b.ref)
+    want = orc.pattern_search(b.search_jobs, b.org, b.ref)
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("shape", ALL_SHAPES)
+@pytest.mark.parametrize("use_had", [1, 0])
+def test_k2_matches_oracle(ctx, shape, use_had):
+    c, r = shape
+    orc = _oracle.oracle()
+    n = 2 if c * r >= 2048 else 5
+    b = PuBatch(c, r, n, seed=c * 17 + r + use_had, sr=24, use_had=use_had, n_start=3)
+    got = ctx.pattern_search_gt(b.gt_jobs, b.org, b.ref)
+    want = orc.pattern_search_gt(b.gt_jobs, b.org, b.ref)
+    gt_assert_equal(got, want)
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (16, 16), (16, 12), (32, 16), (8, 4)])
+def test_main10_matches_oracle(ctx, shape):
+    """10-bit input keeps the reference's quirks: 255 clip inside the warp, >>2 distortion scaling."""
+    c, r = shape
+    orc = _oracle.oracle()
+    b = PuBatch(c, r, 4, seed=c + r, bit_depth=10, sr=20, n_start=3)
+    assert ctx.pattern_search(b.search_jobs, b.org, b.ref).tobytes() == \
+        orc.pattern_search(b.search_jobs, b.org, b.ref).tobytes()
+    gt_assert_equal(ctx.pattern_search_gt(b.gt_jobs, b.org, b.ref), orc.pattern_search_gt(b.gt_jobs, b.org, b.ref))
+
+
+def test_golden_vectors_of_compiled_reference(ctx):
+    g = np.load(os.path.join(GOLD, "search_golden.npz"))
+    for k in range(int(g["n_search"])):
+        t = "s%02d" % k
+        org, ref = g[t + "_org"], g[t + "_ref"]
+        assert ctx.pattern_search(g[t + "_k1_jobs"], org, ref).tobytes() == g[t + "_k1_out"].tobytes(), k
+        gt_assert_equal(ctx.pattern_search_gt(g[t + "_k2_jobs"], org, ref), g[t + "_k2_out"], extras=False)
+    g = np.load(os.path.join(GOLD, "dist_golden.npz"))
+    for k in range(int(g["n_dist"])):
+        t = "d%03d" % k
+        assert (ctx.dist(g[t + "_jobs"], g[t + "_org"], g[t + "_cur"]) == g[t + "_out"]).all(), k
+
+
+def test_k2_edge_cases(ctx):
+    orc = _oracle.oracle()
+    b = PuBatch(16, 16, 6, seed=21, sr=24, n_start=3)
+    # zero start vectors: nothing searched
+    j = b.gt_jobs.copy(); j["ss_cand"]["hor"] = 0; j["ss_cand"]["ver"] = 0; j["amvp"]["hor"] = 0; j["amvp"]["ver"] = 0
+    r = ctx.pattern_search_gt(j, b.org, b.ref)
+    assert (r["gt_flag"] == 0).all() and (r["n_candidates"] == 0).all() and (r["cost"] == j["threshold"]).all()
+    # unbeatable threshold, thresholds near the optimum (ties resolved by strict '<' in loop order)
+    full = orc.pattern_search_gt(b.gt_jobs, b.org, b.ref)
+    for delta in (0, 1, 2, 40):
+        j = b.gt_jobs.copy(); j["threshold"] = full["cost"] + delta
+        gt_assert_equal(ctx.pattern_search_gt(j, b.org, b.ref), orc.pattern_search_gt(j, b.org, b.ref))
+    j = b.gt_jobs.copy(); j["threshold"] = 0
+    r = ctx.pattern_search_gt(j, b.org, b.ref)
+    assert (r["gt_flag"] == 0).all() and (r["n_candidates"] == 3 * 4 * 56).all()
+    # start vectors whose window overlaps NOT_VALID samples (clamped to 0 by the staging)
+    j = b.gt_jobs.copy(); j["ss_cand"]["hor"] = -4; j["ss_cand"]["ver"] = -12
+    gt_assert_equal(ctx.pattern_search_gt(j, b.org, b.ref), orc.pattern_search_gt(j, b.org, b.ref))
+    # flat content: many exact ties
+    flat_org = np.full_like(b.org, 100); flat_ref = np.where(b.ref < 0, b.ref, 100).astype(np.int16)
+    gt_assert_equal(ctx.pattern_search_gt(b.gt_jobs, flat_org, flat_ref),
+                    orc.pattern_search_gt(b.gt_jobs, flat_org, flat_ref))
+    assert ctx.pattern_search(b.search_jobs, flat_org, flat_ref).tobytes() == \
+        orc.pattern_search(b.search_jobs, flat_org, flat_ref).tobytes()
+
+
+def test_k1_edge_cases(ctx):
+    orc = _oracle.oracle()
+    b = PuBatch(16, 8, 5, seed=2, sr=20)
+    for mod in ("empty", "all_invalid", "no_ss", "no_fen", "ragged"):
+        s, ref = b.search_jobs.copy(), b.ref
+        if mod == "empty":
+            s["rng_top"] = s["rng_bottom"] + 1
+        elif mod == "all_invalid":
+            ref = np.full_like(b.ref, -1)
+        elif mod == "no_ss":
+            s["is_ss"] = 0
+        elif mod == "no_fen":
+            s["fast_enc"] = 0
+        elif mod == "ragged":
+            s["rng_left"] += np.arange(5); s["rng_right"] -= 2 * np.arange(5); s["rng_top"] += 3
+        assert ctx.pattern_search(s, b.org, ref).tobytes() == orc.pattern_search(s, b.org, ref).tobytes(), mod
+    # sentinel inside a block whose probes are valid (cannot happen in the encoder; SAD must still be exact)
+    ref = b.ref.copy().reshape(5, b.ph, b.pw)
+    ref[:, 3:6, 10:14] = -1
+    ref = ref.reshape(-1)
+    assert ctx.pattern_search(b.search_jobs, b.org, ref).tobytes() == \
+        orc.pattern_search(b.search_jobs, b.org, ref).tobytes()
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (64, 64), (16, 12), (4, 8), (2, 2), (6, 2), (20, 6), (48, 64)])
+def test_k3_matches_oracle(ctx, shape):
+    c, r = shape
+    orc = _oracle.oracle()
+    for bit_depth in (8, 10):
+        for func, sub in ((hop.HOP_DF_HADS, 0), (hop.HOP_DF_SAD, 0), (hop.HOP_DF_SAD, 1)):
+            if sub and r < 2:
+                continue
+            jobs, org, cur = dist_jobs(c, r, 7, seed=c * 3 + r, bit_depth=bit_depth, func=func, sub_shift=sub)
+            assert (ctx.dist(jobs, org, cur) == orc.dist(jobs, org, cur)).all()
+
+
+def test_k4_reference_mirror(ctx):
+    """Patch-by-patch mirror update + incremental border extension == full extendPicBorder each time."""
+    rng = np.random.default_rng(4)
+    pic_w, pic_h, m = 192, 128, 80
+    ctx.ref_create(pic_w, pic_h, m)
+    ctx.ref_reset(-1)
+    host = np.full((pic_h + 2 * m, pic_w + 2 * m), -1, dtype=np.int16)
+    assert (ctx.ref_download() == host).all()
+    for cy in range(0, pic_h, 64):
+        for cx in range(0, pic_w, 64):
+            for (bx, by, bs) in [(0, 0, 32), (32, 0, 32), (0, 32, 32), (32, 32, 16), (48, 32, 16), (32, 48, 16), (48, 48, 16),
+                                 (0, 0, 64)]:
+                blk = rng.integers(0, 256, size=(bs, bs)).astype(np.int16)
+                ctx.ref_update(cx + bx, cy + by, blk)
+                host[m + cy + by:m + cy + by + bs, m + cx + bx:m + cx + bx + bs] = blk
+                _oracle.extend_border_oracle(host, pic_w, pic_h, m)
+            assert (ctx.ref_download() == host).all(), (cx, cy)
+    # golden vector of the compiled reference's extendPicBorder
+    g = np.load(os.path.join(GOLD, "border_golden.npz"))
+    pw, ph, mm = int(g["pic_w"]), int(g["pic_h"]), int(g["margin"])
+    ctx.ref_create(pw, ph, mm)
+    ctx.ref_reset(-1)
+    ctx.ref_update(0, 0, g["before"][mm:mm + ph, mm:mm + pw])
+    assert (ctx.ref_download() == g["after"]).all()
+
+
+def test_search_on_the_mirror(ctx):
+    """ref == NULL: jobs address the context's SS reference mirror (negative offsets reach the margin)."""
+    orc = _oracle.oracle()
+    rng = np.random.default_rng(8)
+    pic_w, pic_h, m = 128, 128, 80
+    ctx.ref_create(pic_w, pic_h, m)
+    ctx.ref_reset(-1)
+    host = np.full((pic_h + 2 * m, pic_w + 2 * m), -1, dtype=np.int16)
+    img = rng.integers(0, 256, size=(pic_h, pic_w)).astype(np.int16)
+    for (x, y, w, h) in [(0, 0, 128, 64), (0, 64, 64, 64)]:       # first CTU row + first CTU of the second
+        ctx.ref_update(x, y, img[y:y + h, x:x + w])
+        host[m + y:m + y + h, m + x:m + x + w] = img[y:y + h, x:x + w]
+        _oracle.extend_border_oracle(host, pic_w, pic_h, m)
+    stride = pic_w + 2 * m
+    b = PuBatch(16, 16, 1, seed=1, sr=16)
+    s = b.search_jobs.copy()
+    s["ref_stride"] = stride
+    s["ref_off"] = 64 * stride + 64            # PU at (64,64) relative to sample (0,0)
+    s["rng_left"], s["rng_right"], s["rng_top"], s["rng_bottom"] = -72, 40, -72, -4
+    got = ctx.pattern_search(s, b.org, None)
+    s2 = s.copy(); s2["ref_off"] += m * stride + m
+    want = orc.pattern_search(s2, b.org, host.reshape(-1))
+    assert got.tobytes() == want.tobytes()
+    gj = b.gt_jobs.copy()
+    gj["ref_stride"] = stride; gj["ref_off"] = 64 * stride + 64
+    gj["ss_cand"]["hor"] = got["mv"]["hor"]; gj["ss_cand"]["ver"] = got["mv"]["ver"]
+    gj["amvp"]["hor"][:, 0] = -70 * 4; gj["amvp"]["ver"][:, 0] = -66 * 4      # window reaches into the margin
+    g2 = gj.copy(); g2["ref_off"] += m * stride + m
+    gt_assert_equal(ctx.pattern_search_gt(gj, b.org, None), orc.pattern_search_gt(g2, b.org, host.reshape(-1)))
+
+
+def test_full_size_properties(ctx):
+    """BASELINE sizes (SearchRange 128, up to 64x64): properties that need no CPU oracle run.
+    (a) threshold idempotence: re-running K2 with threshold = its own best cost accepts nothing;
+    (b) threshold monotonicity: cost(threshold=T) == min(T, cost(threshold=MAX));
+    (c) K1 optimum is a fixed point: restricting the window to the winner returns the same SAD/cost;
+    (d) every call scores exactly starts*passes*56 candidates."""
+    for (c, r, n) in [(64, 64, 8), (32, 32, 16), (16, 16, 32), (8, 8, 64)]:
+        b = PuBatch(c, r, n, seed=c, n_start=2)
+        full = ctx.pattern_search_gt(b.gt_jobs, b.org, b.ref)
+        assert (full["n_candidates"] == 2 * gt_passes(c, r) * 56).all()
+        assert (full["gt_flag"] == 1).all()
+        j = b.gt_jobs.copy(); j["threshold"] = full["cost"]
+        again = ctx.pattern_search_gt(j, b.org, b.ref)
+        assert (again["gt_flag"] == 0).all() and (again["cost"] == full["cost"]).all()
+        k1 = ctx.pattern_search(b.search_jobs, b.org, b.ref)
+        assert (k1["found"] == 1).all()
+        s = b.search_jobs.copy()
+        s["rng_left"] = s["rng_right"] = k1["mv"]["hor"]; s["rng_top"] = s["rng_bottom"] = k1["mv"]["ver"]
+        one = ctx.pattern_search(s, b.org, b.ref)
+        assert one.tobytes() == k1.tobytes()
+        # oracle spot check on one PU of the full-size batch
+        orc = _oracle.oracle()
+        assert orc.pattern_search_gt(b.gt_jobs[:1], b.org, b.ref).tobytes() == full[:1].tobytes()
+
+
+def test_device_entry_points_with_torch_buffers(ctx):
+    """HBM-resident path used by bench.py: torch owns the device buffers and the stream."""
+    import torch
+    orc = _oracle.oracle()
+    b = PuBatch(16, 16, 9, seed=77, sr=24, n_start=2)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a.view(np.uint8).copy()).to(dev)
+    d_org, d_ref = t(b.org), t(b.ref)
+    d_sj, d_gj = t(b.search_jobs), t(b.gt_jobs)
+    d_so = torch.zeros(len(b.search_jobs) * hop.SEARCH_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+    d_go = torch.zeros(len(b.gt_jobs) * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.pattern_search_dev(b.n, d_sj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_so.data_ptr(), stream)
+    ctx.pattern_search_gt_dev(b.n, d_gj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_go.data_ptr(), 16, 16, stream)
+    torch.cuda.synchronize()
+    so = d_so.cpu().numpy().view(hop.SEARCH_RES_DT)
+    go = d_go.cpu().numpy().view(hop.GT_RES_DT)
+    assert so.tobytes() == orc.pattern_search(b.search_jobs, b.org, b.ref).tobytes()
+    assert go.tobytes() == orc.pattern_search_gt(b.gt_jobs, b.org, b.ref).tobytes()
