@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- HOP candidate-search throughput on B200 (BASELINE.json metric, configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--pus P]
+
+One "step" = one pass of the HOP hot path (K2: xPatternSearchGT, all diamond passes, 1 start vector)
+over one batch of synthetic PUs: P PUs for each of the shapes 8x8, 16x16, 32x32, 64x64 (P = 4096 by
+default), inputs = original block + the 2W x 2H causal window of the start vector, threshold
+MAX_UINT-1 so every candidate is warped and scored.  A HOP candidate = one affine corner set that is
+warped (bilinear, IEEE binary64) and scored (Hadamard SATD + lambda*bits): 56 per pass.
+
+  value      HOP candidates/s, whole job (all ranks), inputs already resident in HBM
+  e2e        same metric through the host C-ABI call hop_pattern_search_gt_batch with HOST buffers:
+             H2D copies of jobs/org/windows and the D2H read of the results are inside the timed region
+  roofline   dominant kernel k2_gt_search against the fp64 pipe (the warp is binary64 by reference
+             semantics) using a peak measured in this run by hop_probe_alu; the HBM view is reported
+             beside it (`hbm`) because the contract asks for it, although the kernel is ALU bound
+  cpu_baseline  the compiled reference (oracle/_ref/libhopref.so, kind "reference") or the C port of
+             it (oracle/, kind "port") on a bounded sample of the same workload, host cores stated
+
+N > 1 (torchrun): one process per GPU, each rank owns an independent batch (weak scaling, no data-path
+collective: PUs / lenslet images are independent); NCCL is used for the barriers and the max-over-ranks
+time only.  --impl reference times the reference's own CPU implementation on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+SHAPES = [(8, 8), (16, 16), (32, 32), (64, 64)]
+FP64_OPS_PER_PIXEL = 24      # Fx,Fy 8 + p,q 4 + bilinear 11 + rounding 1
+INT_OPS_PER_PIXEL = 15       # Hadamard 9 + clamps 6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pus", type=int, default=4096, help="PUs per shape per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="PUs per shape in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_batches(hop, pus, seed):
+    from hevc_hop_b200.workload import GtBatch
+    from hevc_hop_b200.lenslet import lenslet_luma
+    src = lenslet_luma(1024, 1024, seed=seed).astype(np.int16)
+    return [GtBatch(c, r, pus, seed=seed * 16 + i, source=src) for i, (c, r) in enumerate(SHAPES)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for (t, line) in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                smax = float(f[2])
+                if t0 <= t <= t1 + 0.1:
+                    sm.append(float(f[1]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline (the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, shape_idx, n, seed = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    graft.load_package()
+    import _oracle
+    from hevc_hop_b200.workload import GtBatch
+    chk = _oracle.ref() if kind == "reference" else _oracle.oracle()
+    c, r = SHAPES[shape_idx]
+    b = GtBatch(c, r, n, seed=seed)
+    t = time.perf_counter()
+    out = chk.pattern_search_gt(b.gt_jobs, b.org, b.ref)
+    dt = time.perf_counter() - t
+    return b.candidates(), dt, os.getpid(), int(out["cost"].astype(np.int64).sum() & 0xFFFFFFFF)
+
+
+def cpu_baseline(sample_per_shape, procs):
+    """Time the reference CPU path on `procs` processes; returns (candidates/s, kind, cores, sample text)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    graft.load_package()
+    import _oracle
+    import multiprocessing as mp
+    kind = "reference" if _oracle.ref() is not None else "port"
+    if kind == "port":
+        _oracle.oracle()   # build once before forking
+    # split every shape's sample over the workers so that all workers carry the same mix
+    per = max(1, sample_per_shape // procs)
+    tasks = [(kind, s, per, 1000 + 17 * w + s) for w in range(procs) for s in range(len(SHAPES))]
+    if procs == 1:
+        res = [_cpu_worker(t) for t in tasks]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, tasks, chunksize=len(SHAPES))
+    # search time only (input synthesis excluded); the processes run concurrently, one per core, so the
+    # job's duration is the slowest process's summed search time
+    per_pid = {}
+    for (_, dt, pid, _) in res:
+        per_pid[pid] = per_pid.get(pid, 0.0) + dt
+    wall = max(per_pid.values())
+    cands = sum(r[0] for r in res)
+    sample = "%d PUs of each shape %s per process x %d processes, all diamond passes, 1 start vector" % (
+        per, "/".join("%dx%d" % s for s in SHAPES), procs)
+    return cands / wall, kind, procs, sample, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, kind, c, sample, wall = cpu_baseline(8 * procs, procs)   # 8 PUs of each shape per process
+        if i >= args.warmup:
+            vals.append((v, wall))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([w for _, w in vals]) * 1e3)
+    line = {
+        "impl": "reference", "metric": "HOP candidates/s", "value": value, "unit": "candidates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: standalone HOP candidate-search microbench, PUs 8x8/16x16/32x32/64x64, "
+                               "full diamond grid, 1 start vector, HadamardME, 8-bit, QP32 lambda (bounded CPU sample)"},
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": c, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libhopgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hop = graft.load_package()
+    ctx = hop.HopContext(local)
+    batches = make_batches(hop, args.pus, seed=rank + 1)
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.uint8)).to(dev)
+
+    def pinned(a):
+        t = torch.from_numpy(a.view(np.uint8)).pin_memory()
+        return t
+
+    dbat = []
+    for b in batches:
+        d = {"b": b, "jobs": to_dev(b.gt_jobs), "org": to_dev(b.org), "ref": to_dev(b.ref),
+             "out": torch.zeros(b.n * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev),
+             "h_jobs": pinned(b.gt_jobs), "h_org": pinned(b.org), "h_ref": pinned(b.ref),
+             "h_out": torch.zeros(b.n * hop.GT_RES_DT.itemsize, dtype=torch.uint8).pin_memory()}
+        dbat.append(d)
+    # all library work and all timing events live on the context's own stream (torch's default stream
+    # has handle 0, which the ABI reads as "use the context stream")
+    tstream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = ctx.stream
+    cands_per_step = sum(b.candidates() for b in batches)
+    pix_per_step = sum(b.pixel_candidates() for b in batches)
+    in_bytes = sum(b.input_bytes() for b in batches)
+    out_bytes = sum(b.n * hop.GT_RES_DT.itemsize for b in batches)
+
+    def step_resident():
+        for d in dbat:
+            b = d["b"]
+            ctx.pattern_search_gt_dev(b.n, d["jobs"].data_ptr(), d["org"].data_ptr(), d["ref"].data_ptr(),
+                                      d["out"].data_ptr(), b.cols, b.rows, stream)
+
+    def step_e2e():
+        # the reference-facing host call: pinned HOST buffers in, results back on the host
+        for d in dbat:
+            b = d["b"]
+            ctx._check(ctx.lib.hop_pattern_search_gt_batch(
+                ctx.h, b.n, d["h_jobs"].data_ptr(), d["h_org"].data_ptr(), b.org.size,
+                d["h_ref"].data_ptr(), b.ref.size, d["h_out"].data_ptr()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ALU peaks for the roofline, measured in this run (burst, kernel alone)
+    peaks = {}
+    if rank == 0:
+        for what, name in ((2, "fp64_add"), (3, "fp64_mul"), (0, "int32_add"), (5, "int32_lop3"), (1, "vabsdiff4")):
+            peaks[name] = max(ctx.probe_alu(what)[0] for _ in range(2))
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ctx.launch_count
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(dbat) + 1)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(tstream)
+    for s in range(args.steps):
+        for i, d in enumerate(dbat):
+            b = d["b"]
+            ev[s][i].record(tstream)
+            ctx.pattern_search_gt_dev(b.n, d["jobs"].data_ptr(), d["org"].data_ptr(), d["ref"].data_ptr(),
+                                      d["out"].data_ptr(), b.cols, b.rows, stream)
+        ev[s][len(dbat)].record(tstream)
+    e1.record(tstream)
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = cands_per_step * world / (ms_per_step * 1e-3)
+    # per-shape kernel durations (CUDA events on the launching stream)
+    per_shape_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)])) for i in range(len(dbat))]
+
+    # parity spot check of what was just timed (outside the timed region): first PUs of every shape
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    parity = None
+    if rank == 0:
+        import _oracle
+        orc = _oracle.oracle()
+        parity = True
+        for d in dbat:
+            b = d["b"]
+            got = d["out"].cpu().numpy().view(hop.GT_RES_DT)[:2]
+            want = orc.pattern_search_gt(b.gt_jobs[:2], b.org, b.ref)
+            parity &= got.tobytes() == want.tobytes()
+
+    # end-to-end through the host C-ABI call
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = cands_per_step * world / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (k2_gt_search, all four launches of a step)
+    kern_ms = sum(per_shape_ms)
+    fp64_ops = FP64_OPS_PER_PIXEL * pix_per_step
+    int_ops = INT_OPS_PER_PIXEL * pix_per_step
+    fp64_peak = max(peaks["fp64_add"], peaks["fp64_mul"])
+    achieved = fp64_ops / (kern_ms * 1e-3) / 1e9
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    hbm_achieved = (in_bytes + out_bytes) / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_step")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k2_gt_search", "bound": "fp64-alu", "achieved": achieved, "peak": fp64_peak, "unit": "Gop/s",
+        "frac": achieved / fp64_peak, "traffic": traffic,
+        "peak_source": "hop_probe_alu DADD/DMUL loop, measured in this run (MEASURED_PEAKS.json has no fp64/int32 figure)",
+        "algorithmic": {"fp64_ops_per_pixel_candidate": FP64_OPS_PER_PIXEL, "int32_ops_per_pixel_candidate": INT_OPS_PER_PIXEL,
+                        "pixel_candidates_per_step": pix_per_step},
+        "int32": {"achieved": int_ops / (kern_ms * 1e-3) / 1e9, "peak": peaks["int32_lop3"], "unit": "Gop/s",
+                  "frac": int_ops / (kern_ms * 1e-3) / 1e9 / peaks["int32_lop3"], "peak_int32_add": peaks["int32_add"]},
+        "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                "algorithmic_bytes_per_step": in_bytes + out_bytes, "peak_source": hbm_src},
+        "kernel_ms_per_step": kern_ms, "per_shape_ms": dict(zip(["%dx%d" % s for s in SHAPES], per_shape_ms)),
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, kind, cores, sample, wall = cpu_baseline(args.cpu_sample, 1)
+        cpu = {"value": v, "unit": "candidates/s", "cores": cores, "kind": kind, "sample": sample, "seconds": wall}
+
+    line = {
+        "metric": "HOP candidates/s", "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+        "config": {"workload": "configs[2]: standalone HOP candidate-search microbench, %d PUs of each of 8x8/16x16/32x32/64x64 "
+                               "per GPU, full diamond grid (3/4/5/6 passes x 56 affine candidates), 1 start vector, HadamardME, "
+                               "8-bit, QP32 lambda" % args.pus,
+                   "l2": "inputs larger than L2 (%.0f MB per step per GPU)" % (in_bytes / 1e6),
+                   "candidates_per_step_per_gpu": cands_per_step},
+        "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "ms_per_step": e2e_ms, "api": "hop_pattern_search_gt_batch (host buffers, pinned)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "parity_spot_check": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,142 +65,129 @@ struct GtShared {
   int32_t  best_ss_x, best_ss_y;
   int32_t  best_index;
   uint32_t n_cand;
+  unsigned long long red_key[2];
+  uint32_t red_cnt[2];
 };
+constexpr size_t GT_SHARED_BYTES = (sizeof(GtShared) + 15) / 16 * 16;
 
 // ---- in-register Walsh-Hadamard tiles ---------------------------------------------------------
-template <int N> struct Tile;
-
-template <> struct Tile<8> {
-  int d[64];
+template <int N>
+struct Tile {
+  int d[N * N];
   __device__ __forceinline__ void row_transform(int r)
   {
-    int* p = d + r * 8;
+    int* p = d + r * N;
 #pragma unroll
-    for (int len = 1; len < 8; len <<= 1)
+    for (int len = 1; len < N; len <<= 1)
 #pragma unroll
-      for (int i = 0; i < 8; i += len << 1)
+      for (int i = 0; i < N; i += len << 1)
 #pragma unroll
         for (int j = i; j < i + len; j++) { int a = p[j], b = p[j + len]; p[j] = a + b; p[j + len] = a - b; }
   }
+  // column butterflies + sum of magnitudes; the last butterfly stage is folded into the magnitude sum:
+  // |a+b| + |a-b| == 2*max(|a|,|b|)
   __device__ __forceinline__ uint32_t satd()
   {
 #pragma unroll
-    for (int x = 0; x < 8; x++)
+    for (int x = 0; x < N; x++)
 #pragma unroll
-      for (int len = 1; len < 8; len <<= 1)
+      for (int len = 1; len < N / 2; len <<= 1)
 #pragma unroll
-        for (int i = 0; i < 8; i += len << 1)
+        for (int i = 0; i < N; i += len << 1)
 #pragma unroll
           for (int j = i; j < i + len; j++) {
-            int a = d[j * 8 + x], b = d[(j + len) * 8 + x];
-            d[j * 8 + x] = a + b; d[(j + len) * 8 + x] = a - b;
+            int a = d[j * N + x], b = d[(j + len) * N + x];
+            d[j * N + x] = a + b; d[(j + len) * N + x] = a - b;
           }
-    int s = 0;
+    unsigned s = 0;
 #pragma unroll
-    for (int k = 0; k < 64; k++) s += abs(d[k]);
-    return (uint32_t)((s + 2) >> 2);           // xCalcHADs8x8, TComRdCost.cpp:1572
+    for (int x = 0; x < N; x++)
+#pragma unroll
+      for (int j = 0; j < N / 2; j++) s += (unsigned)max(abs(d[j * N + x]), abs(d[(j + N / 2) * N + x]));
+    s <<= 1;
+    return N == 8 ? (s + 2) >> 2 : (s + 1) >> 1;   // xCalcHADs8x8 :1572 / xCalcHADs4x4 :1476
   }
   __device__ __forceinline__ uint32_t sad()
   {
-    int s = 0;
+    unsigned s = 0;
 #pragma unroll
-    for (int k = 0; k < 64; k++) s += abs(d[k]);
-    return (uint32_t)s;
+    for (int k = 0; k < N * N; k++) s = __sad(d[k], 0, s);
+    return s;
   }
 };
 
-template <> struct Tile<4> {
-  int d[16];
-  __device__ __forceinline__ void row_transform(int r)
-  {
-    int* p = d + r * 4;
-#pragma unroll
-    for (int len = 1; len < 4; len <<= 1)
-#pragma unroll
-      for (int i = 0; i < 4; i += len << 1)
-#pragma unroll
-        for (int j = i; j < i + len; j++) { int a = p[j], b = p[j + len]; p[j] = a + b; p[j + len] = a - b; }
-  }
-  __device__ __forceinline__ uint32_t satd()
-  {
-#pragma unroll
-    for (int x = 0; x < 4; x++)
-#pragma unroll
-      for (int len = 1; len < 4; len <<= 1)
-#pragma unroll
-        for (int i = 0; i < 4; i += len << 1)
-#pragma unroll
-          for (int j = i; j < i + len; j++) {
-            int a = d[j * 4 + x], b = d[(j + len) * 4 + x];
-            d[j * 4 + x] = a + b; d[(j + len) * 4 + x] = a - b;
-          }
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) s += abs(d[k]);
-    return (uint32_t)((s + 1) >> 1);           // xCalcHADs4x4, TComRdCost.cpp:1476
-  }
-  __device__ __forceinline__ uint32_t sad()
-  {
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) s += abs(d[k]);
-    return (uint32_t)s;
-  }
-};
+// exact (double)n for 0 <= n < 2^31 without a conversion instruction: 2^52 + n is representable
+__device__ __forceinline__ double small_int_to_double(int n)
+{
+  return __dsub_rn(__hiloint2double(0x43300000, n), 4503599627370496.0);
+}
 
 // One warped sample: ProjectiveTransform body for the affine case (h2 == h5 == 0 => denominator is
 // exactly 1.0, so the reference's division returns its numerator unchanged), TComPrediction.cpp:925-972,1025.
-//   win  : clamped window samples, addressed win[(Y + w) * wstride + (X + w)]
+//   win  : high 32-bit words of the samples' binary64 representation (samples < 2^20 have a zero low
+//          word), addressed win[(Y + w) * wstride + (X + w)] -- reading a sample costs no conversion
 //   lim_x/lim_y : w + cols - 1 / w + rows - 1
-__device__ __forceinline__ int warp_sample(const int16_t* __restrict__ win, int wstride, int w,
+__device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int wstride, int w,
                                            double Fx, double Fy, int off_x, int off_y,
                                            double off_xd, double off_yd, int lim_x, int lim_y)
 {
-  int Y = (int)Fy - off_y;                       // C truncation toward zero
-  int X = (int)Fx - off_x;
-  double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)Y);
-  double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)X);
-  if (Y < -w) Y = -w;
-  if (X < -w) X = -w;
-  if (Y > lim_y) Y = lim_y;
-  if (X > lim_x) X = lim_x;
-  if (Y + 1 > lim_y) Y = lim_y - 1;
-  if (X + 1 > lim_x) X = lim_x - 1;
-  const int16_t* r0 = win + (Y + w) * wstride + (X + w);
-  const int16_t* r1 = r0 + wstride;
-  double A = (double)r0[0], B = (double)r0[1], C = (double)r1[0], D = (double)r1[1];
-  double omp = __dsub_rn(1.0, p), omq = __dsub_rn(1.0, q);
+  int Y = __double2int_rz(Fy) - off_y;           // C truncation toward zero
+  int X = __double2int_rz(Fx) - off_x;
+  const double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)Y);
+  const double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)X);
+  // the six ordered clamps of :950-961 collapse to [-w, lim-1]: after the first four the value is in
+  // [-w, lim]; the last two map lim to lim-1
+  Y = min(max(Y, -w), lim_y - 1);
+  X = min(max(X, -w), lim_x - 1);
+  const uint32_t* r0 = win + (Y + w) * wstride + (X + w);
+  const uint32_t* r1 = r0 + wstride;
+  const double A = __hiloint2double((int)r0[0], 0), B = __hiloint2double((int)r0[1], 0);
+  const double C = __hiloint2double((int)r1[0], 0), D = __hiloint2double((int)r1[1], 0);
+  const double omp = __dsub_rn(1.0, p), omq = __dsub_rn(1.0, q);
   double aux = __dmul_rn(omq, __dadd_rn(__dmul_rn(omp, A), __dmul_rn(p, B)));
   aux = __dadd_rn(aux, __dmul_rn(q, __dadd_rn(__dmul_rn(omp, C), __dmul_rn(p, D))));
-  if (aux > 255.0) aux = 255.0;                  // hard-coded 8-bit clip (also for 10-bit input)
-  if (aux < 0.0) aux = 0.0;
-  return (int)__dadd_rn(aux, 0.5);               // (Pel)(aux + 0.5)
+  // "if (aux > 255) aux = 255; if (aux < 0) aux = 0; (Pel)(aux + 0.5)": the clip commutes with the
+  // rounding -- trunc(aux + 0.5) clamped to [0,255] gives the same integer for every finite aux
+  const int v = __double2int_rz(__dadd_rn(aux, 0.5));
+  return min(max(v, 0), 255);
 }
 
 template <int N, bool HAD>
-__device__ __forceinline__ uint32_t eval_tile(const GtShared& sh, int c, int tx, int ty,
-                                              const int16_t* __restrict__ org, int org_stride,
-                                              const int16_t* __restrict__ win, int wstride, int w,
+__device__ __forceinline__ uint32_t eval_tile(double h0, double h3, double h6, double h1, double h4, double h7,
+                                              int tx, int ty, const int* __restrict__ org,
+                                              const uint32_t* __restrict__ win, int wstride, int w,
                                               int cols, int rows)
 {
   const int off_x = cols >> 1, off_y = rows >> 1;          // W/2 - W/4 with W = 2*cols
-  const double off_xd = (double)off_x, off_yd = (double)off_y;
+  const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
   const int lim_x = w + cols - 1, lim_y = w + rows - 1;
-  const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
-  const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  double h0x[N], h1x[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const double xd = small_int_to_double(off_x + tx + k);
+    h0x[k] = __dmul_rn(h0, xd);
+    h1x[k] = __dmul_rn(h1, xd);
+  }
   Tile<N> t;
 #pragma unroll
   for (int r = 0; r < N; r++) {
-    const double yd = (double)(off_y + ty + r);
+    const double yd = small_int_to_double(off_y + ty + r);
     const double h3y = __dmul_rn(h3, yd), h4y = __dmul_rn(h4, yd);
+    int o[N];
+    const int* orow = org + (ty + r) * cols + tx;
+    if (N == 8) {
+      const int4 a = *reinterpret_cast<const int4*>(orow), b = *reinterpret_cast<const int4*>(orow + 4);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4 % N] = b.x; o[5 % N] = b.y; o[6 % N] = b.z; o[7 % N] = b.w;
+    } else {
+      const int4 a = *reinterpret_cast<const int4*>(orow);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    }
 #pragma unroll
     for (int k = 0; k < N; k++) {
-      const double xd = (double)(off_x + tx + k);
       // (h0*x + h3*y) + h6, left to right
-      double Fx = __dadd_rn(__dadd_rn(__dmul_rn(h0, xd), h3y), h6);
-      double Fy = __dadd_rn(__dadd_rn(__dmul_rn(h1, xd), h4y), h7);
-      int v = warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
-      t.d[r * N + k] = (int)org[(ty + r) * org_stride + tx + k] - v;
+      const double Fx = __dadd_rn(__dadd_rn(h0x[k], h3y), h6);
+      const double Fy = __dadd_rn(__dadd_rn(h1x[k], h4y), h7);
+      t.d[r * N + k] = o[k] - warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
     }
     if (HAD) t.row_transform(r);
   }
@@ -208,23 +195,34 @@ __device__ __forceinline__ uint32_t eval_tile(const GtShared& sh, int c, int tx,
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
-// dynamic shared memory: [GtShared][org rows*cols int16][window (cols+2w)*(rows+2w) int16]
+// dynamic shared memory: [GtShared][org rows*cols int32][window (rows+2w) x wstride uint32]
+// Thread layout: blockDim.x = GT_CANDS * groups; thread -> (candidate c = tid % 56, group g = tid / 56);
+// a thread keeps its candidate for the whole pass and walks the tiles g, g+groups, ...
 template <int N, bool HAD>
-__device__ __forceinline__ void run_tasks(GtShared& sh, const int16_t* s_org, const int16_t* s_win,
+__device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const uint32_t* s_win,
                                           int wstride, int w, int cols, int rows)
 {
+  const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
+  if (g >= groups || !sh.valid[c]) return;
   const int tiles_x = cols / N, ntiles = tiles_x * (rows / N);
-  const int ntask = ntiles * GT_CANDS;
-  for (int t = threadIdx.x; t < ntask; t += blockDim.x) {
-    const int c = t % GT_CANDS, tile = t / GT_CANDS;
-    if (!sh.valid[c]) continue;
+  const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
+  const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  uint32_t acc = 0;
+  for (int tile = g; tile < ntiles; tile += groups) {
     const int tx = (tile % tiles_x) * N, ty = (tile / tiles_x) * N;
-    uint32_t v = eval_tile<N, HAD>(sh, c, tx, ty, s_org, cols, s_win, wstride, w, cols, rows);
-    atomicAdd(&sh.dist[c], v);
+    acc += eval_tile<N, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, wstride, w, cols, rows);
   }
+  if (groups == 1) sh.dist[c] = acc;
+  else atomicAdd(&sh.dist[c], acc);
 }
 
-__global__ void __launch_bounds__(GT_THREADS)
+__host__ __device__ __forceinline__ int gt_win_stride(int win_w)
+{
+  // stride == 8 (mod 32) words: the 2x2 footprints of neighbouring candidates fall into distinct banks
+  return ((win_w + 23) / 32) * 32 + 8;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 2)
 k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
              const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out)
 {
@@ -240,9 +238,9 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
   int last_step = nss_window >> 6;                              // :4763 (IT_MAX_NSS_Iteration 6)
   if (last_step == 0) last_step = 1;
   const int win_w = cols + 2 * w, win_h = rows + 2 * w;
-  const int wstride = win_w | 1;                                // odd stride: fewer bank conflicts
-  int16_t* s_org = reinterpret_cast<int16_t*>(smem_raw + sizeof(GtShared));
-  int16_t* s_win = s_org + rows * cols;
+  const int wstride = gt_win_stride(win_w);
+  int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
+  uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + rows * cols);
   const int16_t* org = org_buf + job.org_off;
   const int16_t* ref_y = ref_buf + job.ref_off;
   const int max_val = (1 << job.bit_depth) - 1;
@@ -271,12 +269,13 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
     const int Hor = (int16_t)(Hx << 2), Ver = (int16_t)(Hy << 2);   // Short, quarter-pel
     __syncthreads();   // previous pass done with s_win
     // window staging: samples [Hx - w, Hx + w + cols) x [Hy - w, Hy + w + rows) relative to the PU,
-    // clamped to [0, 2^bd - 1] (filterCopy first+last, TComInterpolationFilter.cpp:113-154)
+    // clamped to [0, 2^bd - 1] (filterCopy first+last, TComInterpolationFilter.cpp:113-154), stored as
+    // the high word of their binary64 value
     for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
-      const int wy = i / win_w, wx = i % win_w;
+      const int wy = i / win_w, wx = i - wy * win_w;
       int v = ref_y[(Hy - w + wy) * job.ref_stride + (Hx - w + wx)];
-      v = v < 0 ? 0 : (v > max_val ? max_val : v);
-      s_win[wy * wstride + wx] = (int16_t)v;
+      v = min(max(v, 0), max_val);
+      s_win[wy * wstride + wx] = (uint32_t)__double2hiint((double)v);
     }
     const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);        // :5345
 
@@ -337,20 +336,29 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
         else             run_tasks<4, false>(sh, s_org, s_win, wstride, w, cols, rows);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        // ordered argmin with the carried threshold: loop order, strict '<' (:5361)
-        uint32_t best = sh.dist_best;
-        int best_c = -1;
-        uint32_t n = 0;
-        for (int c = 0; c < GT_CANDS; c++) {
-          if (!sh.valid[c]) continue;
-          n++;
-          const uint32_t d = (sh.dist[c] >> dist_shift) + sh.add_cost[c];
-          if (d < best) { best = d; best_c = c; }
+      if (threadIdx.x < 64) {
+        // ordered argmin with the carried threshold: the serial loop keeps the FIRST strict minimum in
+        // loop order (:5361) == the minimum of (cost, loop index) over the pass, accepted iff it beats
+        // the running best
+        const int c = threadIdx.x;
+        const bool ok = c < GT_CANDS && sh.valid[c];
+        unsigned long long key = ok ? ((unsigned long long)((sh.dist[c] >> dist_shift) + sh.add_cost[c]) << 8) | (unsigned)c
+                                    : ~0ull;
+        const unsigned n_ok = __popc(__ballot_sync(0xffffffffu, ok));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other < key ? other : key;
         }
-        sh.n_cand += n;
+        if ((threadIdx.x & 31) == 0) { sh.red_key[threadIdx.x >> 5] = key; sh.red_cnt[threadIdx.x >> 5] = n_ok; }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned long long key = sh.red_key[0] < sh.red_key[1] ? sh.red_key[0] : sh.red_key[1];
+        sh.n_cand += sh.red_cnt[0] + sh.red_cnt[1];
+        const int best_c = (key != ~0ull && (uint32_t)(key >> 8) < sh.dist_best) ? (int)(key & 0xff) : -1;
         if (best_c >= 0) {                                      // :5363-5383
-          sh.dist_best = best;
+          sh.dist_best = (uint32_t)(key >> 8);
           for (int k = 0; k < 8; k++) { sh.best_corner[k] = sh.corner[best_c][k]; sh.centre[k] = sh.corner[best_c][k]; }
           sh.best_ss_x = Hor; sh.best_ss_y = Ver;
           sh.best_index = (b * 8 + pass) * 64 + best_c;
@@ -392,8 +400,8 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
 size_t gt_smem_bytes(int max_cols, int max_rows)
 {
   const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
-  const size_t win = (size_t)((max_cols + 2 * w) | 1) * (max_rows + 2 * w);
-  return sizeof(GtShared) + sizeof(int16_t) * ((size_t)max_cols * max_rows + win) + 16;
+  const size_t win = (size_t)gt_win_stride(max_cols + 2 * w) * (max_rows + 2 * w);
+  return GT_SHARED_BYTES + sizeof(int) * (size_t)max_cols * max_rows + sizeof(uint32_t) * win;
 }
 
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
@@ -406,11 +414,12 @@ cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  // CTA size: one thread per (candidate, tile) task of a pass, capped at GT_THREADS
+  // CTA = 56 candidates x `groups` tile groups (a thread keeps its candidate for a whole pass)
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
-  int threads = GT_CANDS * (max_cols / tile) * (max_rows / tile);
-  threads = threads > GT_THREADS ? GT_THREADS : ((threads + 31) / 32) * 32;
-  if (threads < 64) threads = 64;   // the candidate set-up uses GT_CANDS (56) threads
+  int groups = (max_cols / tile) * (max_rows / tile);
+  if (groups > GT_THREADS / GT_CANDS) groups = GT_THREADS / GT_CANDS;
+  int threads = GT_CANDS * groups;
+  if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
   k2_gt_search<<<n, threads, gt_smem_bytes(max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out);
   if (launches) (*launches)++;
   return cudaGetLastError();

@@ -139,3 +139,58 @@ def dist_jobs(cols, rows, n, seed=0, bit_depth=8, func=HOP_DF_HADS, sub_shift=0)
     jobs["cols"], jobs["rows"] = cols, rows
     jobs["func"], jobs["sub_shift"], jobs["bit_depth"] = func, sub_shift, bit_depth
     return jobs, org.reshape(-1), cur.reshape(-1)
+
+
+class GtBatch:
+    """K2-only microbench batch (BASELINE.json configs[2]): per PU the original block and the compact
+    2W x 2H reference window of ONE start vector -- exactly the samples xPatternSearchGT stages into
+    m_filteredBlock[0][0] (TEncSearch.cpp:5161-5165).  ref_off is set so that the start vector
+    (ss_cand) lands on the window; the PU's own position lies outside the buffer and is never read."""
+
+    def __init__(self, cols, rows, n, seed=0, bit_depth=8, qp=32, use_had=1, threshold=0xFFFFFFFE, source=None):
+        self.cols, self.rows, self.n = cols, rows, n
+        rng = np.random.default_rng(seed)
+        if source is None:
+            source = lenslet_luma(1024, 1024, seed=seed, bit_depth=bit_depth).astype(np.int16)
+        sh, sw = source.shape
+        ww, wh = 2 * cols, 2 * rows
+        win = np.empty((n, wh, ww), dtype=np.int16)
+        org = np.empty((n, rows, cols), dtype=np.int16)
+        ys = rng.integers(0, sh - wh - 16, size=n)
+        xs = rng.integers(0, sw - ww - 16, size=n)
+        for i in range(n):
+            win[i] = source[ys[i]:ys[i] + wh, xs[i]:xs[i] + ww]
+            # the block one micro-image pitch (15 px) to the right of the window centre: self-similar content
+            oy, ox = ys[i] + rows // 2, xs[i] + cols // 2 + 15
+            org[i] = source[oy:oy + rows, ox:ox + cols]
+        self.org = org.reshape(-1)
+        self.ref = win.reshape(-1)
+        hx = rng.integers(-120, -8, size=n)
+        hy = rng.integers(-120, -8, size=n)
+        gj = np.zeros(n, dtype=GT_JOB_DT)
+        idx = np.arange(n, dtype=np.int64)
+        gj["org_off"] = idx * (rows * cols)
+        gj["org_stride"] = cols
+        gj["ref_stride"] = ww
+        gj["ref_off"] = idx * (ww * wh) + (rows // 2 - hy) * ww + (cols // 2 - hx)
+        gj["cols"], gj["rows"] = cols, rows
+        gj["ss_cand"]["hor"] = hx.astype(np.int16)
+        gj["ss_cand"]["ver"] = hy.astype(np.int16)
+        gj["num_pred"] = 2          # fillMvpCand pads with zero vectors, which the search skips
+        gj["threshold"] = threshold
+        gj["use_had"] = use_had
+        gj["bit_depth"] = bit_depth
+        gj["cost"]["lambda_cost"] = lambda_motion_sad(qp)
+        gj["cost"]["cost_scale"] = 0
+        gj["cost"]["pred"]["hor"] = ((hx + rng.integers(-3, 4, size=n)) * 4).astype(np.int16)
+        gj["cost"]["pred"]["ver"] = ((hy + rng.integers(-3, 4, size=n)) * 4).astype(np.int16)
+        self.gt_jobs = gj
+
+    def candidates(self):
+        return self.n * gt_passes(self.cols, self.rows) * CANDIDATES_PER_PASS
+
+    def pixel_candidates(self):
+        return self.candidates() * self.cols * self.rows
+
+    def input_bytes(self):
+        return self.org.nbytes + self.ref.nbytes + self.gt_jobs.nbytes

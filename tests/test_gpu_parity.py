@@ -197,8 +197,10 @@ def test_search_on_the_mirror(ctx):
 
 def test_full_size_properties(ctx):
     """BASELINE sizes (SearchRange 128, up to 64x64): properties that need no CPU oracle run.
-    (a) threshold idempotence: re-running K2 with threshold = its own best cost accepts nothing;
-    (b) threshold monotonicity: cost(threshold=T) == min(T, cost(threshold=MAX));
+    (a) threshold consistency: re-running K2 with threshold = its own best cost either accepts nothing
+        (cost == threshold) or finds a strictly better cost (the diamond walk is greedy, so a different
+        threshold may steer it elsewhere) -- it can never return a worse one;
+    (b) an accepted result always beats the threshold strictly;
     (c) K1 optimum is a fixed point: restricting the window to the winner returns the same SAD/cost;
     (d) every call scores exactly starts*passes*56 candidates."""
     for (c, r, n) in [(64, 64, 8), (32, 32, 16), (16, 16, 32), (8, 8, 64)]:
@@ -208,7 +210,8 @@ def test_full_size_properties(ctx):
         assert (full["gt_flag"] == 1).all()
         j = b.gt_jobs.copy(); j["threshold"] = full["cost"]
         again = ctx.pattern_search_gt(j, b.org, b.ref)
-        assert (again["gt_flag"] == 0).all() and (again["cost"] == full["cost"]).all()
+        assert (again["cost"] <= full["cost"]).all()
+        assert ((again["gt_flag"] == 1) == (again["cost"] < full["cost"])).all()
         k1 = ctx.pattern_search(b.search_jobs, b.org, b.ref)
         assert (k1["found"] == 1).all()
         s = b.search_jobs.copy()
@@ -231,7 +234,8 @@ def test_device_entry_points_with_torch_buffers(ctx):
     d_sj, d_gj = t(b.search_jobs), t(b.gt_jobs)
     d_so = torch.zeros(len(b.search_jobs) * hop.SEARCH_RES_DT.itemsize, dtype=torch.uint8, device=dev)
     d_go = torch.zeros(len(b.gt_jobs) * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()                     # uploads done before the context's stream reads them
+    stream = ctx.stream
     ctx.pattern_search_dev(b.n, d_sj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_so.data_ptr(), stream)
     ctx.pattern_search_gt_dev(b.n, d_gj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_go.data_ptr(), 16, 16, stream)
     torch.cuda.synchronize()
