@@ -152,12 +152,14 @@ __device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int
   return min(max(v, 0), 255);
 }
 
-template <int N, bool HAD>
-__device__ __forceinline__ uint32_t eval_tile(double h0, double h3, double h6, double h1, double h4, double h7,
-                                              int tx, int ty, const int* __restrict__ org,
-                                              const uint32_t* __restrict__ win, int wstride, int w,
-                                              int cols, int rows)
+// ---- 4x4 tiles (PU shapes with a dimension of 4 or 12): one thread per tile -------------------
+template <bool HAD>
+__device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, double h1, double h4, double h7,
+                                               int tx, int ty, const int* __restrict__ org,
+                                               const uint32_t* __restrict__ win, int wstride, int w,
+                                               int cols, int rows)
 {
+  constexpr int N = 4;
   const int off_x = cols >> 1, off_y = rows >> 1;          // W/2 - W/4 with W = 2*cols
   const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
   const int lim_x = w + cols - 1, lim_y = w + rows - 1;
@@ -173,19 +175,11 @@ __device__ __forceinline__ uint32_t eval_tile(double h0, double h3, double h6, d
   for (int r = 0; r < N; r++) {
     const double yd = small_int_to_double(off_y + ty + r);
     const double h3y = __dmul_rn(h3, yd), h4y = __dmul_rn(h4, yd);
-    int o[N];
-    const int* orow = org + (ty + r) * cols + tx;
-    if (N == 8) {
-      const int4 a = *reinterpret_cast<const int4*>(orow), b = *reinterpret_cast<const int4*>(orow + 4);
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4 % N] = b.x; o[5 % N] = b.y; o[6 % N] = b.z; o[7 % N] = b.w;
-    } else {
-      const int4 a = *reinterpret_cast<const int4*>(orow);
-      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-    }
+    const int4 a = *reinterpret_cast<const int4*>(org + (ty + r) * cols + tx);
+    const int o[N] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int k = 0; k < N; k++) {
-      // (h0*x + h3*y) + h6, left to right
-      const double Fx = __dadd_rn(__dadd_rn(h0x[k], h3y), h6);
+      const double Fx = __dadd_rn(__dadd_rn(h0x[k], h3y), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x[k], h4y), h7);
       t.d[r * N + k] = o[k] - warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
     }
@@ -194,26 +188,121 @@ __device__ __forceinline__ uint32_t eval_tile(double h0, double h3, double h6, d
   return HAD ? t.satd() : t.sad();
 }
 
-// ---- the kernel -------------------------------------------------------------------------------
+// ---- 8x8 tiles: two adjacent lanes per tile, 4 rows x 8 columns each ----------------------------
+// Keeps the unrolled body at 32 pixels (instruction-cache resident) and the register tile at 32 words.
+// Lane `half` owns rows 4*half .. 4*half+3: horizontal 8-point and vertical 4-point butterflies run in
+// registers; the last vertical stage pairs coefficient (j,k) of the two halves and is folded into the
+// magnitude sum: |a+b| + |a-b| == 2*max(|a|,|b|).  Each lane handles 16 of the 32 coefficient pairs
+// after one shuffle per pair.  Returns the rounded tile SATD in both lanes (or the half-tile SAD).
+template <bool HAD>
+__device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double h6, double h1, double h4, double h7,
+                                                    int tx, int ty, int half, const int* __restrict__ org,
+                                                    const uint32_t* __restrict__ win, int wstride, int w,
+                                                    int cols, int rows)
+{
+  const int off_x = cols >> 1, off_y = rows >> 1;
+  const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
+  const int lim_x = w + cols - 1, lim_y = w + rows - 1;
+  const int y0 = ty + 4 * half;
+  double h3y[4], h4y[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const double yd = small_int_to_double(off_y + y0 + r);
+    h3y[r] = __dmul_rn(h3, yd);
+    h4y[r] = __dmul_rn(h4, yd);
+  }
+  int d[32];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const double xd = small_int_to_double(off_x + tx + k);
+    const double h0x = __dmul_rn(h0, xd), h1x = __dmul_rn(h1, xd);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double Fx = __dadd_rn(__dadd_rn(h0x, h3y[r]), h6);    // (h0*x + h3*y) + h6, left to right
+      const double Fy = __dadd_rn(__dadd_rn(h1x, h4y[r]), h7);
+      d[r * 8 + k] = org[(y0 + r) * cols + tx + k] -
+                     warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
+    }
+  }
+  if (!HAD) {
+    unsigned s = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) s = __sad(d[i], 0, s);
+    return s;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++)                      // horizontal 8-point
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          const int a = d[r * 8 + j], b = d[r * 8 + j + len];
+          d[r * 8 + j] = a + b; d[r * 8 + j + len] = a - b;
+        }
+#pragma unroll
+  for (int k = 0; k < 8; k++)                      // vertical 4-point inside the half
+#pragma unroll
+    for (int len = 1; len < 4; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 4; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          const int a = d[j * 8 + k], b = d[(j + len) * 8 + k];
+          d[j * 8 + k] = a + b; d[(j + len) * 8 + k] = a - b;
+        }
+  unsigned s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int mine = half ? d[16 + i] : d[i];
+    const int send = half ? d[i] : d[16 + i];
+    const int recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    s += (unsigned)max(abs(mine), abs(recv));
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return (s + 1) >> 1;                             // (2*sum + 2) >> 2, xCalcHADs8x8 TComRdCost.cpp:1572
+}
+
+// ---- task loops -----------------------------------------------------------------------------------
 // dynamic shared memory: [GtShared][org rows*cols int32][window (rows+2w) x wstride uint32]
-// Thread layout: blockDim.x = GT_CANDS * groups; thread -> (candidate c = tid % 56, group g = tid / 56);
-// a thread keeps its candidate for the whole pass and walks the tiles g, g+groups, ...
-template <int N, bool HAD>
-__device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                          int wstride, int w, int cols, int rows)
+// N == 4: blockDim.x = 56 * groups, thread -> (c = tid % 56, g = tid / 56), tiles g, g+groups, ...
+// N == 8: blockDim.x = 112 * groups, thread -> (half = tid & 1, c = (tid >> 1) % 56, g = (tid >> 1) / 56)
+// A thread keeps its candidate (and the six map coefficients) for the whole pass.
+template <bool HAD>
+__device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const uint32_t* s_win,
+                                           int wstride, int w, int cols, int rows)
 {
   const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
   if (g >= groups || !sh.valid[c]) return;
-  const int tiles_x = cols / N, ntiles = tiles_x * (rows / N);
+  const int tiles_x = cols / 4, ntiles = tiles_x * (rows / 4);
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
   uint32_t acc = 0;
   for (int tile = g; tile < ntiles; tile += groups) {
-    const int tx = (tile % tiles_x) * N, ty = (tile / tiles_x) * N;
-    acc += eval_tile<N, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, wstride, w, cols, rows);
+    const int tx = (tile % tiles_x) * 4, ty = (tile / tiles_x) * 4;
+    acc += eval_tile4<HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, wstride, w, cols, rows);
   }
-  if (groups == 1) sh.dist[c] = acc;
-  else atomicAdd(&sh.dist[c], acc);
+  atomicAdd(&sh.dist[c], acc);
+}
+
+template <bool HAD>
+__device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const uint32_t* s_win,
+                                           int wstride, int w, int cols, int rows)
+{
+  const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
+  const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = blockDim.x / (2 * GT_CANDS);
+  // lanes of a pair always agree on (c, g), so the shuffles inside eval_half_tile8 see both lanes
+  if (g >= groups || !sh.valid[c]) return;
+  const int tiles_x = cols / 8, ntiles = tiles_x * (rows / 8);
+  const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
+  const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  uint32_t acc = 0;
+  for (int tile = g; tile < ntiles; tile += groups) {
+    const int tx = (tile % tiles_x) * 8, ty = (tile / tiles_x) * 8;
+    acc += eval_half_tile8<HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, wstride, w, cols, rows);
+  }
+  if (!HAD || half == 0) atomicAdd(&sh.dist[c], acc);   // HAD: both lanes hold the tile sums, count once
 }
 
 __host__ __device__ __forceinline__ int gt_win_stride(int win_w)
@@ -329,11 +418,11 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
       }
       __syncthreads();
       if (tile_n == 8) {
-        if (job.use_had) run_tasks<8, true>(sh, s_org, s_win, wstride, w, cols, rows);
-        else             run_tasks<8, false>(sh, s_org, s_win, wstride, w, cols, rows);
+        if (job.use_had) run_tasks8<true>(sh, s_org, s_win, wstride, w, cols, rows);
+        else             run_tasks8<false>(sh, s_org, s_win, wstride, w, cols, rows);
       } else {
-        if (job.use_had) run_tasks<4, true>(sh, s_org, s_win, wstride, w, cols, rows);
-        else             run_tasks<4, false>(sh, s_org, s_win, wstride, w, cols, rows);
+        if (job.use_had) run_tasks4<true>(sh, s_org, s_win, wstride, w, cols, rows);
+        else             run_tasks4<false>(sh, s_org, s_win, wstride, w, cols, rows);
       }
       __syncthreads();
       if (threadIdx.x < 64) {
@@ -414,11 +503,12 @@ cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  // CTA = 56 candidates x `groups` tile groups (a thread keeps its candidate for a whole pass)
+  // CTA = 56 candidates x `groups` tile groups x (2 lanes per 8x8 tile | 1 lane per 4x4 tile)
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
+  const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
   int groups = (max_cols / tile) * (max_rows / tile);
-  if (groups > GT_THREADS / GT_CANDS) groups = GT_THREADS / GT_CANDS;
-  int threads = GT_CANDS * groups;
+  if (groups > GT_THREADS / per_group) groups = GT_THREADS / per_group;
+  int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
   k2_gt_search<<<n, threads, gt_smem_bytes(max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out);
   if (launches) (*launches)++;
