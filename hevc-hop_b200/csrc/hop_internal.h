@@ -7,7 +7,7 @@
 namespace hop {
 
 constexpr int GT_CANDS   = 56;    // affine corner sets per diamond pass
-constexpr int GT_THREADS = 224;   // K2 CTA size upper bound: 56 candidates x 4 tile groups
+constexpr int GT_THREADS = 336;   // K2 CTA size upper bound: 56 candidates x 2 lanes x 3 tile groups
 constexpr int K1_THREADS = 256;
 constexpr int K1_MAX_SLICES = 32; // CTAs cooperating on one PU's search window
 

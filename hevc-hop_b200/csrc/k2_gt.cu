@@ -124,45 +124,50 @@ __device__ __forceinline__ double small_int_to_double(int n)
 
 // One warped sample: ProjectiveTransform body for the affine case (h2 == h5 == 0 => denominator is
 // exactly 1.0, so the reference's division returns its numerator unchanged), TComPrediction.cpp:925-972,1025.
-//   win  : high 32-bit words of the samples' binary64 representation (samples < 2^20 have a zero low
-//          word), addressed win[(Y + w) * wstride + (X + w)] -- reading a sample costs no conversion
-//   lim_x/lim_y : w + cols - 1 / w + rows - 1
-__device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int wstride, int w,
-                                           double Fx, double Fy, int off_x, int off_y,
-                                           double off_xd, double off_yd, int lim_x, int lim_y)
+//   win    : the clamped window samples as the HIGH 32-bit word of their binary64 value (integers < 2^20
+//            have a zero low word), so reading a sample costs no int->double conversion;
+//            win[Yc * WS + Xc] with Yc = Y + w, Xc = X + w
+//   lim_xw : (w + cols - 1) - 1 + w, lim_yw likewise -- the upper clamp in window coordinates
+template <int WS>
+__device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int w,
+                                           double Fx, double Fy, int off_x, int off_y, double off_xd,
+                                           double off_yd, int lim_xw, int lim_yw)
 {
-  int Y = __double2int_rz(Fy) - off_y;           // C truncation toward zero
-  int X = __double2int_rz(Fx) - off_x;
+  const int Y = __double2int_rz(Fy) - off_y;     // C truncation toward zero
+  const int X = __double2int_rz(Fx) - off_x;
   const double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)Y);
   const double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)X);
   // the six ordered clamps of :950-961 collapse to [-w, lim-1]: after the first four the value is in
-  // [-w, lim]; the last two map lim to lim-1
-  Y = min(max(Y, -w), lim_y - 1);
-  X = min(max(X, -w), lim_x - 1);
-  const uint32_t* r0 = win + (Y + w) * wstride + (X + w);
-  const uint32_t* r1 = r0 + wstride;
+  // [-w, lim]; the last two map lim to lim-1.  In window coordinates: max(min(Y + w, lim_yw), 0).
+  const int Yc = __vimin_s32_relu(Y + w, lim_yw);
+  const int Xc = __vimin_s32_relu(X + w, lim_xw);
+  const uint32_t* r0 = win + Yc * WS + Xc;
   const double A = __hiloint2double((int)r0[0], 0), B = __hiloint2double((int)r0[1], 0);
-  const double C = __hiloint2double((int)r1[0], 0), D = __hiloint2double((int)r1[1], 0);
+  const double C = __hiloint2double((int)r0[WS], 0), D = __hiloint2double((int)r0[WS + 1], 0);
   const double omp = __dsub_rn(1.0, p), omq = __dsub_rn(1.0, q);
   double aux = __dmul_rn(omq, __dadd_rn(__dmul_rn(omp, A), __dmul_rn(p, B)));
   aux = __dadd_rn(aux, __dmul_rn(q, __dadd_rn(__dmul_rn(omp, C), __dmul_rn(p, D))));
-  // "if (aux > 255) aux = 255; if (aux < 0) aux = 0; (Pel)(aux + 0.5)": the clip commutes with the
-  // rounding -- trunc(aux + 0.5) clamped to [0,255] gives the same integer for every finite aux
-  const int v = __double2int_rz(__dadd_rn(aux, 0.5));
-  return min(max(v, 0), 255);
+  // "if (aux > 255) aux = 255; if (aux < 0) aux = 0; (Pel)(aux + 0.5)":
+  //  (1) the clip commutes with the rounding: clamping the rounded integer to [0,255] is the same;
+  //  (2) trunc(fl(aux + 0.5)) == round-to-nearest(aux): p and q are rationals with the ODD denominator
+  //      D = (2*cols-1)(2*rows-1), so the exact bilinear value has denominator D^2 and stays at least
+  //      1/(2*D^2) >= 1.9e-9 away from every half-integer, four orders of magnitude more than the
+  //      accumulated binary64 rounding error (< 1e-12) -- ties never occur (warp rounding).
+  //  Adding 1.5*2^52 leaves round-to-nearest(aux) in the low word: no double->int conversion.
+  const int v = __double2loint(__dadd_rn(aux, 6755399441055744.0));
+  return __vimin_s32_relu(v, 255);
 }
 
 // ---- 4x4 tiles (PU shapes with a dimension of 4 or 12): one thread per tile -------------------
-template <bool HAD>
+template <int WS, bool HAD>
 __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, double h1, double h4, double h7,
                                                int tx, int ty, const int* __restrict__ org,
-                                               const uint32_t* __restrict__ win, int wstride, int w,
-                                               int cols, int rows)
+                                               const uint32_t* __restrict__ win, int w, int cols, int rows)
 {
   constexpr int N = 4;
   const int off_x = cols >> 1, off_y = rows >> 1;          // W/2 - W/4 with W = 2*cols
   const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
-  const int lim_x = w + cols - 1, lim_y = w + rows - 1;
+  const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
   double h0x[N], h1x[N];
 #pragma unroll
   for (int k = 0; k < N; k++) {
@@ -181,7 +186,7 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
     for (int k = 0; k < N; k++) {
       const double Fx = __dadd_rn(__dadd_rn(h0x[k], h3y), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x[k], h4y), h7);
-      t.d[r * N + k] = o[k] - warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
+      t.d[r * N + k] = o[k] - warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_xw, lim_yw);
     }
     if (HAD) t.row_transform(r);
   }
@@ -194,15 +199,14 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
 // registers; the last vertical stage pairs coefficient (j,k) of the two halves and is folded into the
 // magnitude sum: |a+b| + |a-b| == 2*max(|a|,|b|).  Each lane handles 16 of the 32 coefficient pairs
 // after one shuffle per pair.  Returns the rounded tile SATD in both lanes (or the half-tile SAD).
-template <bool HAD>
+template <int WS, bool HAD>
 __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double h6, double h1, double h4, double h7,
                                                     int tx, int ty, int half, const int* __restrict__ org,
-                                                    const uint32_t* __restrict__ win, int wstride, int w,
-                                                    int cols, int rows)
+                                                    const uint32_t* __restrict__ win, int w, int cols, int rows)
 {
   const int off_x = cols >> 1, off_y = rows >> 1;
   const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
-  const int lim_x = w + cols - 1, lim_y = w + rows - 1;
+  const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
   const int y0 = ty + 4 * half;
   double h3y[4], h4y[4];
 #pragma unroll
@@ -213,6 +217,13 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
   }
   int d[32];
 #pragma unroll
+  for (int r = 0; r < 4; r++) {                    // original block: two 16-byte loads per row
+    const int4 a = *reinterpret_cast<const int4*>(org + (y0 + r) * cols + tx);
+    const int4 b = *reinterpret_cast<const int4*>(org + (y0 + r) * cols + tx + 4);
+    d[r * 8 + 0] = a.x; d[r * 8 + 1] = a.y; d[r * 8 + 2] = a.z; d[r * 8 + 3] = a.w;
+    d[r * 8 + 4] = b.x; d[r * 8 + 5] = b.y; d[r * 8 + 6] = b.z; d[r * 8 + 7] = b.w;
+  }
+#pragma unroll
   for (int k = 0; k < 8; k++) {
     const double xd = small_int_to_double(off_x + tx + k);
     const double h0x = __dmul_rn(h0, xd), h1x = __dmul_rn(h1, xd);
@@ -220,8 +231,7 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
     for (int r = 0; r < 4; r++) {
       const double Fx = __dadd_rn(__dadd_rn(h0x, h3y[r]), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x, h4y[r]), h7);
-      d[r * 8 + k] = org[(y0 + r) * cols + tx + k] -
-                     warp_sample(win, wstride, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_x, lim_y);
+      d[r * 8 + k] -= warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_xw, lim_yw);
     }
   }
   if (!HAD) {
@@ -252,26 +262,29 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
           const int a = d[j * 8 + k], b = d[(j + len) * 8 + k];
           d[j * 8 + k] = a + b; d[(j + len) * 8 + k] = a - b;
         }
+  // only the two lanes of the pair take part: other pairs of the warp may run a different number of
+  // tiles (or none, for a rejected candidate), so a full-warp mask would wait for lanes that left
+  const unsigned pair_mask = 3u << (threadIdx.x & 30u);
   unsigned s = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     const int mine = half ? d[16 + i] : d[i];
     const int send = half ? d[i] : d[16 + i];
-    const int recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    const int recv = __shfl_xor_sync(pair_mask, send, 1);
     s += (unsigned)max(abs(mine), abs(recv));
   }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(pair_mask, s, 1);
   return (s + 1) >> 1;                             // (2*sum + 2) >> 2, xCalcHADs8x8 TComRdCost.cpp:1572
 }
 
 // ---- task loops -----------------------------------------------------------------------------------
-// dynamic shared memory: [GtShared][org rows*cols int32][window (rows+2w) x wstride uint32]
+// dynamic shared memory: [GtShared][org rows*cols int32][window (rows+2w) x WS uint32 high words]
 // N == 4: blockDim.x = 56 * groups, thread -> (c = tid % 56, g = tid / 56), tiles g, g+groups, ...
 // N == 8: blockDim.x = 112 * groups, thread -> (half = tid & 1, c = (tid >> 1) % 56, g = (tid >> 1) / 56)
 // A thread keeps its candidate (and the six map coefficients) for the whole pass.
-template <bool HAD>
+template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int wstride, int w, int cols, int rows)
+                                           int w, int cols, int rows)
 {
   const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
   if (g >= groups || !sh.valid[c]) return;
@@ -281,14 +294,14 @@ __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const
   uint32_t acc = 0;
   for (int tile = g; tile < ntiles; tile += groups) {
     const int tx = (tile % tiles_x) * 4, ty = (tile / tiles_x) * 4;
-    acc += eval_tile4<HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, wstride, w, cols, rows);
+    acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, w, cols, rows);
   }
   atomicAdd(&sh.dist[c], acc);
 }
 
-template <bool HAD>
+template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int wstride, int w, int cols, int rows)
+                                           int w, int cols, int rows)
 {
   const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
   const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = blockDim.x / (2 * GT_CANDS);
@@ -300,18 +313,23 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
   uint32_t acc = 0;
   for (int tile = g; tile < ntiles; tile += groups) {
     const int tx = (tile % tiles_x) * 8, ty = (tile / tiles_x) * 8;
-    acc += eval_half_tile8<HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, wstride, w, cols, rows);
+    acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, w, cols, rows);
   }
   if (!HAD || half == 0) atomicAdd(&sh.dist[c], acc);   // HAD: both lanes hold the tile sums, count once
 }
 
-__host__ __device__ __forceinline__ int gt_win_stride(int win_w)
+// Window row stride classes (in 32-bit words), compile-time so that the 2x2 footprint is one address
+// plus immediates.  WS == 1 (mod 32): (X, Y) -> bank (X + Y) mod 32, so the two lanes of a tile pair
+// (4 rows apart) and the 2x2 footprints of neighbouring candidates spread over the banks.
+// win_w = cols + min(cols, rows) <= 128.
+__host__ __device__ constexpr int gt_stride_class(int win_w)
 {
-  // stride == 8 (mod 32) words: the 2x2 footprints of neighbouring candidates fall into distinct banks
-  return ((win_w + 23) / 32) * 32 + 8;
+  return win_w <= 33 ? 33 : win_w <= 65 ? 65 : win_w <= 97 ? 97 : 129;
 }
+constexpr int gt_class_threads(int) { return GT_THREADS; }
 
-__global__ void __launch_bounds__(GT_THREADS, 2)
+template <int WS>
+__global__ void __launch_bounds__(gt_class_threads(WS), 2)
 k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
              const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out)
 {
@@ -327,9 +345,9 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
   int last_step = nss_window >> 6;                              // :4763 (IT_MAX_NSS_Iteration 6)
   if (last_step == 0) last_step = 1;
   const int win_w = cols + 2 * w, win_h = rows + 2 * w;
-  const int wstride = gt_win_stride(win_w);
   int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
-  uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + rows * cols);
+  uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + ((rows * cols + 3) & ~3));
+  if (win_w > WS) return;   // host picked the wrong stride class (cannot happen through the ABI)
   const int16_t* org = org_buf + job.org_off;
   const int16_t* ref_y = ref_buf + job.ref_off;
   const int max_val = (1 << job.bit_depth) - 1;
@@ -359,12 +377,12 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
     __syncthreads();   // previous pass done with s_win
     // window staging: samples [Hx - w, Hx + w + cols) x [Hy - w, Hy + w + rows) relative to the PU,
     // clamped to [0, 2^bd - 1] (filterCopy first+last, TComInterpolationFilter.cpp:113-154), stored as
-    // the high word of their binary64 value
+    // the high word of their binary64 value (converted once, exact)
     for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
       const int wy = i / win_w, wx = i - wy * win_w;
       int v = ref_y[(Hy - w + wy) * job.ref_stride + (Hx - w + wx)];
       v = min(max(v, 0), max_val);
-      s_win[wy * wstride + wx] = (uint32_t)__double2hiint((double)v);
+      s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
     }
     const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);        // :5345
 
@@ -418,11 +436,11 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
       }
       __syncthreads();
       if (tile_n == 8) {
-        if (job.use_had) run_tasks8<true>(sh, s_org, s_win, wstride, w, cols, rows);
-        else             run_tasks8<false>(sh, s_org, s_win, wstride, w, cols, rows);
+        if (job.use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows);
+        else             run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows);
       } else {
-        if (job.use_had) run_tasks4<true>(sh, s_org, s_win, wstride, w, cols, rows);
-        else             run_tasks4<false>(sh, s_org, s_win, wstride, w, cols, rows);
+        if (job.use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows);
+        else             run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows);
       }
       __syncthreads();
       if (threadIdx.x < 64) {
@@ -486,33 +504,50 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
   }
 }
 
-size_t gt_smem_bytes(int max_cols, int max_rows)
+static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
 {
   const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
-  const size_t win = (size_t)gt_win_stride(max_cols + 2 * w) * (max_rows + 2 * w);
-  return GT_SHARED_BYTES + sizeof(int) * (size_t)max_cols * max_rows + sizeof(uint32_t) * win;
+  const size_t org = ((size_t)max_cols * max_rows + 3) & ~(size_t)3;
+  return GT_SHARED_BYTES + sizeof(int) * org + sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
 }
 
-cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches)
+template <int WS>
+static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                                   HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream)
 {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k2_gt_search, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)gt_smem_bytes(HOP_MAX_PU, HOP_MAX_PU));
+    cudaError_t e = cudaFuncSetAttribute(k2_gt_search<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   // CTA = 56 candidates x `groups` tile groups x (2 lanes per 8x8 tile | 1 lane per 4x4 tile)
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
-  int groups = (max_cols / tile) * (max_rows / tile);
-  if (groups > GT_THREADS / per_group) groups = GT_THREADS / per_group;
+  const int ntiles = (max_cols / tile) * (max_rows / tile);
+  const int max_groups = gt_class_threads(WS) / per_group;
+  int groups = ntiles < max_groups ? ntiles : max_groups;
+  // fewest loop trips wins; on a tie the smaller CTA (less idle lanes in the last trip)
+  for (int g = groups - 1; g >= 1; g--)
+    if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
-  k2_gt_search<<<n, threads, gt_smem_bytes(max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out);
-  if (launches) (*launches)++;
+  k2_gt_search<WS><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out);
   return cudaGetLastError();
+}
+
+cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches)
+{
+  const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
+  if (launches) (*launches)++;
+  switch (gt_stride_class(win_w)) {
+    case 33:  return gt_launch_class<33>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
+    case 65:  return gt_launch_class<65>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
+    case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
+    default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
+  }
 }
 
 }  // namespace hop
