@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--pus", type=int, default=4096, help="PUs per shape per GPU")
     ap.add_argument("--cpu-sample", type=int, default=48, help="PUs per shape in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--k1-pus", type=int, default=256, help="PUs per shape for the secondary K1 (SS full search) measurement; 0 = skip")
     return ap.parse_args()
 
 
@@ -180,6 +181,43 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# secondary: K1 full search (SAD positions/s), reported beside the headline
+# ---------------------------------------------------------------------------------------------------
+def measure_k1(hop, ctx, torch, dev, tstream, pus, peaks):
+    from hevc_hop_b200.workload import PuBatch
+    from hevc_hop_b200.lenslet import lenslet_luma
+    src = lenslet_luma(1024, 1024, seed=99).astype(np.int16)
+    res = {"unit": "SAD positions/s", "per_shape": {}}
+    tot_pos, tot_px, tot_ms = 0, 0, 0.0
+    for i, (c, r) in enumerate(SHAPES):
+        b = PuBatch(c, r, pus, seed=300 + i, source=src)
+        d_jobs = torch.from_numpy(b.search_jobs.view(np.uint8)).to(dev)
+        d_org = torch.from_numpy(b.org.view(np.uint8)).to(dev)
+        d_ref = torch.from_numpy(b.ref.view(np.uint8)).to(dev)
+        d_out = torch.zeros(b.n * hop.SEARCH_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(3):
+            if it == 1:
+                e0.record(tstream)
+            ctx.pattern_search_dev(b.n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_out.data_ptr(), ctx.stream)
+        e1.record(tstream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        j = b.search_jobs[0]
+        npos = int((j["rng_right"] - j["rng_left"] + 1) * (j["rng_bottom"] - j["rng_top"] + 1)) * b.n
+        px = npos * c * (r // 2 if r > 8 else r)
+        res["per_shape"]["%dx%d" % (c, r)] = {"ms": ms, "positions_per_s": npos / (ms * 1e-3), "pixel_sads_per_s": px / (ms * 1e-3)}
+        tot_pos += npos; tot_px += px; tot_ms += ms
+    res["value"] = tot_pos / (tot_ms * 1e-3)
+    res["pixel_sads_per_s"] = tot_px / (tot_ms * 1e-3)
+    res["vabsdiff4_peak_pixel_sads_per_s"] = peaks.get("vabsdiff4", 0) * 4e9
+    res["frac_of_vabsdiff4_peak"] = res["pixel_sads_per_s"] / max(1.0, res["vabsdiff4_peak_pixel_sads_per_s"])
+    res["workload"] = "%d PUs of each of 8x8/16x16/32x32/64x64, SearchRange 128 causal window (257x125 positions), FEN row sub-sampling" % pus
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -318,6 +356,11 @@ def run_ours(args):
     e2e_ms = float(t.item())
     e2e_value = cands_per_step * world / (e2e_ms * 1e-3)
 
+    # secondary measurement (rank 0, outside the headline region): K1 = xPatternSearch, SearchRange 128
+    k1 = None
+    if rank == 0 and args.k1_pus > 0:
+        k1 = measure_k1(hop, ctx, torch, dev, tstream, args.k1_pus, peaks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -376,6 +419,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "parity_spot_check": parity,
+        "k1_sad_search": k1,
     }
     print(json.dumps(line))
     if world > 1:

@@ -225,6 +225,26 @@ const int16_t* hop_ref_origin_dev(HopCtx* ctx)
 // ---------------------------------------------------------------------------------------------
 // device entry points
 // ---------------------------------------------------------------------------------------------
+namespace {
+int k1_slices(const HopCtx* ctx, int n)
+{
+  // enough CTAs to cover the machine a few times: a single in-encoder call spreads one PU's window
+  // over many SMs, a large batch needs no extra split
+  int slices = (2 * ctx->sm_count + n - 1) / n;
+  return slices > K1_MAX_SLICES ? K1_MAX_SLICES : (slices < 1 ? 1 : slices);
+}
+int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+               HopSearchResult* d_out, int smem_bytes, cudaStream_t s)
+{
+  int st = ensure(ctx, ctx->keys, sizeof(unsigned long long) * (size_t)n);
+  if (st) return st;
+  int l = 0;
+  CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, k1_slices(ctx, n), smem_bytes, s, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+}  // namespace
+
 int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org,
                                  const int16_t* d_ref, HopSearchResult* d_out, void* stream)
 {
@@ -233,15 +253,7 @@ int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,
   if (n < 0 || (n > 0 && (!d_jobs || !d_org || !d_ref || !d_out))) return fail(HOP_ERR_ARG, "NULL device buffer");
   if (n == 0) return HOP_OK;
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-  st = ensure(ctx, ctx->keys, sizeof(unsigned long long) * (size_t)n);
-  if (st) return st;
-  // enough CTAs to cover the machine a few times: a single in-encoder call spreads one PU's window
-  // over many SMs, a large batch needs no extra split
-  int slices = (4 * ctx->sm_count + n - 1) / n;
-  int l = 0;
-  CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, slices, s, &l));
-  ctx->launches += l;
-  return HOP_OK;
+  return search_dev(ctx, n, d_jobs, d_org, d_ref, d_out, K1_DEFAULT_SMEM, s);
 }
 
 int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org,
@@ -319,8 +331,14 @@ int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs, const
   st = stage_inputs(ctx, n, jobs, sizeof(HopSearchJob), org, org_samples, ref, ref_samples,
                     sizeof(HopSearchResult) * (size_t)n, &d_ref);
   if (st) return st;
-  st = hop_pattern_search_batch_dev(ctx, n, (const HopSearchJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref,
-                                    (HopSearchResult*)ctx->out.p, ctx->stream);
+  size_t smem = 0;
+  const int slices = k1_slices(ctx, n);
+  for (int i = 0; i < n; i++) {
+    const size_t b = search_smem_bytes(jobs[i], slices);
+    if (b > smem) smem = b;
+  }
+  st = search_dev(ctx, n, (const HopSearchJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref,
+                  (HopSearchResult*)ctx->out.p, (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream);
   if (st) return st;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopSearchResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

@@ -8,6 +8,19 @@
 // strict minimum in raster order" equals the minimum of the 64-bit key (cost << 32 | rasterIndex)
 // over the positions that pass the SS gates.  The window of one PU is split over `slices` CTAs (so a
 // single in-encoder call can use many SMs); CTAs merge through atomicMin on one 64-bit word per PU.
+//
+// Two paths inside one kernel, both on the GPU, both exact:
+//   * byte path (8-bit content): the slice's window is staged ONCE into shared memory as packed bytes
+//     (NOT_VALID -> 0), a thread owns 4 adjacent x positions (the four byte alignments of a word, made
+//     with funnel shifts) x 4 y positions that share reference rows, and accumulates with
+//     VABSDIFF4.U8.ACC (4 pixel-SADs + accumulate per instruction).  The sentinel is handled exactly:
+//     while staging, the CTA records per row where the NOT_VALID samples start and checks that they
+//     form the monotone staircase the SS reference always has (valid set closed to the left and
+//     upwards).  Then a position that passes isValidPattern has no NOT_VALID sample in its footprint,
+//     and positions that fail are discarded by the reference too -- so aliasing -1 with 0 is invisible.
+//   * generic path (any bit depth, any sentinel layout, widths that are no multiple of 4): one thread
+//     per position on the int16 samples.  Taken when the staircase check fails, for 10-bit content, and
+//     for non-SS searches over windows that contain NOT_VALID samples.
 #include "hop_common.cuh"
 #include "hop_internal.h"
 
@@ -19,39 +32,59 @@ __global__ void k1_init_keys(int n, unsigned long long* keys)
   if (i < n) keys[i] = ~0ull;
 }
 
-// v1: one thread per search position, original block in shared memory, reference rows read through
-// the read-only path (adjacent threads read overlapping rows, so L1 serves most of it).
-__global__ void __launch_bounds__(K1_THREADS)
-k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
-          const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys)
+struct K1Geom {            // per-CTA geometry of the slice, identical on host and device
+  int nx, ny, y_lo, y_hi;  // window size, position rows [y_lo, y_hi) of this slice
+  int step, rused;         // row sub-sampling step and number of block rows used
+  int st_rows, st_cols;    // staged rows / columns that the reference itself would touch
+  int sw;                  // staged row stride in bytes (multiple of 16)
+};
+
+__host__ __device__ inline int k1_sub_shift(const HopSearchJob& job)
 {
-  __shared__ int16_t s_org[HOP_MAX_PU * HOP_MAX_PU];
-  __shared__ unsigned long long s_red[32];
-  const int job_id = blockIdx.x;
-  const HopSearchJob job = jobs[job_id];
-  const int cols = job.cols, rows = job.rows;
-  const int nx = job.rng_right - job.rng_left + 1;
-  const int ny = job.rng_bottom - job.rng_top + 1;
-  if (nx <= 0 || ny <= 0) return;
-  int sub_shift = (job.fast_enc && rows > 8) ? 1 : 0;           // TEncSearch.cpp:6303-6309
-  if (!sad_width_has_subshift(cols)) sub_shift = 0;             // generic xGetSAD ignores it
-  const int step = 1 << sub_shift;
-  const int dist_shift = job.bit_depth - 8;
-  const int16_t* org = org_buf + job.org_off;
-  const int16_t* ref_y = ref_buf + job.ref_off;
-  const int stride = job.ref_stride;
+  int s = (job.fast_enc && job.rows > 8) ? 1 : 0;               // TEncSearch.cpp:6303-6309
+  if (!sad_width_has_subshift(job.cols)) s = 0;                 // generic xGetSAD ignores iSubShift
+  return s;
+}
 
-  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
-    s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
-  __syncthreads();
+__host__ __device__ inline K1Geom k1_geom(const HopSearchJob& job, int slice, int slices)
+{
+  K1Geom g;
+  g.nx = job.rng_right - job.rng_left + 1;
+  g.ny = job.rng_bottom - job.rng_top + 1;
+  const int rows_per = (g.ny + slices - 1) / slices;
+  g.y_lo = slice * rows_per;
+  g.y_hi = g.y_lo + rows_per < g.ny ? g.y_lo + rows_per : g.ny;
+  g.step = 1 << k1_sub_shift(job);
+  g.rused = job.rows / g.step;
+  const int ny_s = g.y_hi - g.y_lo;
+  // last block row read is (rused-1)*step; the SS probes add row rows+4 and column cols+4
+  g.st_rows = ny_s + (job.is_ss ? job.rows + 4 : (g.rused - 1) * g.step);
+  g.st_cols = g.nx + (job.is_ss ? job.cols + 4 : job.cols - 1);
+  const int ngx = (g.nx + 3) / 4;
+  g.sw = ((4 * ngx + job.cols + 8) + 15) & ~15;
+  return g;
+}
 
-  // rows of the window handled by this slice
-  const int slices = gridDim.y, slice = blockIdx.y;
-  const int rows_per = (ny + slices - 1) / slices;
-  const int y_lo = slice * rows_per, y_hi = min(ny, y_lo + rows_per);
+__host__ __device__ inline size_t k1_smem_bytes(const HopSearchJob& job, const K1Geom& g)
+{
+  // [staged window bytes][org bytes][first_invalid + invalid count per staged row][bits tables]
+  size_t b = (size_t)g.st_rows * g.sw + 16;
+  b += ((size_t)g.rused * job.cols + 15) & ~(size_t)15;
+  b += sizeof(int) * 2 * (size_t)g.st_rows;
+  b += sizeof(int) * (size_t)(g.nx + (g.y_hi - g.y_lo));
+  return b + 64;
+}
+
+// ---- generic path: one thread per position on the int16 samples -------------------------------
+__device__ __forceinline__ unsigned long long k1_generic(const HopSearchJob& job, const K1Geom& g,
+                                                         const int16_t* __restrict__ org,
+                                                         const int16_t* __restrict__ ref_y)
+{
+  const int cols = job.cols, rows = job.rows, stride = job.ref_stride;
+  const int sub_shift = k1_sub_shift(job), dist_shift = job.bit_depth - 8;
   unsigned long long best = ~0ull;
-  for (int idx = y_lo * nx + threadIdx.x; idx < y_hi * nx; idx += blockDim.x) {
-    const int py = idx / nx, px = idx - py * nx;
+  for (int idx = g.y_lo * g.nx + threadIdx.x; idx < g.y_hi * g.nx; idx += blockDim.x) {
+    const int py = idx / g.nx, px = idx - py * g.nx;
     const int x = job.rng_left + px, y = job.rng_top + py;
     const int16_t* srch = ref_y + (long long)y * stride + x;
     if (job.is_ss) {
@@ -60,11 +93,10 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
       if (__ldg(lb) == HOP_NOT_VALID || __ldg(lb + cols + 4) == HOP_NOT_VALID) continue;   // :6330
     }
     uint32_t sum = 0;
-    for (int r = 0; r < rows; r += step) {
+    for (int r = 0; r < rows; r += g.step) {
       const int16_t* rr = srch + r * stride;
-      const int16_t* oo = s_org + r * cols;
-#pragma unroll 4
-      for (int c = 0; c < cols; c++) sum = __sad((int)oo[c], (int)__ldg(rr + c), sum);
+      const int16_t* oo = org + r * job.org_stride;
+      for (int c = 0; c < cols; c++) sum = __sad((int)__ldg(oo + c), (int)__ldg(rr + c), sum);
     }
     sum <<= sub_shift;
     sum >>= dist_shift;
@@ -72,6 +104,203 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
     const unsigned long long key = ((unsigned long long)sum << 32) | (unsigned)idx;
     best = key < best ? key : best;
   }
+  return best;
+}
+
+__device__ __forceinline__ unsigned vsad4_acc(unsigned a, unsigned b, unsigned c)
+{
+  unsigned d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+constexpr int K1_Q = 4;   // y positions per thread (they share reference rows)
+
+// ---- byte path ----------------------------------------------------------------------------------
+// WORDS = cols / 4 (compile time so that the per-row word loop unrolls)
+template <int WORDS>
+__device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, const K1Geom& g,
+                                                       const unsigned char* __restrict__ s_win,
+                                                       const unsigned* __restrict__ s_org,
+                                                       const int* __restrict__ s_first_invalid,
+                                                       const int* __restrict__ s_bits_x,
+                                                       const int* __restrict__ s_bits_y)
+{
+  const int S = g.step, R = g.rused;
+  const int ny_s = g.y_hi - g.y_lo;
+  const int ngx = (g.nx + 3) / 4;
+  const int sub_shift = k1_sub_shift(job);
+  unsigned long long best = ~0ull;
+  // task = (x group of 4, parity class, group of K1_Q positions of that class)
+  int ntask_y = 0;
+  for (int pi = 0; pi < S; pi++) {
+    const int t_cnt = (ny_s - pi + S - 1) / S;
+    ntask_y += t_cnt > 0 ? (t_cnt + K1_Q - 1) / K1_Q : 0;
+  }
+  const int ntask = ngx * ntask_y;
+  for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+    const int xg = task % ngx;
+    int ty = task / ngx, pi = 0;
+    {   // locate (parity, group) from the flattened y-task index
+      const int t0 = (ny_s + S - 1) / S;
+      const int g0 = t0 > 0 ? (t0 + K1_Q - 1) / K1_Q : 0;
+      if (ty >= g0) { ty -= g0; pi = 1; }
+    }
+    const int q0 = pi + S * (ty * K1_Q);          // first position row (relative to the slice)
+    unsigned acc[4][K1_Q];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int j = 0; j < K1_Q; j++) acc[a][j] = 0;
+    const unsigned char* col0 = s_win + 4 * xg;
+    for (int m = 0; m < R + K1_Q - 1; m++) {
+      const int srow = q0 + S * m;                // staged row of this reference row
+      if (srow >= g.st_rows) break;               // only rows of positions beyond the slice remain
+      const unsigned* rw = reinterpret_cast<const unsigned*>(col0 + (size_t)srow * g.sw);
+      unsigned sh[4][WORDS];
+      unsigned w0 = rw[0];
+#pragma unroll
+      for (int k = 0; k < WORDS; k++) {
+        const unsigned w1 = rw[k + 1];
+        sh[0][k] = w0;
+        sh[1][k] = __funnelshift_r(w0, w1, 8);
+        sh[2][k] = __funnelshift_r(w0, w1, 16);
+        sh[3][k] = __funnelshift_r(w0, w1, 24);
+        w0 = w1;
+      }
+#pragma unroll
+      for (int j = 0; j < K1_Q; j++) {
+        const int r = m - j;                      // block row (in sub-sampled rows) of position j
+        if (r < 0 || r >= R) continue;            // uniform across the CTA
+        const unsigned* ow = s_org + r * WORDS;
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) {
+          const unsigned o = ow[k];
+#pragma unroll
+          for (int a = 0; a < 4; a++) acc[a][j] = vsad4_acc(o, sh[a][k], acc[a][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K1_Q; j++) {
+      const int q = q0 + S * j;                   // position row relative to the slice
+      if (q >= ny_s) continue;
+      const int py = g.y_lo + q, y = job.rng_top + py;
+      const int prow = q + job.rows + 4;          // staged row of the isValidPattern probes
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int px = 4 * xg + a;
+        if (px >= g.nx) continue;
+        const int x = job.rng_left + px;
+        if (job.is_ss) {
+          if ((x >= job.offset_x) && (y > job.offset_y)) continue;          // :6328
+          // staircase window: both probes valid <=> the right one lies left of the row's first NOT_VALID
+          if (px + job.cols + 4 >= s_first_invalid[prow]) continue;         // :6330
+        }
+        unsigned sum = acc[a][j] << sub_shift;
+        sum += (job.cost.lambda_cost * (unsigned)(s_bits_x[px] + s_bits_y[q])) >> 16;   // :6336
+        const unsigned long long key = ((unsigned long long)sum << 32) | (unsigned)(py * g.nx + px);
+        best = key < best ? key : best;
+      }
+    }
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+          const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys, int smem_limit)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ unsigned long long s_red[32];
+  __shared__ int s_unclean;
+  const int job_id = blockIdx.x;
+  const HopSearchJob job = jobs[job_id];
+  const K1Geom g = k1_geom(job, blockIdx.y, gridDim.y);
+  if (g.nx <= 0 || g.ny <= 0 || g.y_lo >= g.y_hi) return;
+  const int16_t* org = org_buf + job.org_off;
+  const int16_t* ref_y = ref_buf + job.ref_off;
+  const int cols = job.cols, rows = job.rows;
+
+  bool bytes_ok = job.bit_depth == 8 && (cols % 4) == 0 && cols <= HOP_MAX_PU && rows <= HOP_MAX_PU &&
+                  k1_smem_bytes(job, g) <= (size_t)smem_limit;
+  unsigned long long best;
+  if (bytes_ok) {
+    unsigned char* s_win = smem;
+    unsigned* s_org = reinterpret_cast<unsigned*>(smem + (((size_t)g.st_rows * g.sw + 15) & ~(size_t)15));
+    int* s_first_invalid = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_org) +
+                                                  (((size_t)g.rused * cols + 15) & ~(size_t)15));
+    int* s_cnt_invalid = s_first_invalid + g.st_rows;
+    int* s_bits_x = s_cnt_invalid + g.st_rows;
+    int* s_bits_y = s_bits_x + g.nx;
+    const int ny_s = g.y_hi - g.y_lo;
+    if (threadIdx.x == 0) s_unclean = 0;
+    for (int i = threadIdx.x; i < g.st_rows; i += blockDim.x) { s_first_invalid[i] = 0x7fffffff; s_cnt_invalid[i] = 0; }
+    // bit-length tables of the motion cost (TComRdCost.h:196-199)
+    for (int i = threadIdx.x; i < g.nx; i += blockDim.x)
+      s_bits_x[i] = (int)component_bits(((job.rng_left + i) << job.cost.cost_scale) - job.cost.pred.hor);
+    for (int i = threadIdx.x; i < ny_s; i += blockDim.x)
+      s_bits_y[i] = (int)component_bits(((job.rng_top + g.y_lo + i) << job.cost.cost_scale) - job.cost.pred.ver);
+    __syncthreads();
+    // original block: the sub-sampled rows, packed to bytes
+    int bad = 0;
+    for (int i = threadIdx.x; i < g.rused * (cols / 4); i += blockDim.x) {
+      const int r = i / (cols / 4), k = i - r * (cols / 4);
+      const int16_t* o = org + (r * g.step) * job.org_stride + 4 * k;
+      unsigned w = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) { const int v = o[b]; bad |= (v < 0) | (v > 255); w |= (unsigned)(v & 255) << (8 * b); }
+      s_org[i] = w;
+    }
+    // reference window of the slice: rows [rng_top + y_lo, ...), columns [rng_left, ...)
+    const int16_t* win0 = ref_y + (long long)(job.rng_top + g.y_lo) * job.ref_stride + job.rng_left;
+    const int wpr = g.sw / 4;
+    for (int i = threadIdx.x; i < g.st_rows * wpr; i += blockDim.x) {
+      const int r = i / wpr, k = i - r * wpr;
+      const int16_t* p = win0 + (long long)r * job.ref_stride + 4 * k;
+      unsigned w = 0;
+      int n_inv = 0, first = 0x7fffffff;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int c = 4 * k + b;
+        int v = 0;
+        if (c < g.st_cols) {                                   // never read what the reference would not
+          v = __ldg(p + b);
+          if (v == HOP_NOT_VALID) { n_inv++; first = first < c ? first : c; v = 0; }
+          else bad |= (v < 0) | (v > 255);
+        }
+        w |= (unsigned)(v & 255) << (8 * b);
+      }
+      reinterpret_cast<unsigned*>(s_win + (size_t)r * g.sw)[k] = w;
+      if (n_inv) { atomicMin(&s_first_invalid[r], first); atomicAdd(&s_cnt_invalid[r], n_inv); }
+    }
+    if (bad) s_unclean = 1;
+    __syncthreads();
+    // staircase check: NOT_VALID samples form a suffix of every row, starting no later than in the row above
+    for (int r = threadIdx.x; r < g.st_rows; r += blockDim.x) {
+      const int first = s_first_invalid[r], cnt = s_cnt_invalid[r];
+      bool ok = cnt == 0 || cnt == g.st_cols - first;
+      if (r > 0 && first > s_first_invalid[r - 1]) ok = false;
+      if (!job.is_ss && cnt != 0) ok = false;                  // no validity gate: footprints may hold -1
+      if (!ok) s_unclean = 1;
+    }
+    __syncthreads();
+    bytes_ok = s_unclean == 0;
+    if (bytes_ok) {
+      switch (cols / 4) {
+        case 1:  best = k1_bytes<1>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 2:  best = k1_bytes<2>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 3:  best = k1_bytes<3>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 4:  best = k1_bytes<4>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 6:  best = k1_bytes<6>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 8:  best = k1_bytes<8>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 12: best = k1_bytes<12>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        case 16: best = k1_bytes<16>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y); break;
+        default: bytes_ok = false; break;
+      }
+    }
+  }
+  if (!bytes_ok) best = k1_generic(job, g, org, ref_y);
   best = block_min_u64(best, s_red);
   if (threadIdx.x == 0 && best != ~0ull) atomicMin(&keys[job_id], best);
 }
@@ -100,16 +329,38 @@ __global__ void k1_finalize(int n, const HopSearchJob* __restrict__ jobs,
 }
 
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                          HopSearchResult* d_out, unsigned long long* d_keys, int slices,
+                          HopSearchResult* d_out, unsigned long long* d_keys, int slices, int smem_bytes,
                           cudaStream_t stream, int* launches)
 {
+  static int attr_set = 0;
+  const int smem_max = 160 * 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k1_search, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) return e;
+    attr_set = 1;
+  }
   if (slices < 1) slices = 1;
   if (slices > K1_MAX_SLICES) slices = K1_MAX_SLICES;
+  if (smem_bytes > smem_max) smem_bytes = smem_max;
+  if (smem_bytes < 1024) smem_bytes = 1024;
   k1_init_keys<<<(n + 255) / 256, 256, 0, stream>>>(n, d_keys);
-  k1_search<<<dim3(n, slices), K1_THREADS, 0, stream>>>(n, d_jobs, d_org, d_ref, d_keys);
+  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, smem_bytes);
   k1_finalize<<<(n + 255) / 256, 256, 0, stream>>>(n, d_jobs, d_keys, d_out);
   if (launches) *launches += 3;
   return cudaGetLastError();
+}
+
+// Shared memory the byte path wants for `job` when its window is cut into `slices` (host side helper).
+size_t search_smem_bytes(const HopSearchJob& job, int slices)
+{
+  size_t worst = 0;
+  for (int s = 0; s < slices; s++) {
+    const K1Geom g = k1_geom(job, s, slices);
+    if (g.y_lo >= g.y_hi) continue;
+    const size_t b = k1_smem_bytes(job, g);
+    if (b > worst) worst = b;
+  }
+  return worst;
 }
 
 }  // namespace hop

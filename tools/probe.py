@@ -1,5 +1,5 @@
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 hop = g.load_package()
 ctx = hop.HopContext(0)
