@@ -117,6 +117,7 @@ ABI = [
     ("hop_shape_supported", C.c_int, [C.c_int, C.c_int]),
     ("hop_ref_create", C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     ("hop_ref_reset", C.c_int, [_P, C.c_int]),
+    ("hop_ref_upload", C.c_int, [_P, _P, C.c_size_t]),
     ("hop_ref_update", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     ("hop_ref_download", C.c_int, [_P, _P, C.c_size_t]),
     ("hop_ref_stride", C.c_int, [_P]),
@@ -206,6 +207,10 @@ class HopContext:
 
     def ref_reset(self, value=HOP_NOT_VALID):
         self._check(self.lib.hop_ref_reset(self.h, value))
+
+    def ref_upload(self, plane):
+        plane = np.ascontiguousarray(plane, dtype=np.int16)
+        self._check(self.lib.hop_ref_upload(self.h, _ptr(plane), plane.size))
 
     def ref_update(self, x, y, block):
         block = np.ascontiguousarray(block, dtype=np.int16)

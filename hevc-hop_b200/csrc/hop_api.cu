@@ -185,6 +185,19 @@ int hop_ref_reset(HopCtx* ctx, int value)
   return HOP_OK;
 }
 
+int hop_ref_upload(HopCtx* ctx, const int16_t* plane, size_t plane_samples)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (!ctx->plane) return fail(HOP_ERR_STATE, "hop_ref_upload before hop_ref_create");
+  size_t samples = (size_t)ctx->stride * (ctx->pic_h + 2 * ctx->margin);
+  if (!plane || plane_samples != samples) return fail(HOP_ERR_ARG, "plane has %zu samples, the mirror %zu", plane_samples, samples);
+  CU(cudaMemcpyAsync(ctx->plane, plane, samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // the host plane may change right after the call
+  ctx->plane_valid = true;
+  return HOP_OK;
+}
+
 int hop_ref_update(HopCtx* ctx, int x, int y, int w, int h, const int16_t* src, int src_stride)
 {
   int st = bind(ctx);

@@ -149,6 +149,8 @@ int  hop_shape_supported(int cols, int rows);
 /* SS reference mirror (K4).  pic_w/pic_h luma size, margin as TComPicYuv (80), stride = pic_w+2*margin. */
 int  hop_ref_create(HopCtx* ctx, int pic_w, int pic_h, int margin);
 int  hop_ref_reset(HopCtx* ctx, int value);       /* setPicPel(NOT_VALID), TComSlice.cpp:253 */
+/* upload a whole host plane incl. margins ((pic_h+2m) x stride samples), e.g. right after the reset */
+int  hop_ref_upload(HopCtx* ctx, const int16_t* plane, size_t plane_samples);
 /* copy a w x h block of reconstruction to (x,y) and re-extend the borders (TEncCu.cpp:1694-1696) */
 int  hop_ref_update(HopCtx* ctx, int x, int y, int w, int h, const int16_t* src, int src_stride);
 /* read back the whole plane incl. margins ((pic_h+2m) x stride samples) -- tests / debugging */

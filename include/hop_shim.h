@@ -1,0 +1,154 @@
+/*
+ * hop_shim.h -- C++ glue between the HM-15 / HEVC-HOP encoder classes and the libhopgpu C ABI.
+ *
+ * Header-only; compiled INSIDE the reference tree (it uses TComPattern, TComMv, TComPicYuv, TComRdCost,
+ * TComDataCU exactly as TEncSearch does).  It keeps the call signatures of
+ *   TEncSearch::xPatternSearch   (TLibEncoder/TEncSearch.h:471-486)
+ *   TEncSearch::xPatternSearchGT (TLibEncoder/TEncSearch.h:488-517)
+ * so that their bodies become one call each (INTEGRATION.md shows the patch).  Error convention of the
+ * reference: no error returns -- a failing GPU call prints to stderr and exits (no CPU fallback).
+ */
+#ifndef HOP_SHIM_H
+#define HOP_SHIM_H
+
+#include <cstdio>
+#include <cstdlib>
+#include "hop_gpu.h"
+
+namespace hopshim {
+
+struct State {
+  HopCtx*    ctx;
+  const Pel* origin;       // host address of sample (0,0) of the mirrored SS reference plane
+  const Pel* buf_lo;       // first / one-past-last host sample of that plane incl. margins
+  const Pel* buf_hi;
+  int        stride;
+  State() : ctx(NULL), origin(NULL), buf_lo(NULL), buf_hi(NULL), stride(0) {}
+};
+
+inline State& state() { static State s; return s; }
+
+inline void check(int status, const char* what)
+{
+  if (status != HOP_OK) {
+    fprintf(stderr, "libhopgpu: %s failed (%d): %s\n", what, status, hop_last_error());
+    exit(EXIT_FAILURE);
+  }
+}
+
+inline HopCtx* ctx()
+{
+  State& s = state();
+  if (!s.ctx) {
+    const char* dev = getenv("HOP_DEVICE");
+    check(hop_ctx_create(dev ? atoi(dev) : 0, &s.ctx), "hop_ctx_create");
+  }
+  return s.ctx;
+}
+
+/* After TComSlice::setRefPicList wired the SS reference of an ISS slice (TEncGOP.cpp:794): the plane was
+ * reset to NOT_VALID and border-extended on the host; mirror it as it is. */
+inline void refReset(TComPicYuv* pic)
+{
+  State& s = state();
+  const int m = pic->getLumaMargin(), w = pic->getWidth(), h = pic->getHeight();
+  check(hop_ref_create(ctx(), w, h, m), "hop_ref_create");
+  const size_t samples = (size_t)pic->getStride() * (h + 2 * m);
+  check(hop_ref_upload(s.ctx, pic->getBufY(), samples), "hop_ref_upload");
+  s.origin = pic->getLumaAddr();
+  s.buf_lo = pic->getBufY();
+  s.buf_hi = pic->getBufY() + samples;
+  s.stride = pic->getStride();
+}
+
+/* After TEncCu::xCopyYuv2SSRef copied a CU's reconstruction and re-extended the borders (TEncCu.cpp:1694-1696) */
+inline void refUpdate(TComPicYuv* pic, int x, int y, int w, int h)
+{
+  State& s = state();
+  if (pic->getLumaAddr() != s.origin) return;     // not the mirrored plane
+  check(hop_ref_update(s.ctx, x, y, w, h, pic->getLumaAddr() + (size_t)y * pic->getStride() + x, pic->getStride()),
+        "hop_ref_update");
+}
+
+inline bool owns(const Pel* p) { const State& s = state(); return s.ctx && p >= s.buf_lo && p < s.buf_hi; }
+
+inline HopCostState costState(TComRdCost* rd)
+{
+  HopCostState c;
+  c.lambda_cost = rd->hopGetCost();
+  c.cost_scale  = rd->hopGetCostScale();
+  c.pred.hor    = rd->hopGetPredictor().getHor();
+  c.pred.ver    = rd->hopGetPredictor().getVer();
+  return c;
+}
+
+/* Body of TEncSearch::xPatternSearch for an SS reference (TEncSearch.cpp:6262-6371). */
+inline void xPatternSearch(TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride, TComMv* pcMvSrchRngLT,
+                           TComMv* pcMvSrchRngRB, TComMv& rcMv, UInt& ruiSAD, Int riOffsetX, Int riOffsetY,
+                           TComMv* ssBestCand, Bool isSSE, Bool useFastEnc, Int bitDepth, TComRdCost* rd)
+{
+  State& s = state();
+  HopSearchJob j;
+  j.org_off = 0;
+  j.ref_off = piRefY - s.origin;
+  j.org_stride = pcPatternKey->getPatternLStride();
+  j.ref_stride = iRefStride;
+  j.cols = pcPatternKey->getROIYWidth();
+  j.rows = pcPatternKey->getROIYHeight();
+  j.rng_left = pcMvSrchRngLT->getHor(); j.rng_top = pcMvSrchRngLT->getVer();
+  j.rng_right = pcMvSrchRngRB->getHor(); j.rng_bottom = pcMvSrchRngRB->getVer();
+  j.offset_x = riOffsetX; j.offset_y = riOffsetY;
+  j.is_ss = isSSE ? 1 : 0;
+  j.fast_enc = useFastEnc ? 1 : 0;
+  j.bit_depth = bitDepth;
+  j.cost = costState(rd);
+  HopSearchResult r;
+  const size_t org_samples = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+  check(hop_pattern_search_batch(s.ctx, 1, &j, pcPatternKey->getROIY(), org_samples, NULL, 0, &r), "hop_pattern_search_batch");
+  if (!r.found) { ruiSAD = MAX_UINT; return; }          // :6356-6360, rcMv / ssBestCand untouched
+  rcMv.set(r.mv.hor, r.mv.ver);                          // :6363
+  ssBestCand[0].set(r.mv.hor, r.mv.ver);                 // :6344 (IT_SS_NUMBER_OF_BEST_CAND 1)
+  ruiSAD = r.sad;                                        // :6365
+}
+
+/* Body of TEncSearch::xPatternSearchGT, diamond branch (TEncSearch.cpp:4686-4790, 5093-5467). */
+inline void xPatternSearchGT(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
+                             TComMv* pcMvInt, TComMv* rcMvHalf, TComMv* rcMvQter, TComMv* rcGT0, TComMv* rcGT1,
+                             TComMv* rcGT2, TComMv* rcGT3, Bool& gtFlag, UInt& ruiCost, TComMv* bestSSCand,
+                             Bool useHADME, Int bitDepth, TComRdCost* rd)
+{
+  State& s = state();
+  HopGtJob j;
+  j.org_off = 0;
+  j.ref_off = piRefY - s.origin;
+  j.org_stride = pcPatternKey->getPatternLStride();
+  j.ref_stride = iRefStride;
+  j.cols = pcPatternKey->getROIYWidth();
+  j.rows = pcPatternKey->getROIYHeight();
+  j.ss_cand.hor = bestSSCand[0].getHor(); j.ss_cand.ver = bestSSCand[0].getVer();
+  AMVPInfo* amvp = pcCU->getCUMvField(REF_PIC_LIST_0)->getAMVPInfo();     // :5100-5104
+  j.num_pred = amvp->iN;
+  for (int i = 0; i < HOP_MAX_PRED; i++) {
+    j.amvp[i].hor = i < amvp->iN ? amvp->m_acMvCand[i].getHor() : 0;
+    j.amvp[i].ver = i < amvp->iN ? amvp->m_acMvCand[i].getVer() : 0;
+  }
+  j.threshold = ruiCost;
+  j.use_had = useHADME ? 1 : 0;
+  j.bit_depth = bitDepth;
+  j.cost = costState(rd);
+  HopGtResult r;
+  const size_t org_samples = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+  check(hop_pattern_search_gt_batch(s.ctx, 1, &j, pcPatternKey->getROIY(), org_samples, NULL, 0, &r), "hop_pattern_search_gt_batch");
+  rcGT0->set(r.gt[0].hor, r.gt[0].ver); rcGT1->set(r.gt[1].hor, r.gt[1].ver);
+  rcGT2->set(r.gt[2].hor, r.gt[2].ver); rcGT3->set(r.gt[3].hor, r.gt[3].ver);
+  gtFlag = r.gt_flag != 0;
+  if (r.gt_flag) {                                       // :5441-5457
+    ruiCost = r.cost;
+    pcMvInt->set(r.mv_int.hor, r.mv_int.ver);
+    rcMvHalf->set(0, 0);
+    rcMvQter->set(0, 0);
+  }
+}
+
+}  // namespace hopshim
+#endif

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Generate the GPU-enabled copies of the four reference files the drop-in touches.
+
+    python integration/patch_reference.py /root/reference/source/Lib  <scratch dir>
+
+Reads the unmodified reference sources where they lie and writes patched copies to the scratch
+directory (never into the repo): the patch is the one INTEGRATION.md documents --
+
+  TLibCommon/TComRdCost.h      + three read-only accessors of the motion-cost state
+  TLibEncoder/TEncSearch.cpp   bodies of xPatternSearch / xPatternSearchGT forward to hop_shim.h
+  TLibEncoder/TEncCu.cpp       xCopyYuv2SSRef notifies the device mirror after the CU copy
+  TLibEncoder/TEncGOP.cpp      the mirror is (re)loaded when the SS reference is wired to the slice
+
+Every edit is anchored on an exact line of the reference; the script fails loudly if an anchor moved.
+"""
+import os
+import sys
+
+
+def patch(text, anchor, insert, where="after", count=1):
+    n = text.count(anchor)
+    if n != count:
+        raise SystemExit("anchor %r found %d times (expected %d)" % (anchor[:60], n, count))
+    if where == "after":
+        return text.replace(anchor, anchor + insert)
+    return text.replace(anchor, insert + anchor)
+
+
+def main():
+    src, out = sys.argv[1], sys.argv[2]
+    rd = lambda p: open(os.path.join(src, p), encoding="latin-1").read()
+
+    def wr(p, t):
+        os.makedirs(os.path.dirname(os.path.join(out, p)), exist_ok=True)
+        open(os.path.join(out, p), "w", encoding="latin-1").write(t)
+
+    # --- TComRdCost.h: accessors (inline, no layout change) ---------------------------------------
+    t = rd("TLibCommon/TComRdCost.h")
+    t = patch(t, "};// END CLASS DEFINITION TComRdCost",
+              "public:\n"
+              "  // libhopgpu: read-only view of the motion-cost state used by getCost()/getBits()\n"
+              "  UInt          hopGetCost()      const { return m_uiCost; }\n"
+              "  Int           hopGetCostScale() const { return m_iCostScale; }\n"
+              "  const TComMv& hopGetPredictor() const { return m_mvPredictor; }\n", where="before")
+    wr("TLibCommon/TComRdCost.h", t)
+
+    # --- TEncSearch.cpp ---------------------------------------------------------------------------
+    t = rd("TLibEncoder/TEncSearch.cpp")
+    t = patch(t, '#include "TEncSearch.h"\n', '#include "hop_shim.h"   // libhopgpu\n')
+    t = patch(t,
+              "  UInt  uiSad;\n  UInt  uiSadBest         = MAX_UINT;\n  Int   iBestX = 0;\n  Int   iBestY = 0;\n  \n  Pel*  piRefSrch;\n",
+              "  // libhopgpu: the SS full search runs on the GPU mirror of the SS reference\n"
+              "  if ( isSSE && hopshim::owns( piRefY ) )\n"
+              "  {\n"
+              "    hopshim::xPatternSearch( pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD,\n"
+              "                             riOffsetX, riOffsetY, ssBestCand, isSSE, m_pcEncCfg->getUseFastEnc(), g_bitDepthY, m_pcRdCost );\n"
+              "    return;\n"
+              "  }\n", where="before")
+    t = patch(t,
+              "\t//gtFlag = true;\n\trcGT0->set(0,0);\n",
+              "\t// libhopgpu: the HOP / geometric-transform candidate search runs on the GPU\n"
+              "\tif ( hopshim::owns( piRefY ) )\n"
+              "\t{\n"
+              "\t\thopshim::xPatternSearchGT( pcCU, pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, rcGT0, rcGT1, rcGT2, rcGT3,\n"
+              "\t\t                           gtFlag, ruiCost, bestSSCand, m_pcEncCfg->getUseHADME(), g_bitDepthY, m_pcRdCost );\n"
+              "\t\treturn;\n"
+              "\t}\n", where="before")
+    wr("TLibEncoder/TEncSearch.cpp", t)
+
+    # --- TEncCu.cpp -------------------------------------------------------------------------------
+    t = rd("TLibEncoder/TEncCu.cpp")
+    t = patch(t, '#include "TEncCu.h"\n', '#include "hop_shim.h"   // libhopgpu\n')
+    t = patch(t,
+              "    rpcPic->getPicYuvRec()->setBorderExtension(false);\n    rpcPic->getPicYuvRec()->extendPicBorder();\n",
+              "    hopshim::refUpdate( rpcPic->getPicYuvRec(), uiLPelX, uiTPelY, g_uiMaxCUWidth>>uiDepth, g_uiMaxCUHeight>>uiDepth );   // libhopgpu\n")
+    wr("TLibEncoder/TEncCu.cpp", t)
+
+    # --- TEncGOP.cpp ------------------------------------------------------------------------------
+    t = rd("TLibEncoder/TEncGOP.cpp")
+    t = patch(t, '#include "TEncGOP.h"\n', '#include "hop_shim.h"   // libhopgpu\n')
+    t = patch(t,
+              "    pcSlice->setRefPicList ( rcListPic, m_pcEncTop->getSSRefEncoder() );\n",
+              "    if ( pcSlice->isIntraSS() ) hopshim::refReset( m_pcEncTop->getSSRefEncoder()->getPicYuvRec() );   // libhopgpu\n")
+    wr("TLibEncoder/TEncGOP.cpp", t)
+    print("patched sources written to", out)
+
+
+if __name__ == "__main__":
+    main()
