@@ -13,9 +13,38 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include "hop_gpu.h"
 
 namespace hopshim {
+
+/* HOP_STATS=1: wall time spent inside the library per entry point, printed when the encoder exits */
+struct Stats {
+  double   sec[4];
+  unsigned long long calls[4];
+  bool     on;
+  Stats() : on(getenv("HOP_STATS") != NULL) { for (int i = 0; i < 4; i++) { sec[i] = 0; calls[i] = 0; } }
+  ~Stats()
+  {
+    if (!on) return;
+    static const char* name[4] = {"xPatternSearch", "xPatternSearchGT", "refUpdate", "refReset"};
+    for (int i = 0; i < 4; i++)
+      fprintf(stderr, "hopshim: %-18s %9llu calls %9.3f s (%.1f us/call)\n", name[i], calls[i], sec[i],
+              calls[i] ? 1e6 * sec[i] / calls[i] : 0.0);
+  }
+};
+inline Stats& stats() { static Stats s; return s; }
+struct Timer {
+  int k; timespec t0;
+  explicit Timer(int kind) : k(kind) { if (stats().on) clock_gettime(CLOCK_MONOTONIC, &t0); }
+  ~Timer()
+  {
+    if (!stats().on) return;
+    timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+    stats().sec[k] += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    stats().calls[k]++;
+  }
+};
 
 struct State {
   HopCtx*    ctx;
@@ -50,6 +79,7 @@ inline HopCtx* ctx()
  * reset to NOT_VALID and border-extended on the host; mirror it as it is. */
 inline void refReset(TComPicYuv* pic)
 {
+  Timer tm(3);
   State& s = state();
   const int m = pic->getLumaMargin(), w = pic->getWidth(), h = pic->getHeight();
   check(hop_ref_create(ctx(), w, h, m), "hop_ref_create");
@@ -66,6 +96,7 @@ inline void refUpdate(TComPicYuv* pic, int x, int y, int w, int h)
 {
   State& s = state();
   if (pic->getLumaAddr() != s.origin) return;     // not the mirrored plane
+  Timer tm(2);
   check(hop_ref_update(s.ctx, x, y, w, h, pic->getLumaAddr() + (size_t)y * pic->getStride() + x, pic->getStride()),
         "hop_ref_update");
 }
@@ -87,6 +118,7 @@ inline void xPatternSearch(TComPattern* pcPatternKey, Pel* piRefY, Int iRefStrid
                            TComMv* pcMvSrchRngRB, TComMv& rcMv, UInt& ruiSAD, Int riOffsetX, Int riOffsetY,
                            TComMv* ssBestCand, Bool isSSE, Bool useFastEnc, Int bitDepth, TComRdCost* rd)
 {
+  Timer tm(0);
   State& s = state();
   HopSearchJob j;
   j.org_off = 0;
@@ -117,6 +149,7 @@ inline void xPatternSearchGT(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* p
                              TComMv* rcGT2, TComMv* rcGT3, Bool& gtFlag, UInt& ruiCost, TComMv* bestSSCand,
                              Bool useHADME, Int bitDepth, TComRdCost* rd)
 {
+  Timer tm(1);
   State& s = state();
   HopGtJob j;
   j.org_off = 0;
