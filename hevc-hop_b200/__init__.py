@@ -21,6 +21,7 @@ HOP_NOT_VALID = -1
 HOP_DF_SAD = 8
 HOP_DF_HADS = 22
 HOP_MAX_PRED = 3
+HOP_SWEEP_CANDS = 7200
 
 
 class HopError(RuntimeError):
@@ -128,6 +129,9 @@ ABI = [
     ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     ("hop_dist_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    ("hop_gt_sweep_keys_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    ("hop_gt_sweep_finalize_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    ("hop_gt_sweep_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_ctx_launch_count", C.c_uint64, [_P]),
     ("hop_probe_alu", C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
@@ -254,6 +258,22 @@ class HopContext:
 
     def dist_dev(self, n, d_jobs, d_org, d_cur, d_out, stream=None):
         self._check(self.lib.hop_dist_batch_dev(self.h, n, d_jobs, d_org, d_cur, d_out, stream))
+
+    # ---- exhaustive sweep ----
+    def gt_sweep(self, jobs, org, ref):
+        jobs = np.ascontiguousarray(jobs, dtype=GT_JOB_DT)
+        out = np.zeros(len(jobs), dtype=GT_RES_DT)
+        self._check(self.lib.hop_gt_sweep_batch(
+            self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
+        return out
+
+    def gt_sweep_keys_dev(self, n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, d_keys, d_counts=None,
+                          stream=None):
+        self._check(self.lib.hop_gt_sweep_keys_dev(self.h, n, d_jobs, d_org, d_ref, max_cols, max_rows,
+                                                   cand_begin, cand_end, d_keys, d_counts, stream))
+
+    def gt_sweep_finalize_dev(self, n, d_jobs, d_keys, d_counts, d_out, stream=None):
+        self._check(self.lib.hop_gt_sweep_finalize_dev(self.h, n, d_jobs, d_keys, d_counts, d_out, stream))
 
     def probe_alu(self, what):
         g, ms = C.c_double(), C.c_double()

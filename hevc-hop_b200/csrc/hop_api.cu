@@ -80,6 +80,22 @@ int shape_ok(int cols, int rows)
 }
 
 bool g_table_ready[64] = {false};
+bool g_sweep_ready[64] = {false};
+
+int sweep_table_ready(HopCtx* ctx)
+{
+  if (ctx->device < 64 && g_sweep_ready[ctx->device]) return HOP_OK;
+  SweepCand* table = new (std::nothrow) SweepCand[SWEEP_CANDS];
+  if (!table) return fail(HOP_ERR_NOMEM, "out of host memory");
+  int count = 0;
+  sweep_build_table(table, &count);
+  if (count != SWEEP_CANDS) { delete[] table; return fail(HOP_ERR_STATE, "sweep table has %d entries, expected %d", count, SWEEP_CANDS); }
+  cudaError_t e = sweep_upload_table(table);
+  delete[] table;
+  if (e != cudaSuccess) return fail(HOP_ERR_CUDA, "sweep table upload: %s", cudaGetErrorString(e));
+  if (ctx->device < 64) g_sweep_ready[ctx->device] = true;
+  return HOP_OK;
+}
 
 }  // namespace
 
@@ -404,6 +420,83 @@ int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs, const int16_t* or
                           (uint32_t*)ctx->out.p, ctx->stream);
   if (st) return st;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exhaustive sweep
+// ---------------------------------------------------------------------------------------------
+int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                          int max_cols, int max_rows, int cand_begin, int cand_end,
+                          uint64_t* d_keys, uint32_t* d_counts, void* stream)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!d_jobs || !d_org || !d_ref || !d_keys))) return fail(HOP_ERR_ARG, "NULL device buffer");
+  if (max_cols < 4 || max_cols > HOP_MAX_PU || max_rows < 4 || max_rows > HOP_MAX_PU)
+    return fail(HOP_ERR_ARG, "shape bound %dx%d out of range", max_cols, max_rows);
+  if (cand_begin < 0 || cand_end > SWEEP_CANDS || cand_begin > cand_end)
+    return fail(HOP_ERR_ARG, "candidate slice [%d,%d) outside [0,%d]", cand_begin, cand_end, SWEEP_CANDS);
+  if (n == 0) return HOP_OK;
+  if ((st = sweep_table_ready(ctx))) return st;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int l = 0;
+  CU(sweep_init_launch(n, (unsigned long long*)d_keys, d_counts, s, &l));
+  if (cand_end > cand_begin) {
+    const int batches = (cand_end - cand_begin + GT_CANDS - 1) / GT_CANDS;
+    int chunks = (2 * ctx->sm_count + n - 1) / n;      // spread one PU's candidate batches over the machine
+    if (chunks > batches) chunks = batches;
+    if (chunks < 1) chunks = 1;
+    CU(sweep_keys_launch(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks,
+                         (unsigned long long*)d_keys, d_counts, s, &l));
+  }
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+int hop_gt_sweep_finalize_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const uint64_t* d_keys,
+                              const uint32_t* d_counts, HopGtResult* d_out, void* stream)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!d_jobs || !d_keys || !d_out))) return fail(HOP_ERR_ARG, "NULL device buffer");
+  if (n == 0) return HOP_OK;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int l = 0;
+  CU(sweep_finalize_launch(n, d_jobs, (const unsigned long long*)d_keys, d_counts, d_out, s, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+int hop_gt_sweep_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* org, size_t org_samples,
+                       const int16_t* ref, size_t ref_samples, HopGtResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  int max_cols = 4, max_rows = 4;
+  for (int i = 0; i < n; i++) {
+    const HopGtJob& j = jobs[i];
+    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 14)
+      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d", i, j.cols, j.rows, j.bit_depth);
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+  }
+  const int16_t* d_ref = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,
+                    sizeof(HopGtResult) * (size_t)n, &d_ref);
+  if (st) return st;
+  if ((st = ensure(ctx, ctx->keys, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)n + 16))) return st;
+  uint64_t* d_keys = (uint64_t*)ctx->keys.p;
+  uint32_t* d_counts = (uint32_t*)(d_keys + n);
+  st = hop_gt_sweep_keys_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, max_cols, max_rows,
+                             0, SWEEP_CANDS, d_keys, d_counts, ctx->stream);
+  if (st) return st;
+  st = hop_gt_sweep_finalize_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, d_keys, d_counts, (HopGtResult*)ctx->out.p, ctx->stream);
+  if (st) return st;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopGtResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
 }

@@ -16,6 +16,17 @@ void        gt_build_offset_table(int8_t table[GT_CANDS][8], int* count);
 cudaError_t gt_upload_offset_table(const int8_t table[GT_CANDS][8]);
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                       HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);
+// exhaustive sweep (reference mode IT_GT_SEARCH 1, N = 2): 85^2 - 25 parallelogram offset patterns
+constexpr int SWEEP_CANDS = 7200;
+struct SweepCand { int8_t o[8]; uint32_t flat; };   // x0,y0,...,x3,y3 in [-2,2]; flat 8-deep loop index
+void        sweep_build_table(SweepCand* table, int* count);
+cudaError_t sweep_upload_table(const SweepCand* table);
+cudaError_t sweep_init_launch(int n, unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches);
+cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                              int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
+                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches);
+cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,
+                                  const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches);
 // K1
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, int slices, int smem_bytes,

@@ -162,10 +162,10 @@ __device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int
 template <int WS, bool HAD>
 __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, double h1, double h4, double h7,
                                                int tx, int ty, const int* __restrict__ org,
-                                               const uint32_t* __restrict__ win, int w, int cols, int rows)
+                                               const uint32_t* __restrict__ win, int w, int cols, int rows,
+                                               int off_x, int off_y)
 {
-  constexpr int N = 4;
-  const int off_x = cols >> 1, off_y = rows >> 1;          // W/2 - W/4 with W = 2*cols
+  constexpr int N = 4;   // off_x/off_y: W/2 - W/4 with W = 2*cols on the 2x grid, 0 on the 1x grid (sweep)
   const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
   const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
   double h0x[N], h1x[N];
@@ -202,9 +202,9 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
 template <int WS, bool HAD>
 __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double h6, double h1, double h4, double h7,
                                                     int tx, int ty, int half, const int* __restrict__ org,
-                                                    const uint32_t* __restrict__ win, int w, int cols, int rows)
+                                                    const uint32_t* __restrict__ win, int w, int cols, int rows,
+                                                    int off_x, int off_y)
 {
-  const int off_x = cols >> 1, off_y = rows >> 1;
   const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
   const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
   const int y0 = ty + 4 * half;
@@ -284,7 +284,7 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
 // A thread keeps its candidate (and the six map coefficients) for the whole pass.
 template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int w, int cols, int rows)
+                                           int w, int cols, int rows, int off_x, int off_y)
 {
   const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
   if (g >= groups || !sh.valid[c]) return;
@@ -294,14 +294,14 @@ __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const
   uint32_t acc = 0;
   for (int tile = g; tile < ntiles; tile += groups) {
     const int tx = (tile % tiles_x) * 4, ty = (tile / tiles_x) * 4;
-    acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, w, cols, rows);
+    acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, w, cols, rows, off_x, off_y);
   }
   atomicAdd(&sh.dist[c], acc);
 }
 
 template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int w, int cols, int rows)
+                                           int w, int cols, int rows, int off_x, int off_y)
 {
   const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
   const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = blockDim.x / (2 * GT_CANDS);
@@ -313,9 +313,22 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
   uint32_t acc = 0;
   for (int tile = g; tile < ntiles; tile += groups) {
     const int tx = (tile % tiles_x) * 8, ty = (tile / tiles_x) * 8;
-    acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, w, cols, rows);
+    acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, w, cols, rows, off_x, off_y);
   }
   if (!HAD || half == 0) atomicAdd(&sh.dist[c], acc);   // HAD: both lanes hold the tile sums, count once
+}
+
+template <int WS>
+__device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const uint32_t* s_win, int w,
+                                          int cols, int rows, int off_x, int off_y, int tile_n, int use_had)
+{
+  if (tile_n == 8) {
+    if (use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
+    else         run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
+  } else {
+    if (use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
+    else         run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
+  }
 }
 
 // Window row stride classes (in 32-bit words), compile-time so that the 2x2 footprint is one address
@@ -435,13 +448,7 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
         }
       }
       __syncthreads();
-      if (tile_n == 8) {
-        if (job.use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows);
-        else             run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows);
-      } else {
-        if (job.use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows);
-        else             run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows);
-      }
+      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had);
       __syncthreads();
       if (threadIdx.x < 64) {
         // ordered argmin with the carried threshold: the serial loop keeps the FIRST strict minimum in
@@ -504,6 +511,195 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
   }
 }
 
+// ---- exhaustive sweep (reference mode IT_GT_SEARCH 1 + IT_GT_GRID_SIZE 1) ------------------------
+// TEncSearch.cpp:4989-5091: one pass over the 25^4 corner sets around the initial rectangle of the 1x
+// grid; the 7200 parallelogram patterns (in loop order, with their flat loop index) sit in a device
+// table, a slice [cand_begin, cand_end) of which is evaluated -- the unit the multi-GPU sweep shards.
+// Candidates are processed in batches of 56 with the task machinery of the diamond search; the CTA's
+// partial argmin (cost << 32 | flat loop index) is merged with atomicMin into one word per PU.
+__device__ SweepCand d_sweep_table[SWEEP_CANDS];
+
+cudaError_t sweep_upload_table(const SweepCand* table)
+{
+  return cudaMemcpyToSymbol(d_sweep_table, table, sizeof(SweepCand) * SWEEP_CANDS);
+}
+
+void sweep_build_table(SweepCand* table, int* count)
+{
+  int n = 0;
+  const int N = 2;
+  for (int y0 = -N; y0 <= N; y0++) for (int x0 = -N; x0 <= N; x0++)
+  for (int y1 = -N; y1 <= N; y1++) for (int x1 = -N; x1 <= N; x1++)
+  for (int y2 = -N; y2 <= N; y2++) for (int x2 = -N; x2 <= N; x2++)
+  for (int y3 = -N; y3 <= N; y3++) for (int x3 = -N; x3 <= N; x3++) {
+    if (x0 == x1 && x0 == x2 && x0 == x3 && y0 == y1 && y0 == y2 && y0 == y3) continue;   // :5017
+    if (x0 - x1 + x2 - x3 != 0 || y0 - y1 + y2 - y3 != 0) continue;                        // not affine
+    if (n < SWEEP_CANDS) {
+      SweepCand& c = table[n];
+      c.o[0] = x0; c.o[1] = y0; c.o[2] = x1; c.o[3] = y1; c.o[4] = x2; c.o[5] = y2; c.o[6] = x3; c.o[7] = y3;
+      c.flat = (uint32_t)((((((((y0 + N) * 5 + (x0 + N)) * 5 + (y1 + N)) * 5 + (x1 + N)) * 5 + (y2 + N)) * 5 +
+                            (x2 + N)) * 5 + (y3 + N)) * 5 + (x3 + N));
+    }
+    n++;
+  }
+  *count = n;
+}
+
+template <int WS>
+__global__ void __launch_bounds__(gt_class_threads(WS), 2)
+k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+            const int16_t* __restrict__ ref_buf, int cand_begin, int cand_end,
+            unsigned long long* __restrict__ keys, unsigned int* __restrict__ counts)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
+  __shared__ uint32_t s_flat[GT_CANDS];
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  const HopGtJob job = jobs[job_id];
+  const int cols = job.cols, rows = job.rows;
+  const int w = (rows < cols ? rows : cols) >> 1;               // iNSSWindow on the 1x grid (:4756)
+  const int win_w = cols + 2 * w, win_h = rows + 2 * w;
+  int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
+  uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + ((rows * cols + 3) & ~3));
+  if (win_w > WS) return;
+  const int16_t* org = org_buf + job.org_off;
+  const int16_t* ref_y = ref_buf + job.ref_off;
+  const int max_val = (1 << job.bit_depth) - 1;
+  const int dist_shift = job.bit_depth - 8;
+  const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
+  const int mvx = job.ss_cand.hor, mvy = job.ss_cand.ver;       // pcMvInt
+  const int Hor = (int16_t)(mvx << 2), Ver = (int16_t)(mvy << 2);   // :4713-4724 with half = quarter = 0
+
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+    s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
+  for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
+    const int wy = i / win_w, wx = i - wy * win_w;
+    int v = ref_y[(mvy - w + wy) * job.ref_stride + (mvx - w + wx)];
+    v = min(max(v, 0), max_val);
+    s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
+  }
+  const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);          // :5035
+  unsigned long long best = ~0ull;
+  unsigned int scored = 0;
+
+  const int n_batches = (cand_end - cand_begin + GT_CANDS - 1) / GT_CANDS;
+  for (int batch = blockIdx.y; batch < n_batches; batch += gridDim.y) {
+    __syncthreads();
+    if (threadIdx.x < GT_CANDS) {
+      const int c = threadIdx.x, idx = cand_begin + batch * GT_CANDS + c;
+      int ok = 0;
+      if (idx < cand_end) {
+        const SweepCand sc = d_sweep_table[idx];
+        const int ox[4] = {sc.o[0], sc.o[2], sc.o[4], sc.o[6]}, oy[4] = {sc.o[1], sc.o[3], sc.o[5], sc.o[7]};
+        const int cx[4] = {ox[0], cols - 1 + ox[1], cols - 1 + ox[2], ox[3]};               // :4781-4784
+        const int cy[4] = {oy[0], oy[1], rows - 1 + oy[2], rows - 1 + oy[3]};
+        // valid GT location, marginX = marginY = 0 (:5020-5023)
+        const int ax[4] = {ox[0] + mvx, ox[1] + mvx + cols, ox[2] + mvx + cols, ox[3] + mvx};
+        const int ay[4] = {oy[0] + mvy, oy[1] + mvy, oy[2] + mvy + rows, oy[3] + mvy + rows};
+        ok = 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) ok &= ((ax[k] < 0 && ay[k] <= 0) || (ax[k] >= 0 && ay[k] < 0)) ? 1 : 0;
+        if (ok) {
+          // calcParamProjective(iCurrCornerX, iCurrCornerY, dProjective, iCols, iRows), TComPrediction.cpp:807-832
+          const double Wd = __dsub_rn((double)cols, 1.0), Hd = __dsub_rn((double)rows, 1.0);
+          const double dx1 = __dsub_rn((double)cx[1], (double)cx[2]);
+          const double dx2 = __dsub_rn((double)cx[3], (double)cx[2]);
+          const double dx3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cx[0], (double)cx[1]), (double)cx[2]), (double)cx[3]);
+          const double dy1 = __dsub_rn((double)cy[1], (double)cy[2]);
+          const double dy2 = __dsub_rn((double)cy[3], (double)cy[2]);
+          const double dy3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cy[0], (double)cy[1]), (double)cy[2]), (double)cy[3]);
+          const double den = __dsub_rn(__dmul_rn(dx1, dy2), __dmul_rn(dx2, dy1));
+          const double h2 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx3, dy2), __dmul_rn(dx2, dy3)), den), Wd);
+          const double h5 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx1, dy3), __dmul_rn(dx3, dy1)), den), Hd);
+          ok = (h2 == 0.0 && h5 == 0.0) ? 1 : 0;                                             // :5028
+          if (ok) {
+            sh.h0[c] = __dadd_rn(__ddiv_rn((double)(cx[1] - cx[0]), Wd), __dmul_rn(h2, (double)cx[1]));
+            sh.h3[c] = __dadd_rn(__ddiv_rn((double)(cx[3] - cx[0]), Hd), __dmul_rn(h5, (double)cx[3]));
+            sh.h6[c] = (double)cx[0];
+            sh.h1[c] = __dadd_rn(__ddiv_rn((double)(cy[1] - cy[0]), Wd), __dmul_rn(h2, (double)cy[1]));
+            sh.h4[c] = __dadd_rn(__ddiv_rn((double)(cy[3] - cy[0]), Hd), __dmul_rn(h5, (double)cy[3]));
+            sh.h7[c] = (double)cy[0];
+            const uint32_t gb = gt_bits(cx[0], cy[0], cx[1] - cols + 1, cy[1], cx[2] - cols + 1, cy[2] - rows + 1);
+            sh.add_cost[c] = mv_add + bits_cost(job.cost, gb);                                // :5035-5041
+            s_flat[c] = sc.flat;
+          }
+        }
+      }
+      sh.valid[c] = ok;
+      sh.dist[c] = 0;
+    }
+    __syncthreads();
+    run_tasks<WS>(sh, s_org, s_win, w, cols, rows, 0, 0, tile_n, job.use_had);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int c = threadIdx.x;
+      const bool ok = c < GT_CANDS && sh.valid[c];
+      unsigned long long key = ok ? ((unsigned long long)((sh.dist[c] >> dist_shift) + sh.add_cost[c]) << 32) | s_flat[c] : ~0ull;
+      const unsigned n_ok = __popc(__ballot_sync(0xffffffffu, ok));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other < key ? other : key;
+      }
+      if ((threadIdx.x & 31) == 0) { sh.red_key[threadIdx.x >> 5] = key; sh.red_cnt[threadIdx.x >> 5] = n_ok; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long key = sh.red_key[0] < sh.red_key[1] ? sh.red_key[0] : sh.red_key[1];
+      best = key < best ? key : best;
+      scored += sh.red_cnt[0] + sh.red_cnt[1];
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (best != ~0ull) atomicMin(&keys[job_id], best);
+    if (counts && scored) atomicAdd(&counts[job_id], scored);
+  }
+}
+
+__global__ void k2_sweep_init(int n, unsigned long long* keys, unsigned int* counts)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = ~0ull; if (counts) counts[i] = 0; }
+}
+
+// key -> the outputs xPatternSearchGT (mode 1) leaves (:5070-5090)
+__global__ void k2_sweep_finalize(int n, const HopGtJob* __restrict__ jobs, const unsigned long long* __restrict__ keys,
+                                  const unsigned int* __restrict__ counts, HopGtResult* __restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HopGtJob job = jobs[i];
+  const unsigned long long key = keys[i];
+  const int cols = job.cols, rows = job.rows, N = 2;
+  HopGtResult r;
+  r.gt_flag = 0;
+  for (int k = 0; k < 4; k++) { r.gt[k].hor = 0; r.gt[k].ver = 0; }
+  r.cost = job.threshold;
+  r.mv_int.hor = 0; r.mv_int.ver = 0;
+  r.best_index = -1;
+  r.n_candidates = counts ? counts[i] : 0;
+  if (key != ~0ull && (uint32_t)(key >> 32) < job.threshold) {                               // uiDist < uiDistBest
+    uint32_t flat = (uint32_t)key;
+    int o[8];
+    for (int k = 7; k >= 0; k--) { o[k] = (int)(flat % 5) - N; flat /= 5; }                 // y0,x0,...,y3,x3
+    const int bx[4] = {o[1], cols - 1 + o[3], cols - 1 + o[5], o[7]};
+    const int by[4] = {o[0], o[2], rows - 1 + o[4], rows - 1 + o[6]};
+    int any = 0;
+    for (int k = 0; k < 4; k++) any |= bx[k] | by[k];
+    if (any) {
+      r.gt_flag = 1;
+      r.gt[0].hor = (int16_t)bx[0];              r.gt[0].ver = (int16_t)by[0];
+      r.gt[1].hor = (int16_t)(bx[1] - cols + 1); r.gt[1].ver = (int16_t)by[1];
+      r.gt[2].hor = (int16_t)(bx[2] - cols + 1); r.gt[2].ver = (int16_t)(by[2] - rows + 1);
+      r.gt[3].hor = (int16_t)bx[3];              r.gt[3].ver = (int16_t)(by[3] - rows + 1);
+      r.cost = (uint32_t)(key >> 32);
+      r.best_index = (int32_t)(uint32_t)key;
+    }
+  }
+  out[i] = r;
+}
+
 static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
 {
   const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
@@ -548,6 +744,61 @@ cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const
     case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
     default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
   }
+}
+
+template <int WS>
+static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                                      int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
+                                      unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k2_gt_sweep<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
+  const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
+  const int ntiles = (max_cols / tile) * (max_rows / tile);
+  const int max_groups = gt_class_threads(WS) / per_group;
+  int groups = ntiles < max_groups ? ntiles : max_groups;
+  for (int g = groups - 1; g >= 1; g--)
+    if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
+  int threads = per_group * groups;
+  if (threads < 64) threads = 64;
+  k2_gt_sweep<WS><<<dim3(n, chunks), threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(
+      n, d_jobs, d_org, d_ref, cand_begin, cand_end, d_keys, d_counts);
+  return cudaGetLastError();
+}
+
+cudaError_t sweep_init_launch(int n, unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches)
+{
+  k2_sweep_init<<<(n + 255) / 256, 256, 0, stream>>>(n, d_keys, d_counts);
+  if (launches) (*launches)++;
+  return cudaGetLastError();
+}
+
+cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                              int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
+                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches)
+{
+  const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
+  if (launches) (*launches)++;
+  switch (gt_stride_class(win_w)) {
+    case 33:  return sweep_launch_class<33>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
+    case 65:  return sweep_launch_class<65>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
+    case 97:  return sweep_launch_class<97>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
+    default:  return sweep_launch_class<129>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
+  }
+}
+
+cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,
+                                  const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches)
+{
+  k2_sweep_finalize<<<(n + 255) / 256, 256, 0, stream>>>(n, d_jobs, d_keys, d_counts, d_out);
+  if (launches) (*launches)++;
+  return cudaGetLastError();
 }
 
 }  // namespace hop

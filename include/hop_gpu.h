@@ -188,6 +188,24 @@ int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs,
                        const int16_t* d_org, const int16_t* d_cur,
                        uint32_t* d_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Exhaustive HOP parameter sweep -- the reference's compile-time search mode IT_GT_SEARCH 1
+ * ("square unit search", N = 2: 25^4 corner sets around the initial rectangle) as it builds with
+ * IT_GT_GRID_SIZE 1 (TEncSearch.cpp:4989-5091, TypeDef.h:216,228).  Job = HopGtJob with ss_cand = pcMvInt
+ * (half = quarter = 0; amvp ignored).  The HOP_SWEEP_CANDS affine corner sets are indexed in loop order;
+ * a slice [cand_begin, cand_end) yields per PU the partial argmin key (cost << 32 | flat loop index,
+ * all-ones when nothing scored) -- the words a multi-GPU run min-reduces (ncclMin) before finalize.
+ * ------------------------------------------------------------------------------------------- */
+#define HOP_SWEEP_CANDS 7200
+int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                          int max_cols, int max_rows, int cand_begin, int cand_end,
+                          uint64_t* d_keys, uint32_t* d_counts /* may be NULL */, void* stream);
+int hop_gt_sweep_finalize_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const uint64_t* d_keys,
+                              const uint32_t* d_counts /* may be NULL */, HopGtResult* d_out, void* stream);
+/* host convenience: whole candidate range on this GPU */
+int hop_gt_sweep_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* org, size_t org_samples,
+                       const int16_t* ref, size_t ref_samples, HopGtResult* out);
+
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 uint64_t hop_ctx_launch_count(HopCtx* ctx);
 

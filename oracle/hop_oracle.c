@@ -373,6 +373,149 @@ void orc_pattern_search_gt(const HopGtJob* job, const int16_t* org_buf, const in
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Exhaustive sweep -- TLibEncoder/TEncSearch.cpp:4989-5091, the reference's IT_GT_SEARCH == 1
+ * ("square unit search", N = 2 => 25^4 corner sets) as it compiles with IT_GT_GRID_SIZE 1
+ * (SURVEY.md §8e): 1x grid (calcParamProjective / ProjectiveTransform get iCols,iRows :5026-5030,
+ * TComPrediction.cpp:915-944 branch), "valid GT location" test re-enabled (:5020-5023), one pass from
+ * the integer vector pcMvInt (half = quarter = 0), no AMVP start vectors.
+ * cand_begin/cand_end restrict the evaluation to a slice of the AFFINE candidates in loop order (the
+ * unit the multi-GPU sweep shards); key = cost << 32 | flat loop index, ~0 when nothing was scored.
+ * ---------------------------------------------------------------------------------------------- */
+static void projective_transform_grid1(const int16_t* ref, int16_t* aux_out, const double h[9],
+                                       int W, int H, int stride, int nss_window)
+{
+  for (int y = 0; y < H; y++) {                       /* TComPrediction.cpp:916-917 */
+    for (int x = 0; x < W; x++) {
+      double Fx = (h[0] * x + h[3] * y + h[6]) / (h[2] * x + h[5] * y + h[8]);
+      double Fy = (h[1] * x + h[4] * y + h[7]) / (h[2] * x + h[5] * y + h[8]);
+      int Y = (int)Fy;                                /* :929-944 */
+      int X = (int)Fx;
+      double q = (Fy - (double)Y);
+      double p = (Fx - (double)X);
+      if (Y < -nss_window) Y = -nss_window;
+      if (X < -nss_window) X = -nss_window;
+      if (Y > nss_window + H - 1) Y = nss_window + H - 1;
+      if (X > nss_window + W - 1) X = nss_window + W - 1;
+      if (Y + 1 > nss_window + H - 1) Y = nss_window + H - 2;
+      if (X + 1 > nss_window + W - 1) X = nss_window + W - 2;
+      const int16_t* pa = ref + Y * stride;
+      double aux = (1.0 - q) * ((1.0 - p) * (double)(pa[X]) + p * (double)(pa[X + 1]));
+      pa = ref + (Y + 1) * stride;
+      aux += q * ((1.0 - p) * (double)(pa[X]) + p * (double)(pa[X + 1]));
+      if (aux > 255) aux = 255;
+      if (aux < 0) aux = 0;
+      aux_out[x] = (int16_t)(aux + 0.5);              /* :1023 */
+    }
+    aux_out += W;
+  }
+}
+
+uint64_t orc_gt_sweep_key(const HopGtJob* job, const int16_t* org_buf, const int16_t* ref_buf,
+                          int cand_begin, int cand_end, uint32_t* n_scored)
+{
+  const int cols = job->cols, rows = job->rows, N = 2;
+  const int16_t* org = org_buf + job->org_off;
+  const int16_t* ref_y = ref_buf + job->ref_off;
+  const int win_w = cols * 2, win_h = rows * 2;
+  int16_t* window = (int16_t*)malloc(sizeof(int16_t) * win_w * win_h);
+  int16_t* aux = (int16_t*)malloc(sizeof(int16_t) * rows * cols);
+  const int mvx = job->ss_cand.hor, mvy = job->ss_cand.ver;          /* pcMvInt */
+  const int16_t Hor = (int16_t)(mvx << 2), Ver = (int16_t)(mvy << 2);  /* :4713-4724, half = qter = 0 */
+  const int nss_window = ((rows < cols) ? rows : cols) >> 1;          /* :4756, grid 1 */
+  const int i_offset = mvx - cols / 2 + (mvy - rows / 2) * job->ref_stride;   /* :4728 */
+  orc_stage_window(ref_y + i_offset, job->ref_stride, window, win_w, win_h, job->bit_depth);
+  const int16_t* ref_srch = window + (cols / 2) + (rows / 2) * win_w;  /* :4746 */
+  const int cnx[4] = {0, cols - 1, cols - 1, 0}, cny[4] = {0, 0, rows - 1, rows - 1};   /* :4781-4784 */
+  uint64_t best = ~(uint64_t)0;
+  uint32_t scored = 0;
+  int affine_idx = 0;
+  double proj[9];
+  int cx[4], cy[4];
+  for (int y0 = -N; y0 <= N; y0++) { cy[0] = cny[0] + y0;
+  for (int x0 = -N; x0 <= N; x0++) { cx[0] = cnx[0] + x0;
+  for (int y1 = -N; y1 <= N; y1++) { cy[1] = cny[1] + y1;
+  for (int x1 = -N; x1 <= N; x1++) { cx[1] = cnx[1] + x1;
+  for (int y2 = -N; y2 <= N; y2++) { cy[2] = cny[2] + y2;
+  for (int x2 = -N; x2 <= N; x2++) { cx[2] = cnx[2] + x2;
+  for (int y3 = -N; y3 <= N; y3++) { cy[3] = cny[3] + y3;
+  for (int x3 = -N; x3 <= N; x3++) { cx[3] = cnx[3] + x3;
+    if (x0 == x1 && x0 == x2 && x0 == x3 && y0 == y1 && y0 == y2 && y0 == y3) continue;     /* :5017 */
+    /* the multi-GPU shard unit: position among the parallelogram (affine) offset patterns */
+    if (!(x0 - x1 + x2 - x3 == 0 && y0 - y1 + y2 - y3 == 0)) {
+      /* not a parallelogram: the reference's double test below rejects it (h[2], h[5] != 0) */
+      orc_calc_param_projective(cx, cy, proj, cols, rows);
+      if (proj[2] == 0.0 && proj[5] == 0.0) { free(window); free(aux); return 1; }   /* cannot happen */
+      continue;
+    }
+    const int my_idx = affine_idx++;
+    if (my_idx < cand_begin || my_idx >= cand_end) continue;
+    /* valid GT location, marginX = marginY = 0 (:5020-5023) */
+    if (!(((x0 + mvx < 0 && y0 + mvy <= 0) || (x0 + mvx >= 0 && y0 + mvy < 0)) &&
+          ((x1 + mvx + cols < 0 && y1 + mvy <= 0) || (x1 + mvx + cols >= 0 && y1 + mvy < 0)) &&
+          ((x2 + mvx + cols < 0 && y2 + mvy + rows <= 0) || (x2 + mvx + cols >= 0 && y2 + mvy + rows < 0)) &&
+          ((x3 + mvx < 0 && y3 + mvy + rows <= 0) || (x3 + mvx >= 0 && y3 + mvy + rows < 0)))) continue;
+    orc_calc_param_projective(cx, cy, proj, cols, rows);                                   /* :5026 */
+    if (!(proj[2] == 0.0 && proj[5] == 0.0)) continue;                                     /* :5028 */
+    projective_transform_grid1(ref_srch, aux, proj, cols, rows, win_w, nss_window);        /* :5030 */
+    uint32_t dist;
+    if (job->use_had) dist = orc_hads(org, job->org_stride, aux, cols, cols, rows, job->bit_depth);
+    else dist = orc_sad(org, job->org_stride, aux, cols, cols, rows, 0, job->bit_depth);
+    dist += orc_get_cost_xy(&job->cost, Hor, Ver);                                         /* :5035 */
+    dist += orc_get_cost_bits(&job->cost, orc_get_bits_gt(cx[0], cy[0], cx[1] - cols + 1, cy[1],
+                                                          cx[2] - cols + 1, cy[2] - rows + 1));   /* :5036-5041 */
+    scored++;
+    const uint32_t flat = (uint32_t)((((((((y0 + N) * 5 + (x0 + N)) * 5 + (y1 + N)) * 5 + (x1 + N)) * 5 + (y2 + N)) * 5 +
+                                       (x2 + N)) * 5 + (y3 + N)) * 5 + (x3 + N));
+    const uint64_t key = ((uint64_t)dist << 32) | flat;
+    if (key < best) best = key;          /* first strict minimum in loop order == min (cost, flat) */
+  }}}}}}}}
+  free(window); free(aux);
+  if (n_scored) *n_scored = scored;
+  return best;
+}
+
+/* key -> what xPatternSearchGT (mode 1) leaves in its outputs (:5070-5090) */
+void orc_gt_sweep_finalize(const HopGtJob* job, uint64_t key, HopGtResult* out)
+{
+  const int cols = job->cols, rows = job->rows, N = 2;
+  memset(out, 0, sizeof(*out));
+  out->cost = job->threshold;
+  out->best_index = -1;
+  if (key == ~(uint64_t)0 || (uint32_t)(key >> 32) >= job->threshold) return;   /* uiDist < uiDistBest never true */
+  uint32_t flat = (uint32_t)key;
+  int o[8];
+  for (int k = 7; k >= 0; k--) { o[k] = (int)(flat % 5) - N; flat /= 5; }     /* y0,x0,y1,x1,y2,x2,y3,x3 */
+  const int bx[4] = {0 + o[1], cols - 1 + o[3], cols - 1 + o[5], 0 + o[7]};
+  const int by[4] = {0 + o[0], 0 + o[2], rows - 1 + o[4], rows - 1 + o[6]};
+  int any = 0;
+  for (int k = 0; k < 4; k++) any |= (bx[k] != 0) | (by[k] != 0);
+  if (!any) return;
+  out->gt_flag = 1;
+  out->gt[0].hor = (int16_t)bx[0];              out->gt[0].ver = (int16_t)by[0];
+  out->gt[1].hor = (int16_t)(bx[1] - cols + 1); out->gt[1].ver = (int16_t)by[1];
+  out->gt[2].hor = (int16_t)(bx[2] - cols + 1); out->gt[2].ver = (int16_t)(by[2] - rows + 1);
+  out->gt[3].hor = (int16_t)bx[3];              out->gt[3].ver = (int16_t)(by[3] - rows + 1);
+  out->cost = (uint32_t)(key >> 32);
+  out->best_index = (int32_t)(uint32_t)key;
+}
+
+void orc_gt_sweep_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref, HopGtResult* out)
+{
+  for (int i = 0; i < n; i++) {
+    uint32_t scored = 0;
+    uint64_t key = orc_gt_sweep_key(&jobs[i], org, ref, 0, 1 << 30, &scored);
+    orc_gt_sweep_finalize(&jobs[i], key, &out[i]);
+    out[i].n_candidates = scored;
+  }
+}
+
+void orc_gt_sweep_keys_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref,
+                             int cand_begin, int cand_end, uint64_t* keys)
+{
+  for (int i = 0; i < n; i++) keys[i] = orc_gt_sweep_key(&jobs[i], org, ref, cand_begin, cand_end, NULL);
+}
+
 void orc_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* org, const int16_t* ref,
                               HopSearchResult* out)
 {

@@ -60,6 +60,16 @@ void orc_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* or
 void orc_pattern_search_gt_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref,
                                  HopGtResult* out);
 
+/* Exhaustive sweep (reference mode IT_GT_SEARCH 1 + IT_GT_GRID_SIZE 1, TEncSearch.cpp:4989-5091): the job's
+ * ss_cand is pcMvInt; amvp is ignored.  The slice [cand_begin, cand_end) counts AFFINE candidates in loop
+ * order (7200 for N = 2). */
+uint64_t orc_gt_sweep_key(const HopGtJob* job, const int16_t* org, const int16_t* ref,
+                          int cand_begin, int cand_end, uint32_t* n_scored);
+void orc_gt_sweep_finalize(const HopGtJob* job, uint64_t key, HopGtResult* out);
+void orc_gt_sweep_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref, HopGtResult* out);
+void orc_gt_sweep_keys_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref,
+                             int cand_begin, int cand_end, uint64_t* keys);
+
 /* K4: TComPicYuv::extendPicBorder luma part, TComPicYuv.cpp:236-274. plane points at sample (0,0). */
 void orc_extend_border(int16_t* origin, int stride, int pic_w, int pic_h, int margin);
 

@@ -95,6 +95,49 @@ def oracle():
     return _cache["orc"]
 
 
+def gt_sweep(jobs, org, ref):
+    """Oracle statement of the exhaustive sweep (reference mode IT_GT_SEARCH 1 / IT_GT_GRID_SIZE 1)."""
+    o = oracle()
+    hop = o.hop
+    jobs = np.ascontiguousarray(jobs, dtype=hop.GT_JOB_DT)
+    out = np.zeros(len(jobs), dtype=hop.GT_RES_DT)
+    fn = o.lib.orc_gt_sweep_batch
+    fn.argtypes = [C.c_int, _P, _P, _P, _P]; fn.restype = None
+    fn(len(jobs), _np(jobs), _np(org), _np(ref), _np(out))
+    return out
+
+
+def gt_sweep_keys(jobs, org, ref, cand_begin, cand_end):
+    o = oracle()
+    jobs = np.ascontiguousarray(jobs, dtype=o.hop.GT_JOB_DT)
+    keys = np.zeros(len(jobs), dtype=np.uint64)
+    fn = o.lib.orc_gt_sweep_keys_batch
+    fn.argtypes = [C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]; fn.restype = None
+    fn(len(jobs), _np(jobs), _np(org), _np(ref), cand_begin, cand_end, _np(keys))
+    return keys
+
+
+def gt_sweep_finalize(jobs, keys):
+    o = oracle()
+    jobs = np.ascontiguousarray(jobs, dtype=o.hop.GT_JOB_DT)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(len(jobs), dtype=o.hop.GT_RES_DT)
+    fn = o.lib.orc_gt_sweep_finalize
+    fn.argtypes = [_P, C.c_uint64, _P]; fn.restype = None
+    for i in range(len(jobs)):
+        fn(jobs[i:i + 1].ctypes.data, int(keys[i]), out[i:i + 1].ctypes.data)
+    return out
+
+
+def ref_sweep():
+    """The reference compiled in its exhaustive mode (oracle/_ref/libhopref_sweep.so): its
+    xPatternSearchGT IS the sweep.  None when not built."""
+    if "ref_sweep" not in _cache:
+        p = os.path.join(ORACLE_DIR, "_ref", "libhopref_sweep.so")
+        _cache["ref_sweep"] = _Checker(C.CDLL(p), "ref_") if os.path.exists(p) else None
+    return _cache["ref_sweep"]
+
+
 def ref_path():
     return os.path.join(ORACLE_DIR, "_ref", "libhopref.so")
 

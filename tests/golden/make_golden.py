@@ -66,6 +66,23 @@ def main():
     dist["n_dist"] = np.int64(k)
     np.savez_compressed(os.path.join(HERE, "dist_golden.npz"), **dist)
 
+    # exhaustive sweep: outputs of the reference compiled with IT_GT_SEARCH 1 / IT_GT_GRID_SIZE 1
+    rs = _oracle.ref_sweep()
+    assert rs is not None, "build the sweep reference first: make -C oracle ref_sweep"
+    sw = {}
+    k = 0
+    for bit_depth, shapes in ((8, [(8, 8), (16, 16), (8, 4), (4, 8), (16, 12), (32, 8), (32, 32)]), (10, [(8, 8), (16, 8)])):
+        for (c, r) in shapes:
+            for use_had in (1, 0):
+                b = PuBatch(c, r, 2, seed=900 + k, bit_depth=bit_depth, sr=20, use_had=use_had, n_start=1,
+                            threshold=0xFFFFFFFE if k % 2 else 3000)
+                tag = "w%02d" % k
+                sw[tag + "_org"], sw[tag + "_ref"], sw[tag + "_jobs"] = b.org, b.ref, b.gt_jobs
+                sw[tag + "_out"] = rs.pattern_search_gt(b.gt_jobs, b.org, b.ref)
+                k += 1
+    sw["n_sweep"] = np.int64(k)
+    np.savez_compressed(os.path.join(HERE, "sweep_golden.npz"), **sw)
+
     # border extension: random plane with -1 staircase, reference extendPicBorder (margin 80)
     rng = np.random.default_rng(7)
     pic_w, pic_h, m = 96, 72, 80
