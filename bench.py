@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=48, help="PUs per shape in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encode-size", type=int, default=1024, help="edge of the square lenslet image encoded per GPU; 0 = skip")
+    ap.add_argument("--sweep-pus", type=int, default=256, help="PUs (16x16, Main10) of the sharded exhaustive sweep; 0 = skip")
     ap.add_argument("--k1-pus", type=int, default=256, help="PUs per shape for the secondary K1 (SS full search) measurement; 0 = skip")
     return ap.parse_args()
 
@@ -215,6 +216,48 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
                                         "bitstream_identical": hashlib.md5(ref["bitstream"]).hexdigest() ==
                                         hashlib.md5(hop["bitstream"]).hexdigest()}
     return enc
+
+
+# ---------------------------------------------------------------------------------------------------
+# exhaustive HOP parameter sweep (configs[4]): candidates sharded over the ranks, NCCL all-reduce-min
+# ---------------------------------------------------------------------------------------------------
+def measure_sweep(hop, ctx, torch, dist, dev, tstream, pus, rank, world):
+    if pus <= 0:
+        return None
+    from hevc_hop_b200 import sweep
+    from hevc_hop_b200.workload import PuBatch
+    b = PuBatch(16, 16, pus, seed=4242, bit_depth=10, sr=32, n_start=1)      # same inputs on every rank
+    up = lambda a: torch.from_numpy(a.view(np.uint8)).to(dev)
+    d_jobs, d_org, d_ref = up(b.gt_jobs), up(b.org), up(b.ref)
+    d_out = torch.zeros(b.n * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 3
+    for it in range(iters + 1):
+        if it == 1:
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(tstream)
+        sweep.sweep_on_device(ctx, torch, dist, b.n, d_jobs, d_org, d_ref, 16, 16, d_out, rank, world, ctx.stream)
+    e1.record(tstream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    ms = float(t.item())
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    got = d_out.cpu().numpy().view(hop.GT_RES_DT)[:2]
+    want = _oracle.gt_sweep(b.gt_jobs[:2], b.org, b.ref)
+    ok = bool((got["cost"] == want["cost"]).all() and got["gt"].tobytes() == want["gt"].tobytes() and
+              (got["best_index"] == want["best_index"]).all())
+    return {"workload": "%d PUs 16x16 Main10, reference mode IT_GT_SEARCH 1 (N=2): %d affine corner sets per PU, "
+                        "candidate range sharded over %d GPU(s), one all-reduce-min of %d x 8 B" % (pus, hop.HOP_SWEEP_CANDS, world, pus),
+            "scaling": "strong", "ms": ms, "candidates_per_s": pus * hop.HOP_SWEEP_CANDS / (ms * 1e-3),
+            "collective": "ncclAllReduce(min) on int64 keys" if world > 1 else "none (1 rank)", "parity_spot_check": ok}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -393,6 +436,9 @@ def run_ours(args):
     # whole-image encode through the patched reference encoder: one image per GPU (replicas, no collective)
     enc = measure_encode(args, rank, world, local, dist if world > 1 else None, torch, dev)
 
+    # exhaustive sweep sharded over the ranks: the one path with a real exchange (NCCL all-reduce-min)
+    swp = measure_sweep(hop, ctx, torch, dist if world > 1 else None, dev, tstream, args.sweep_pus, rank, world)
+
     # secondary measurement (rank 0, outside the headline region): K1 = xPatternSearch, SearchRange 128
     k1 = None
     if rank == 0 and args.k1_pus > 0:
@@ -458,6 +504,7 @@ def run_ours(args):
         "parity_spot_check": parity,
         "k1_sad_search": k1,
         "encode": enc,
+        "sweep": swp,
     }
     print(json.dumps(line))
     if world > 1:
