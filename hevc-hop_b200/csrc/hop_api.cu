@@ -44,7 +44,10 @@ struct HopCtx {
   cudaStream_t stream = nullptr;
   int          sm_count = 0;
   uint64_t     launches = 0;
-  Scratch      jobs, org, ref, out, keys, sink;
+  Scratch      jobs, org, ref, out, keys, done, sweep_keys, sink;
+  // single-call (in-encoder) path: one pinned host buffer [job | original block | result] and its device twin
+  unsigned char* pin_h = nullptr;
+  unsigned char* pin_d = nullptr;
   // SS reference mirror
   int16_t*     plane = nullptr;
   int          pic_w = 0, pic_h = 0, margin = 0, stride = 0;
@@ -153,8 +156,10 @@ void hop_ctx_destroy(HopCtx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->sink};
+  Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->done, &ctx->sweep_keys, &ctx->sink};
   for (Scratch* s : all) if (s->p) cudaFree(s->p);
+  if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
+  if (ctx->pin_d) cudaFree(ctx->pin_d);
   if (ctx->plane) cudaFree(ctx->plane);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -265,10 +270,16 @@ int k1_slices(const HopCtx* ctx, int n)
 int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                HopSearchResult* d_out, int smem_bytes, cudaStream_t s)
 {
+  // merge words: all-ones keys / zero tickets between launches (the kernel restores them itself)
+  const size_t kcap = ctx->keys.cap, dcap = ctx->done.cap;
   int st = ensure(ctx, ctx->keys, sizeof(unsigned long long) * (size_t)n);
   if (st) return st;
+  if ((st = ensure(ctx, ctx->done, sizeof(unsigned int) * (size_t)n))) return st;
+  if (ctx->keys.cap != kcap) CU(cudaMemsetAsync(ctx->keys.p, 0xFF, ctx->keys.cap, s));
+  if (ctx->done.cap != dcap) CU(cudaMemsetAsync(ctx->done.p, 0, ctx->done.cap, s));
   int l = 0;
-  CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, k1_slices(ctx, n), smem_bytes, s, &l));
+  CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, (unsigned int*)ctx->done.p,
+                   k1_slices(ctx, n), smem_bytes, s, &l));
   ctx->launches += l;
   return HOP_OK;
 }
@@ -321,6 +332,52 @@ int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs, const int16
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+extern "C++" {
+constexpr size_t PIN_JOB = 128;                                   // job slot (both job structs are 80 B)
+constexpr size_t PIN_ORG = HOP_MAX_PU * HOP_MAX_PU * sizeof(int16_t);
+constexpr size_t PIN_OUT = 64;
+constexpr size_t PIN_BYTES = PIN_JOB + PIN_ORG + PIN_OUT;
+
+int pin_ready(HopCtx* ctx)
+{
+  if (ctx->pin_h) return HOP_OK;
+  CU(cudaHostAlloc((void**)&ctx->pin_h, PIN_BYTES, cudaHostAllocDefault));
+  CU(cudaMalloc((void**)&ctx->pin_d, PIN_BYTES));
+  return HOP_OK;
+}
+
+// In-encoder single call on the SS mirror: pack [job | W x H original block] into the pinned buffer (the
+// block becomes contiguous: org_off = 0, org_stride = cols), ONE host-to-device copy, the kernel(s), ONE
+// copy back.  JOB is HopSearchJob or HopGtJob (same leading layout).
+template <typename JOB>
+int pack_single(HopCtx* ctx, const JOB& job, const int16_t* org, size_t org_samples)
+{
+  int st = pin_ready(ctx);
+  if (st) return st;
+  const size_t need = (size_t)(job.rows - 1) * job.org_stride + job.cols;
+  if (job.org_off < 0 || (size_t)job.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
+  JOB packed = job;
+  packed.org_off = 0;
+  packed.org_stride = job.cols;
+  memcpy(ctx->pin_h, &packed, sizeof(JOB));
+  int16_t* dst = (int16_t*)(ctx->pin_h + PIN_JOB);
+  const int16_t* src = org + job.org_off;
+  for (int r = 0; r < job.rows; r++) memcpy(dst + (size_t)r * job.cols, src + (size_t)r * job.org_stride, sizeof(int16_t) * job.cols);
+  CU(cudaMemcpyAsync(ctx->pin_d, ctx->pin_h, PIN_JOB + sizeof(int16_t) * (size_t)job.rows * job.cols,
+                     cudaMemcpyHostToDevice, ctx->stream));
+  return HOP_OK;
+}
+
+template <typename RES>
+int unpack_single(HopCtx* ctx, RES* out)
+{
+  CU(cudaMemcpyAsync(ctx->pin_h + PIN_JOB + PIN_ORG, ctx->pin_d + PIN_JOB + PIN_ORG, sizeof(RES), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->pin_h + PIN_JOB + PIN_ORG, sizeof(RES));
+  return HOP_OK;
+}
+}  // extern "C++"
+
 // upload jobs + org (+ ref unless the mirror is used); returns the device pointers
 int stage_inputs(HopCtx* ctx, int n, const void* jobs, size_t job_size, const int16_t* org, size_t org_samples,
                  const int16_t* ref, size_t ref_samples, size_t out_bytes, const int16_t** d_ref_out)
@@ -356,6 +413,19 @@ int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs, const
     if (j.cols < 1 || j.cols > HOP_MAX_PU || j.rows < 1 || j.rows > HOP_MAX_PU || j.bit_depth < 8 || j.bit_depth > 14)
       return fail(HOP_ERR_ARG, "job %d: unsupported block %dx%d / bit depth %d", i, j.cols, j.rows, j.bit_depth);
   }
+  if (n == 1 && !ref && jobs[0].cols <= HOP_MAX_PU && jobs[0].rows <= HOP_MAX_PU) {
+    // the encoder's call: one PU against the SS mirror
+    if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
+    if ((st = pack_single(ctx, jobs[0], org, org_samples))) return st;
+    HopSearchJob packed;
+    memcpy(&packed, ctx->pin_h, sizeof(packed));
+    const int slices = k1_slices(ctx, 1);
+    size_t smem = search_smem_bytes(packed, slices);
+    st = search_dev(ctx, 1, (const HopSearchJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
+                    (HopSearchResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream);
+    if (st) return st;
+    return unpack_single(ctx, out);
+  }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopSearchJob), org, org_samples, ref, ref_samples,
                     sizeof(HopSearchResult) * (size_t)n, &d_ref);
@@ -388,6 +458,15 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
       return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / num_pred %d", i, j.cols, j.rows, j.bit_depth, j.num_pred);
     if (j.cols > max_cols) max_cols = j.cols;
     if (j.rows > max_rows) max_rows = j.rows;
+  }
+  if (n == 1 && !ref) {
+    if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
+    if ((st = pack_single(ctx, jobs[0], org, org_samples))) return st;
+    st = hop_pattern_search_gt_batch_dev(ctx, 1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB),
+                                         hop_ref_origin_dev(ctx), (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG),
+                                         max_cols, max_rows, ctx->stream);
+    if (st) return st;
+    return unpack_single(ctx, out);
   }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,
@@ -488,8 +567,8 @@ int hop_gt_sweep_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* 
   st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,
                     sizeof(HopGtResult) * (size_t)n, &d_ref);
   if (st) return st;
-  if ((st = ensure(ctx, ctx->keys, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)n + 16))) return st;
-  uint64_t* d_keys = (uint64_t*)ctx->keys.p;
+  if ((st = ensure(ctx, ctx->sweep_keys, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)n + 16))) return st;
+  uint64_t* d_keys = (uint64_t*)ctx->sweep_keys.p;
   uint32_t* d_counts = (uint32_t*)(d_keys + n);
   st = hop_gt_sweep_keys_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, max_cols, max_rows,
                              0, SWEEP_CANDS, d_keys, d_counts, ctx->stream);

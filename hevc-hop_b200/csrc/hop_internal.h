@@ -29,8 +29,8 @@ cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned 
                                   const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches);
 // K1
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                          HopSearchResult* d_out, unsigned long long* d_keys, int slices, int smem_bytes,
-                          cudaStream_t stream, int* launches);
+                          HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
+                          int smem_bytes, cudaStream_t stream, int* launches);
 size_t      search_smem_bytes(const HopSearchJob& job, int slices);
 constexpr int K1_DEFAULT_SMEM = 96 * 1024;   // byte-path budget when the job shapes are not known on the host
 // K3

@@ -26,10 +26,24 @@
 
 namespace hop {
 
-__global__ void k1_init_keys(int n, unsigned long long* keys)
+// keys[] is all-ones and done[] all-zero between launches: the last CTA of a PU (a ticket counter decides)
+// reads the merged key, writes the result and restores both words, so one search is ONE kernel launch.
+__device__ __forceinline__ void k1_write_result(const HopSearchJob& job, unsigned long long key, HopSearchResult* out)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = ~0ull;
+  HopSearchResult r;
+  r.mv.hor = 0; r.mv.ver = 0;
+  if (key == ~0ull) {                                            // TEncSearch.cpp:6356-6360
+    r.found = 0; r.sad = HOP_MAX_UINT; r.cost = HOP_MAX_UINT;
+  } else {
+    const int nx = job.rng_right - job.rng_left + 1;
+    const unsigned idx = (unsigned)(key & 0xffffffffu);
+    const int x = job.rng_left + (int)(idx % (unsigned)nx), y = job.rng_top + (int)(idx / (unsigned)nx);
+    r.found = 1;
+    r.mv.hor = (int16_t)x; r.mv.ver = (int16_t)y;
+    r.cost = (uint32_t)(key >> 32);
+    r.sad = r.cost - mv_cost(job.cost, x, y);                    // :6365
+  }
+  *out = r;
 }
 
 struct K1Geom {            // per-CTA geometry of the slice, identical on host and device
@@ -209,7 +223,8 @@ __device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, 
 
 __global__ void __launch_bounds__(K1_THREADS)
 k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
-          const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys, int smem_limit)
+          const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys,
+          unsigned int* __restrict__ done, HopSearchResult* __restrict__ out, int smem_limit)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned long long s_red[32];
@@ -217,12 +232,12 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
   const int job_id = blockIdx.x;
   const HopSearchJob job = jobs[job_id];
   const K1Geom g = k1_geom(job, blockIdx.y, gridDim.y);
-  if (g.nx <= 0 || g.ny <= 0 || g.y_lo >= g.y_hi) return;
+  const bool empty = g.nx <= 0 || g.ny <= 0 || g.y_lo >= g.y_hi;    // degenerate window / slice beyond it
   const int16_t* org = org_buf + job.org_off;
   const int16_t* ref_y = ref_buf + job.ref_off;
   const int cols = job.cols, rows = job.rows;
 
-  bool bytes_ok = job.bit_depth == 8 && (cols % 4) == 0 && cols <= HOP_MAX_PU && rows <= HOP_MAX_PU &&
+  bool bytes_ok = !empty && job.bit_depth == 8 && (cols % 4) == 0 && cols <= HOP_MAX_PU && rows <= HOP_MAX_PU &&
                   k1_smem_bytes(job, g) <= (size_t)smem_limit;
   unsigned long long best;
   if (bytes_ok) {
@@ -300,37 +315,23 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
       }
     }
   }
-  if (!bytes_ok) best = k1_generic(job, g, org, ref_y);
+  if (!bytes_ok) best = empty ? ~0ull : k1_generic(job, g, org, ref_y);
   best = block_min_u64(best, s_red);
-  if (threadIdx.x == 0 && best != ~0ull) atomicMin(&keys[job_id], best);
-}
-
-__global__ void k1_finalize(int n, const HopSearchJob* __restrict__ jobs,
-                            const unsigned long long* __restrict__ keys, HopSearchResult* __restrict__ out)
-{
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const HopSearchJob job = jobs[i];
-  const unsigned long long key = keys[i];
-  HopSearchResult r;
-  r.mv.hor = 0; r.mv.ver = 0;
-  if (key == ~0ull) {                                            // :6356-6360
-    r.found = 0; r.sad = HOP_MAX_UINT; r.cost = HOP_MAX_UINT;
-  } else {
-    const int nx = job.rng_right - job.rng_left + 1;
-    const unsigned idx = (unsigned)(key & 0xffffffffu);
-    const int x = job.rng_left + (int)(idx % (unsigned)nx), y = job.rng_top + (int)(idx / (unsigned)nx);
-    r.found = 1;
-    r.mv.hor = (int16_t)x; r.mv.ver = (int16_t)y;
-    r.cost = (uint32_t)(key >> 32);
-    r.sad = r.cost - mv_cost(job.cost, x, y);                    // :6365
+  if (threadIdx.x == 0) {
+    if (best != ~0ull) atomicMin(&keys[job_id], best);
+    __threadfence();
+    if (atomicAdd(&done[job_id], 1u) == gridDim.y - 1) {          // last slice of this PU
+      __threadfence();
+      const unsigned long long key = atomicExch(&keys[job_id], ~0ull);
+      done[job_id] = 0;
+      k1_write_result(job, key, &out[job_id]);
+    }
   }
-  out[i] = r;
 }
 
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                          HopSearchResult* d_out, unsigned long long* d_keys, int slices, int smem_bytes,
-                          cudaStream_t stream, int* launches)
+                          HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
+                          int smem_bytes, cudaStream_t stream, int* launches)
 {
   static int attr_set = 0;
   const int smem_max = 160 * 1024;
@@ -343,10 +344,8 @@ cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_or
   if (slices > K1_MAX_SLICES) slices = K1_MAX_SLICES;
   if (smem_bytes > smem_max) smem_bytes = smem_max;
   if (smem_bytes < 1024) smem_bytes = 1024;
-  k1_init_keys<<<(n + 255) / 256, 256, 0, stream>>>(n, d_keys);
-  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, smem_bytes);
-  k1_finalize<<<(n + 255) / 256, 256, 0, stream>>>(n, d_jobs, d_keys, d_out);
-  if (launches) *launches += 3;
+  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes);
+  if (launches) *launches += 1;
   return cudaGetLastError();
 }
 

@@ -418,26 +418,24 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
           cx[k] += s * c_gt_offsets[c][2 * k];
           cy[k] += s * c_gt_offsets[c][2 * k + 1];
         }
-        // calcParamProjective, TComPrediction.cpp:807-832, literally (IEEE binary64, no contraction)
+        // calcParamProjective, TComPrediction.cpp:807-832.  The affine test "h[2] == 0.0 && h[5] == 0.0"
+        // (:5323) is decided exactly in integers: the numerators of h[2], h[5] are products of small
+        // integers (exact in binary64) and vanish together iff dx3 == dy3 == 0 when den != 0; den == 0
+        // gives 0/0 = NaN, which fails the reference's comparison.  For an accepted candidate
+        // h[2] = h[5] = +-0, so h[0] = fl((x1-x0)/W) + (+-0) = fl((x1-x0)/W) etc. -- same values, no
+        // division chain through den.
         const double Wd = __dsub_rn((double)(cols * G), 1.0), Hd = __dsub_rn((double)(rows * G), 1.0);
-        const double dx1 = __dsub_rn((double)cx[1], (double)cx[2]);
-        const double dx2 = __dsub_rn((double)cx[3], (double)cx[2]);
-        const double dx3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cx[0], (double)cx[1]), (double)cx[2]), (double)cx[3]);
-        const double dy1 = __dsub_rn((double)cy[1], (double)cy[2]);
-        const double dy2 = __dsub_rn((double)cy[3], (double)cy[2]);
-        const double dy3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cy[0], (double)cy[1]), (double)cy[2]), (double)cy[3]);
-        const double den = __dsub_rn(__dmul_rn(dx1, dy2), __dmul_rn(dx2, dy1));
-        const double h2 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx3, dy2), __dmul_rn(dx2, dy3)), den), Wd);
-        const double h5 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx1, dy3), __dmul_rn(dx3, dy1)), den), Hd);
-        const int ok = (h2 == 0.0 && h5 == 0.0) ? 1 : 0;        // :5323, NaN (den == 0) fails
+        const int idx3 = cx[0] - cx[1] + cx[2] - cx[3], idy3 = cy[0] - cy[1] + cy[2] - cy[3];
+        const int iden = (cx[1] - cx[2]) * (cy[3] - cy[2]) - (cx[3] - cx[2]) * (cy[1] - cy[2]);
+        const int ok = (idx3 == 0 && idy3 == 0 && iden != 0) ? 1 : 0;
         sh.valid[c] = ok;
         sh.dist[c] = 0;
         if (ok) {
-          sh.h0[c] = __dadd_rn(__ddiv_rn((double)(cx[1] - cx[0]), Wd), __dmul_rn(h2, (double)cx[1]));
-          sh.h3[c] = __dadd_rn(__ddiv_rn((double)(cx[3] - cx[0]), Hd), __dmul_rn(h5, (double)cx[3]));
+          sh.h0[c] = __ddiv_rn((double)(cx[1] - cx[0]), Wd);
+          sh.h3[c] = __ddiv_rn((double)(cx[3] - cx[0]), Hd);
           sh.h6[c] = (double)cx[0];
-          sh.h1[c] = __dadd_rn(__ddiv_rn((double)(cy[1] - cy[0]), Wd), __dmul_rn(h2, (double)cy[1]));
-          sh.h4[c] = __dadd_rn(__ddiv_rn((double)(cy[3] - cy[0]), Hd), __dmul_rn(h5, (double)cy[3]));
+          sh.h1[c] = __ddiv_rn((double)(cy[1] - cy[0]), Wd);
+          sh.h4[c] = __ddiv_rn((double)(cy[3] - cy[0]), Hd);
           sh.h7[c] = (double)cy[0];
           const uint32_t gb = gt_bits(cx[0] / last_step, cy[0] / last_step,
                                       (cx[1] - cols * G + 1) / last_step, cy[1] / last_step,
@@ -601,24 +599,18 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
 #pragma unroll
         for (int k = 0; k < 4; k++) ok &= ((ax[k] < 0 && ay[k] <= 0) || (ax[k] >= 0 && ay[k] < 0)) ? 1 : 0;
         if (ok) {
-          // calcParamProjective(iCurrCornerX, iCurrCornerY, dProjective, iCols, iRows), TComPrediction.cpp:807-832
+          // calcParamProjective(iCurrCornerX, iCurrCornerY, dProjective, iCols, iRows), TComPrediction.cpp:807-832;
+          // affine test (:5028) decided exactly in integers, see k2_gt_search
           const double Wd = __dsub_rn((double)cols, 1.0), Hd = __dsub_rn((double)rows, 1.0);
-          const double dx1 = __dsub_rn((double)cx[1], (double)cx[2]);
-          const double dx2 = __dsub_rn((double)cx[3], (double)cx[2]);
-          const double dx3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cx[0], (double)cx[1]), (double)cx[2]), (double)cx[3]);
-          const double dy1 = __dsub_rn((double)cy[1], (double)cy[2]);
-          const double dy2 = __dsub_rn((double)cy[3], (double)cy[2]);
-          const double dy3 = __dsub_rn(__dadd_rn(__dsub_rn((double)cy[0], (double)cy[1]), (double)cy[2]), (double)cy[3]);
-          const double den = __dsub_rn(__dmul_rn(dx1, dy2), __dmul_rn(dx2, dy1));
-          const double h2 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx3, dy2), __dmul_rn(dx2, dy3)), den), Wd);
-          const double h5 = __ddiv_rn(__ddiv_rn(__dsub_rn(__dmul_rn(dx1, dy3), __dmul_rn(dx3, dy1)), den), Hd);
-          ok = (h2 == 0.0 && h5 == 0.0) ? 1 : 0;                                             // :5028
+          const int idx3 = cx[0] - cx[1] + cx[2] - cx[3], idy3 = cy[0] - cy[1] + cy[2] - cy[3];
+          const int iden = (cx[1] - cx[2]) * (cy[3] - cy[2]) - (cx[3] - cx[2]) * (cy[1] - cy[2]);
+          ok = (idx3 == 0 && idy3 == 0 && iden != 0) ? 1 : 0;
           if (ok) {
-            sh.h0[c] = __dadd_rn(__ddiv_rn((double)(cx[1] - cx[0]), Wd), __dmul_rn(h2, (double)cx[1]));
-            sh.h3[c] = __dadd_rn(__ddiv_rn((double)(cx[3] - cx[0]), Hd), __dmul_rn(h5, (double)cx[3]));
+            sh.h0[c] = __ddiv_rn((double)(cx[1] - cx[0]), Wd);
+            sh.h3[c] = __ddiv_rn((double)(cx[3] - cx[0]), Hd);
             sh.h6[c] = (double)cx[0];
-            sh.h1[c] = __dadd_rn(__ddiv_rn((double)(cy[1] - cy[0]), Wd), __dmul_rn(h2, (double)cy[1]));
-            sh.h4[c] = __dadd_rn(__ddiv_rn((double)(cy[3] - cy[0]), Hd), __dmul_rn(h5, (double)cy[3]));
+            sh.h1[c] = __ddiv_rn((double)(cy[1] - cy[0]), Wd);
+            sh.h4[c] = __ddiv_rn((double)(cy[3] - cy[0]), Hd);
             sh.h7[c] = (double)cy[0];
             const uint32_t gb = gt_bits(cx[0], cy[0], cx[1] - cols + 1, cy[1], cx[2] - cols + 1, cy[2] - rows + 1);
             sh.add_cost[c] = mv_add + bits_cost(job.cost, gb);                                // :5035-5041
