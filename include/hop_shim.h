@@ -22,8 +22,14 @@ namespace hopshim {
 struct Stats {
   double   sec[4];
   unsigned long long calls[4];
+  double   shape_sec[2][17][17];               // [K1|K2][cols/4][rows/4]
+  unsigned long long shape_calls[2][17][17];
   bool     on;
-  Stats() : on(getenv("HOP_STATS") != NULL) { for (int i = 0; i < 4; i++) { sec[i] = 0; calls[i] = 0; } }
+  Stats() : on(getenv("HOP_STATS") != NULL)
+  {
+    for (int i = 0; i < 4; i++) { sec[i] = 0; calls[i] = 0; }
+    for (int k = 0; k < 2; k++) for (int a = 0; a < 17; a++) for (int b = 0; b < 17; b++) { shape_sec[k][a][b] = 0; shape_calls[k][a][b] = 0; }
+  }
   ~Stats()
   {
     if (!on) return;
@@ -31,18 +37,24 @@ struct Stats {
     for (int i = 0; i < 4; i++)
       fprintf(stderr, "hopshim: %-18s %9llu calls %9.3f s (%.1f us/call)\n", name[i], calls[i], sec[i],
               calls[i] ? 1e6 * sec[i] / calls[i] : 0.0);
+    for (int k = 0; k < 2; k++) for (int a = 0; a < 17; a++) for (int b = 0; b < 17; b++)
+      if (shape_calls[k][a][b])
+        fprintf(stderr, "hopshim:   %-16s %2dx%-2d %8llu calls %8.3f s (%.1f us/call)\n", name[k], 4 * a, 4 * b,
+                shape_calls[k][a][b], shape_sec[k][a][b], 1e6 * shape_sec[k][a][b] / shape_calls[k][a][b]);
   }
 };
 inline Stats& stats() { static Stats s; return s; }
 struct Timer {
-  int k; timespec t0;
-  explicit Timer(int kind) : k(kind) { if (stats().on) clock_gettime(CLOCK_MONOTONIC, &t0); }
+  int k, cols, rows; timespec t0;
+  explicit Timer(int kind, int c = 0, int r = 0) : k(kind), cols(c), rows(r) { if (stats().on) clock_gettime(CLOCK_MONOTONIC, &t0); }
   ~Timer()
   {
     if (!stats().on) return;
     timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
-    stats().sec[k] += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    const double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    stats().sec[k] += dt;
     stats().calls[k]++;
+    if (k < 2 && cols > 0 && cols <= 64 && rows > 0 && rows <= 64) { stats().shape_sec[k][cols / 4][rows / 4] += dt; stats().shape_calls[k][cols / 4][rows / 4]++; }
   }
 };
 
@@ -118,7 +130,7 @@ inline void xPatternSearch(TComPattern* pcPatternKey, Pel* piRefY, Int iRefStrid
                            TComMv* pcMvSrchRngRB, TComMv& rcMv, UInt& ruiSAD, Int riOffsetX, Int riOffsetY,
                            TComMv* ssBestCand, Bool isSSE, Bool useFastEnc, Int bitDepth, TComRdCost* rd)
 {
-  Timer tm(0);
+  Timer tm(0, pcPatternKey->getROIYWidth(), pcPatternKey->getROIYHeight());
   State& s = state();
   HopSearchJob j;
   j.org_off = 0;
@@ -149,7 +161,7 @@ inline void xPatternSearchGT(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* p
                              TComMv* rcGT2, TComMv* rcGT3, Bool& gtFlag, UInt& ruiCost, TComMv* bestSSCand,
                              Bool useHADME, Int bitDepth, TComRdCost* rd)
 {
-  Timer tm(1);
+  Timer tm(1, pcPatternKey->getROIYWidth(), pcPatternKey->getROIYHeight());
   State& s = state();
   HopGtJob j;
   j.org_off = 0;
