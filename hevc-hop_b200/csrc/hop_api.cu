@@ -46,8 +46,9 @@ struct HopCtx {
   uint64_t     launches = 0;
   Scratch      jobs, org, ref, out, keys, done, sweep_keys, sink;
   // single-call (in-encoder) path: one pinned host buffer [job | original block | result] and its device twin
-  unsigned char* pin_h = nullptr;
-  unsigned char* pin_d = nullptr;
+  unsigned char* pin_h = nullptr;   // mapped pinned host memory (zero-copy): the GPU reads job + block from it
+  unsigned char* pin_d = nullptr;   // ... through this device alias, and writes result + completion flag back
+  unsigned       pin_seq = 0;
   // SS reference mirror
   int16_t*     plane = nullptr;
   int          pic_w = 0, pic_h = 0, margin = 0, stride = 0;
@@ -159,7 +160,6 @@ void hop_ctx_destroy(HopCtx* ctx)
   Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->done, &ctx->sweep_keys, &ctx->sink};
   for (Scratch* s : all) if (s->p) cudaFree(s->p);
   if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
-  if (ctx->pin_d) cudaFree(ctx->pin_d);
   if (ctx->plane) cudaFree(ctx->plane);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -268,7 +268,7 @@ int k1_slices(const HopCtx* ctx, int n)
   return slices > K1_MAX_SLICES ? K1_MAX_SLICES : (slices < 1 ? 1 : slices);
 }
 int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-               HopSearchResult* d_out, int smem_bytes, cudaStream_t s)
+               HopSearchResult* d_out, int smem_bytes, cudaStream_t s, unsigned* done_flag = nullptr, unsigned seq = 0)
 {
   // merge words: all-ones keys / zero tickets between launches (the kernel restores them itself)
   const size_t kcap = ctx->keys.cap, dcap = ctx->done.cap;
@@ -279,7 +279,7 @@ int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_
   if (ctx->done.cap != dcap) CU(cudaMemsetAsync(ctx->done.p, 0, ctx->done.cap, s));
   int l = 0;
   CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, (unsigned int*)ctx->done.p,
-                   k1_slices(ctx, n), smem_bytes, s, &l));
+                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq));
   ctx->launches += l;
   return HOP_OK;
 }
@@ -333,22 +333,25 @@ int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs, const int16
 namespace {
 
 extern "C++" {
+// In-encoder single call on the SS mirror (the latency path).  One mapped pinned host buffer holds
+// [job | W x H original block | result | completion flag]; the kernel reads the job and the block straight
+// from host memory (a few KB over PCIe), writes the result and then the flag back, and the host spins on
+// the flag: one kernel launch per search, no copy calls, no stream synchronisation.
 constexpr size_t PIN_JOB = 128;                                   // job slot (both job structs are 80 B)
 constexpr size_t PIN_ORG = HOP_MAX_PU * HOP_MAX_PU * sizeof(int16_t);
 constexpr size_t PIN_OUT = 64;
-constexpr size_t PIN_BYTES = PIN_JOB + PIN_ORG + PIN_OUT;
+constexpr size_t PIN_FLAG = 64;
+constexpr size_t PIN_BYTES = PIN_JOB + PIN_ORG + PIN_OUT + PIN_FLAG;
 
 int pin_ready(HopCtx* ctx)
 {
   if (ctx->pin_h) return HOP_OK;
-  CU(cudaHostAlloc((void**)&ctx->pin_h, PIN_BYTES, cudaHostAllocDefault));
-  CU(cudaMalloc((void**)&ctx->pin_d, PIN_BYTES));
+  CU(cudaHostAlloc((void**)&ctx->pin_h, PIN_BYTES, cudaHostAllocMapped));
+  memset(ctx->pin_h, 0, PIN_BYTES);
+  CU(cudaHostGetDevicePointer((void**)&ctx->pin_d, ctx->pin_h, 0));
   return HOP_OK;
 }
 
-// In-encoder single call on the SS mirror: pack [job | W x H original block] into the pinned buffer (the
-// block becomes contiguous: org_off = 0, org_stride = cols), ONE host-to-device copy, the kernel(s), ONE
-// copy back.  JOB is HopSearchJob or HopGtJob (same leading layout).
 template <typename JOB>
 int pack_single(HopCtx* ctx, const JOB& job, const int16_t* org, size_t org_samples)
 {
@@ -357,22 +360,31 @@ int pack_single(HopCtx* ctx, const JOB& job, const int16_t* org, size_t org_samp
   const size_t need = (size_t)(job.rows - 1) * job.org_stride + job.cols;
   if (job.org_off < 0 || (size_t)job.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
   JOB packed = job;
-  packed.org_off = 0;
+  packed.org_off = 0;                          // the block becomes contiguous behind the job
   packed.org_stride = job.cols;
   memcpy(ctx->pin_h, &packed, sizeof(JOB));
   int16_t* dst = (int16_t*)(ctx->pin_h + PIN_JOB);
   const int16_t* src = org + job.org_off;
   for (int r = 0; r < job.rows; r++) memcpy(dst + (size_t)r * job.cols, src + (size_t)r * job.org_stride, sizeof(int16_t) * job.cols);
-  CU(cudaMemcpyAsync(ctx->pin_d, ctx->pin_h, PIN_JOB + sizeof(int16_t) * (size_t)job.rows * job.cols,
-                     cudaMemcpyHostToDevice, ctx->stream));
   return HOP_OK;
 }
 
+inline unsigned* pin_flag_dev(HopCtx* ctx) { return (unsigned*)(ctx->pin_d + PIN_JOB + PIN_ORG + PIN_OUT); }
+
 template <typename RES>
-int unpack_single(HopCtx* ctx, RES* out)
+int unpack_single(HopCtx* ctx, unsigned seq, RES* out)
 {
-  CU(cudaMemcpyAsync(ctx->pin_h + PIN_JOB + PIN_ORG, ctx->pin_d + PIN_JOB + PIN_ORG, sizeof(RES), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  volatile unsigned* flag = (volatile unsigned*)(ctx->pin_h + PIN_JOB + PIN_ORG + PIN_OUT);
+  unsigned long long spins = 0;
+  while (*flag != seq) {
+    if ((++spins & 0xFFFFF) == 0) {            // every ~1M polls: did the kernel die?
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady)
+        return fail(HOP_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
+      if (e == cudaSuccess && *flag != seq) return fail(HOP_ERR_CUDA, "kernel finished without publishing its result");
+    }
+  }
+  __sync_synchronize();
   memcpy(out, ctx->pin_h + PIN_JOB + PIN_ORG, sizeof(RES));
   return HOP_OK;
 }
@@ -421,10 +433,12 @@ int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs, const
     memcpy(&packed, ctx->pin_h, sizeof(packed));
     const int slices = k1_slices(ctx, 1);
     size_t smem = search_smem_bytes(packed, slices);
+    const unsigned seq = ++ctx->pin_seq;
     st = search_dev(ctx, 1, (const HopSearchJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                    (HopSearchResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream);
+                    (HopSearchResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream,
+                    pin_flag_dev(ctx), seq);
     if (st) return st;
-    return unpack_single(ctx, out);
+    return unpack_single(ctx, seq, out);
   }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopSearchJob), org, org_samples, ref, ref_samples,
@@ -462,11 +476,12 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
   if (n == 1 && !ref) {
     if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
     if ((st = pack_single(ctx, jobs[0], org, org_samples))) return st;
-    st = hop_pattern_search_gt_batch_dev(ctx, 1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB),
-                                         hop_ref_origin_dev(ctx), (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG),
-                                         max_cols, max_rows, ctx->stream);
-    if (st) return st;
-    return unpack_single(ctx, out);
+    const unsigned seq = ++ctx->pin_seq;
+    int l = 0;
+    CU(gt_launch(1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
+                 (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l, pin_flag_dev(ctx), seq));
+    ctx->launches += l;
+    return unpack_single(ctx, seq, out);
   }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,

@@ -15,7 +15,8 @@ constexpr int K1_MAX_SLICES = 32; // CTAs cooperating on one PU's search window
 void        gt_build_offset_table(int8_t table[GT_CANDS][8], int* count);
 cudaError_t gt_upload_offset_table(const int8_t table[GT_CANDS][8]);
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);
+                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches,
+                      unsigned* done_flag = nullptr, unsigned seq = 0);
 // exhaustive sweep (reference mode IT_GT_SEARCH 1, N = 2): 85^2 - 25 parallelogram offset patterns
 constexpr int SWEEP_CANDS = 7200;
 struct SweepCand { int8_t o[8]; uint32_t flat; };   // x0,y0,...,x3,y3 in [-2,2]; flat 8-deep loop index
@@ -30,7 +31,8 @@ cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned 
 // K1
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
-                          int smem_bytes, cudaStream_t stream, int* launches);
+                          int smem_bytes, cudaStream_t stream, int* launches,
+                          unsigned* done_flag = nullptr, unsigned seq = 0);
 size_t      search_smem_bytes(const HopSearchJob& job, int slices);
 constexpr int K1_DEFAULT_SMEM = 96 * 1024;   // byte-path budget when the job shapes are not known on the host
 // K3

@@ -224,7 +224,8 @@ __device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, 
 __global__ void __launch_bounds__(K1_THREADS)
 k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
           const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys,
-          unsigned int* __restrict__ done, HopSearchResult* __restrict__ out, int smem_limit)
+          unsigned int* __restrict__ done, HopSearchResult* __restrict__ out, int smem_limit,
+          unsigned* done_flag, unsigned seq)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned long long s_red[32];
@@ -325,13 +326,17 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
       const unsigned long long key = atomicExch(&keys[job_id], ~0ull);
       done[job_id] = 0;
       k1_write_result(job, key, &out[job_id]);
+      if (done_flag) {               // single-call path: result and flag live in mapped host memory
+        __threadfence_system();
+        *(volatile unsigned*)done_flag = seq;
+      }
     }
   }
 }
 
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
-                          int smem_bytes, cudaStream_t stream, int* launches)
+                          int smem_bytes, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
 {
   static int attr_set = 0;
   const int smem_max = 160 * 1024;
@@ -344,7 +349,7 @@ cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_or
   if (slices > K1_MAX_SLICES) slices = K1_MAX_SLICES;
   if (smem_bytes > smem_max) smem_bytes = smem_max;
   if (smem_bytes < 1024) smem_bytes = 1024;
-  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes);
+  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes, done_flag, seq);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

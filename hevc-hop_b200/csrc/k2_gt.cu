@@ -344,7 +344,8 @@ constexpr int gt_class_threads(int) { return GT_THREADS; }
 template <int WS>
 __global__ void __launch_bounds__(gt_class_threads(WS), 2)
 k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
-             const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out)
+             const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out,
+             unsigned* done_flag, unsigned seq)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
@@ -506,6 +507,10 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
       r.best_index = sh.best_index;
     }
     out[job_id] = r;
+    if (done_flag) {                 // single-call path: result and flag live in mapped host memory
+      __threadfence_system();
+      *(volatile unsigned*)done_flag = seq;
+    }
   }
 }
 
@@ -701,7 +706,8 @@ static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
 
 template <int WS>
 static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                                   HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream)
+                                   HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
+                                   unsigned* done_flag, unsigned seq)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -721,20 +727,21 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
-  k2_gt_search<WS><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out);
+  k2_gt_search<WS><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq);
   return cudaGetLastError();
 }
 
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches)
+                      HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches,
+                      unsigned* done_flag, unsigned seq)
 {
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return gt_launch_class<33>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
-    case 65:  return gt_launch_class<65>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
-    case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
-    default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream);
+    case 33:  return gt_launch_class<33>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 65:  return gt_launch_class<65>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
   }
 }
 
