@@ -18,6 +18,7 @@
 //   * ordered argmin: candidates are scanned in loop order with strict '<' against the running best,
 //     which carries across passes and start vectors exactly as uiDistBest does.
 #include "hop_common.cuh"
+#include <cstdlib>
 #include "hop_internal.h"
 
 namespace hop {
@@ -341,8 +342,15 @@ __host__ __device__ constexpr int gt_stride_class(int win_w)
 }
 constexpr int gt_class_threads(int) { return GT_THREADS; }
 
-template <int WS>
-__global__ void __launch_bounds__(gt_class_threads(WS), 2)
+// launch configurations (threads per CTA, min CTAs per SM); HOP_K2_CFG selects one (tuning knob)
+template <int CFG> struct GtCfg;
+template <> struct GtCfg<0> { static constexpr int T = 336, B = 2; };
+template <> struct GtCfg<1> { static constexpr int T = 224, B = 2; };
+template <> struct GtCfg<2> { static constexpr int T = 448, B = 1; };
+template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
+
+template <int WS, int CFG>
+__global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
 k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
              const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out,
              unsigned* done_flag, unsigned seq)
@@ -704,14 +712,14 @@ static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
   return GT_SHARED_BYTES + sizeof(int) * org + sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
 }
 
-template <int WS>
-static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                                   HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
-                                   unsigned* done_flag, unsigned seq)
+template <int WS, int CFG>
+static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                                 HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
+                                 unsigned* done_flag, unsigned seq)
 {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k2_gt_search<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k2_gt_search<WS, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -720,15 +728,33 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
   const int ntiles = (max_cols / tile) * (max_rows / tile);
-  const int max_groups = gt_class_threads(WS) / per_group;
+  const int max_groups = GtCfg<CFG>::T / per_group;
   int groups = ntiles < max_groups ? ntiles : max_groups;
   // fewest loop trips wins; on a tie the smaller CTA (less idle lanes in the last trip)
   for (int g = groups - 1; g >= 1; g--)
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
-  k2_gt_search<WS><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq);
+  k2_gt_search<WS, CFG><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq);
   return cudaGetLastError();
+}
+
+template <int WS>
+static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                                   HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
+                                   unsigned* done_flag, unsigned seq)
+{
+  // measured on B200 (profiles/r01_k2_launch_cfg.txt): 3 CTAs x 224 threads win for the small stride
+  // classes, 2 CTAs x 336 threads for the 64x64 class (shared memory allows only two CTAs there)
+  static int env_cfg = -2;
+  if (env_cfg == -2) { const char* e = getenv("HOP_K2_CFG"); env_cfg = e ? atoi(e) : -1; }
+  const int cfg = env_cfg >= 0 ? env_cfg : (WS == 129 ? 0 : 3);
+  switch (cfg) {
+    case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 3:  return gt_launch_cfg<WS, 3>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    default: return gt_launch_cfg<WS, 0>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+  }
 }
 
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
