@@ -37,6 +37,12 @@ def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=
     t0 = time.perf_counter()
     p = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     dt = time.perf_counter() - t0
+    if p.returncode != 0 and binary == REF_ENCODER:
+        # the unmodified CPU reference was seen to die once right after start-up on a fresh box (signal, no
+        # message); it is only the checker here, so it gets one more try -- the GPU encoder never does
+        t0 = time.perf_counter()
+        p = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        dt = time.perf_counter() - t0
     if p.returncode != 0 or not os.path.exists(os.path.join(tmp, "str.bin")):
         raise RuntimeError("encoder failed (rc=%d, cmd=%s):\n%s\n...\n%s" % (p.returncode, " ".join(cmd), p.stdout[:600], p.stdout[-600:]))
     out = {"bitstream": open(os.path.join(tmp, "str.bin"), "rb").read(),
