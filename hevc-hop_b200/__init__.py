@@ -70,6 +70,28 @@ class HopGtResult(C.Structure):
     ]
 
 
+class HopFracJob(C.Structure):
+    _fields_ = [
+        ("org_off", C.c_int64), ("ref_off", C.c_int64),
+        ("org_stride", C.c_int32), ("ref_stride", C.c_int32),
+        ("cols", C.c_int32), ("rows", C.c_int32),
+        ("mv_int", HopMv), ("use_had", C.c_int32), ("bit_depth", C.c_int32), ("cost", HopCostState),
+    ]
+
+
+class HopFracResult(C.Structure):
+    _fields_ = [("half", HopMv), ("qter", HopMv), ("cost", C.c_uint32), ("cost_half", C.c_uint32)]
+
+
+class HopMotionJob(C.Structure):
+    _fields_ = [("search", HopSearchJob), ("use_had", C.c_int32), ("use_gt", C.c_int32), ("num_pred", C.c_int32),
+                ("amvp", HopMv * HOP_MAX_PRED)]
+
+
+class HopMotionResult(C.Structure):
+    _fields_ = [("search", HopSearchResult), ("refined", C.c_int32), ("frac", HopFracResult), ("gt", HopGtResult)]
+
+
 class HopDistJob(C.Structure):
     _fields_ = [
         ("org_off", C.c_int64), ("cur_off", C.c_int64),
@@ -99,6 +121,18 @@ DIST_JOB_DT = np.dtype([
     ("org_off", "<i8"), ("cur_off", "<i8"), ("org_stride", "<i4"), ("cur_stride", "<i4"),
     ("cols", "<i4"), ("rows", "<i4"), ("func", "<i4"), ("sub_shift", "<i4"), ("bit_depth", "<i4")], align=True)
 
+FRAC_JOB_DT = np.dtype([
+    ("org_off", "<i8"), ("ref_off", "<i8"), ("org_stride", "<i4"), ("ref_stride", "<i4"),
+    ("cols", "<i4"), ("rows", "<i4"), ("mv_int", MV_DT), ("use_had", "<i4"), ("bit_depth", "<i4"), ("cost", COST_DT)], align=True)
+FRAC_RES_DT = np.dtype([("half", MV_DT), ("qter", MV_DT), ("cost", "<u4"), ("cost_half", "<u4")], align=True)
+MOTION_JOB_DT = np.dtype([("search", SEARCH_JOB_DT), ("use_had", "<i4"), ("use_gt", "<i4"), ("num_pred", "<i4"),
+                          ("amvp", MV_DT, (HOP_MAX_PRED,))], align=True)
+MOTION_RES_DT = np.dtype([("search", SEARCH_RES_DT), ("refined", "<i4"), ("frac", FRAC_RES_DT), ("gt", GT_RES_DT)], align=True)
+
+assert FRAC_JOB_DT.itemsize == C.sizeof(HopFracJob), (FRAC_JOB_DT.itemsize, C.sizeof(HopFracJob))
+assert FRAC_RES_DT.itemsize == C.sizeof(HopFracResult) == 16
+assert MOTION_JOB_DT.itemsize == C.sizeof(HopMotionJob), (MOTION_JOB_DT.itemsize, C.sizeof(HopMotionJob))
+assert MOTION_RES_DT.itemsize == C.sizeof(HopMotionResult), (MOTION_RES_DT.itemsize, C.sizeof(HopMotionResult))
 assert SEARCH_JOB_DT.itemsize == C.sizeof(HopSearchJob) == 80
 assert SEARCH_RES_DT.itemsize == C.sizeof(HopSearchResult) == 16
 assert GT_JOB_DT.itemsize == C.sizeof(HopGtJob) == 80
@@ -126,6 +160,8 @@ ABI = [
     ("hop_pattern_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_pattern_search_gt_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_dist_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    ("hop_frac_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    ("hop_motion_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     ("hop_dist_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
@@ -238,6 +274,20 @@ class HopContext:
         jobs = np.ascontiguousarray(jobs, dtype=GT_JOB_DT)
         out = np.zeros(len(jobs), dtype=GT_RES_DT)
         self._check(self.lib.hop_pattern_search_gt_batch(
+            self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
+        return out
+
+    def frac_search(self, jobs, org, ref):
+        jobs = np.ascontiguousarray(jobs, dtype=FRAC_JOB_DT)
+        out = np.zeros(len(jobs), dtype=FRAC_RES_DT)
+        self._check(self.lib.hop_frac_search_batch(
+            self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
+        return out
+
+    def motion_search(self, jobs, org, ref):
+        jobs = np.ascontiguousarray(jobs, dtype=MOTION_JOB_DT)
+        out = np.zeros(len(jobs), dtype=MOTION_RES_DT)
+        self._check(self.lib.hop_motion_search_batch(
             self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
         return out
 

@@ -44,7 +44,7 @@ struct HopCtx {
   cudaStream_t stream = nullptr;
   int          sm_count = 0;
   uint64_t     launches = 0;
-  Scratch      jobs, org, ref, out, keys, done, sweep_keys, sink;
+  Scratch      jobs, org, ref, out, keys, done, sweep_keys, k1res, sink;
   // single-call (in-encoder) path: one pinned host buffer [job | original block | result] and its device twin
   unsigned char* pin_h = nullptr;   // mapped pinned host memory (zero-copy): the GPU reads job + block from it
   unsigned char* pin_d = nullptr;   // ... through this device alias, and writes result + completion flag back
@@ -157,7 +157,7 @@ void hop_ctx_destroy(HopCtx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->done, &ctx->sweep_keys, &ctx->sink};
+  Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->done, &ctx->sweep_keys, &ctx->k1res, &ctx->sink};
   for (Scratch* s : all) if (s->p) cudaFree(s->p);
   if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
   if (ctx->plane) cudaFree(ctx->plane);
@@ -268,7 +268,8 @@ int k1_slices(const HopCtx* ctx, int n)
   return slices > K1_MAX_SLICES ? K1_MAX_SLICES : (slices < 1 ? 1 : slices);
 }
 int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-               HopSearchResult* d_out, int smem_bytes, cudaStream_t s, unsigned* done_flag = nullptr, unsigned seq = 0)
+               HopSearchResult* d_out, int smem_bytes, cudaStream_t s, unsigned* done_flag = nullptr, unsigned seq = 0,
+               int job_stride = 0)
 {
   // merge words: all-ones keys / zero tickets between launches (the kernel restores them itself)
   const size_t kcap = ctx->keys.cap, dcap = ctx->done.cap;
@@ -279,7 +280,7 @@ int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_
   if (ctx->done.cap != dcap) CU(cudaMemsetAsync(ctx->done.p, 0, ctx->done.cap, s));
   int l = 0;
   CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, (unsigned int*)ctx->done.p,
-                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq));
+                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq, job_stride));
   ctx->launches += l;
   return HOP_OK;
 }
@@ -337,9 +338,9 @@ extern "C++" {
 // [job | W x H original block | result | completion flag]; the kernel reads the job and the block straight
 // from host memory (a few KB over PCIe), writes the result and then the flag back, and the host spins on
 // the flag: one kernel launch per search, no copy calls, no stream synchronisation.
-constexpr size_t PIN_JOB = 128;                                   // job slot (both job structs are 80 B)
+constexpr size_t PIN_JOB = 128;                                   // job slot (the largest job struct is 112 B)
 constexpr size_t PIN_ORG = HOP_MAX_PU * HOP_MAX_PU * sizeof(int16_t);
-constexpr size_t PIN_OUT = 64;
+constexpr size_t PIN_OUT = 128;                                   // result slot (HopMotionResult is 76 B)
 constexpr size_t PIN_FLAG = 64;
 constexpr size_t PIN_BYTES = PIN_JOB + PIN_ORG + PIN_OUT + PIN_FLAG;
 
@@ -514,6 +515,98 @@ int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs, const int16_t* or
                           (uint32_t*)ctx->out.p, ctx->stream);
   if (st) return st;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 and the fused motion search
+// ---------------------------------------------------------------------------------------------
+int hop_frac_search_batch(HopCtx* ctx, int n, const HopFracJob* jobs, const int16_t* org, size_t org_samples,
+                          const int16_t* ref, size_t ref_samples, HopFracResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  int max_cols = 4, max_rows = 4;
+  for (int i = 0; i < n; i++) {
+    const HopFracJob& j = jobs[i];
+    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 12)
+      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d", i, j.cols, j.rows, j.bit_depth);
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+  }
+  const int16_t* d_ref = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopFracJob), org, org_samples, ref, ref_samples, sizeof(HopFracResult) * (size_t)n, &d_ref);
+  if (st) return st;
+  int l = 0;
+  CU(frac_launch(n, (const HopFracJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, (HopFracResult*)ctx->out.p,
+                 max_cols, max_rows, ctx->stream, &l));
+  ctx->launches += l;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopFracResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const int16_t* org, size_t org_samples,
+                            const int16_t* ref, size_t ref_samples, HopMotionResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  int max_cols = 4, max_rows = 4;
+  size_t smem = 0;
+  const int slices = k1_slices(ctx, n);
+  for (int i = 0; i < n; i++) {
+    const HopSearchJob& j = jobs[i].search;
+    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 12 || jobs[i].num_pred < 0 || jobs[i].num_pred > HOP_MAX_PRED)
+      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / num_pred %d", i, j.cols, j.rows, j.bit_depth, jobs[i].num_pred);
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+    const size_t b = search_smem_bytes(j, slices);
+    if (b > smem) smem = b;
+  }
+  if (smem > (size_t)(160 * 1024)) smem = 160 * 1024;
+  if ((st = ensure(ctx, ctx->k1res, sizeof(HopSearchResult) * (size_t)n))) return st;
+  HopSearchResult* d_k1 = (HopSearchResult*)ctx->k1res.p;
+  if (n == 1 && !ref) {
+    // the encoder's call: zero-copy job / block / result, two stream-ordered launches, one wait
+    if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
+    if ((st = pin_ready(ctx))) return st;
+    HopMotionJob packed = jobs[0];
+    const HopSearchJob& j = jobs[0].search;
+    const size_t need = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+    if (j.org_off < 0 || (size_t)j.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
+    packed.search.org_off = 0;
+    packed.search.org_stride = j.cols;
+    memcpy(ctx->pin_h, &packed, sizeof(packed));
+    int16_t* dst = (int16_t*)(ctx->pin_h + PIN_JOB);
+    for (int r = 0; r < j.rows; r++) memcpy(dst + (size_t)r * j.cols, org + j.org_off + (size_t)r * j.org_stride, sizeof(int16_t) * j.cols);
+    const unsigned seq = ++ctx->pin_seq;
+    const int16_t* d_org = (const int16_t*)(ctx->pin_d + PIN_JOB);
+    st = search_dev(ctx, 1, (const HopSearchJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1, (int)smem, ctx->stream,
+                    nullptr, 0, (int)sizeof(HopMotionJob));
+    if (st) return st;
+    int l = 0;
+    CU(motion_tail_launch(1, (const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
+                          (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
+                          pin_flag_dev(ctx), seq));
+    ctx->launches += l;
+    return unpack_single(ctx, seq, out);
+  }
+  const int16_t* d_ref = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopMotionJob), org, org_samples, ref, ref_samples, sizeof(HopMotionResult) * (size_t)n, &d_ref);
+  if (st) return st;
+  st = search_dev(ctx, n, (const HopSearchJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, d_k1, (int)smem, ctx->stream,
+                  nullptr, 0, (int)sizeof(HopMotionJob));
+  if (st) return st;
+  int l = 0;
+  CU(motion_tail_launch(n, (const HopMotionJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, d_k1,
+                        (HopMotionResult*)ctx->out.p, max_cols, max_rows, ctx->stream, &l));
+  ctx->launches += l;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopMotionResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
 }

@@ -32,7 +32,13 @@ cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned 
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
                           int smem_bytes, cudaStream_t stream, int* launches,
-                          unsigned* done_flag = nullptr, unsigned seq = 0);
+                          unsigned* done_flag = nullptr, unsigned seq = 0, int job_stride = 0);
+// K5 + fused motion search
+cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                        HopFracResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);
+cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                               const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
+                               cudaStream_t stream, int* launches, unsigned* done_flag = nullptr, unsigned seq = 0);
 size_t      search_smem_bytes(const HopSearchJob& job, int slices);
 constexpr int K1_DEFAULT_SMEM = 96 * 1024;   // byte-path budget when the job shapes are not known on the host
 // K3

@@ -225,13 +225,14 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
           const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys,
           unsigned int* __restrict__ done, HopSearchResult* __restrict__ out, int smem_limit,
-          unsigned* done_flag, unsigned seq)
+          unsigned* done_flag, unsigned seq, int job_stride)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned long long s_red[32];
   __shared__ int s_unclean;
   const int job_id = blockIdx.x;
-  const HopSearchJob job = jobs[job_id];
+  // job_stride: bytes between jobs (HopSearchJob arrays, or the leading member of HopMotionJob arrays)
+  const HopSearchJob job = *reinterpret_cast<const HopSearchJob*>(reinterpret_cast<const char*>(jobs) + (size_t)job_id * job_stride);
   const K1Geom g = k1_geom(job, blockIdx.y, gridDim.y);
   const bool empty = g.nx <= 0 || g.ny <= 0 || g.y_lo >= g.y_hi;    // degenerate window / slice beyond it
   const int16_t* org = org_buf + job.org_off;
@@ -336,7 +337,8 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
 
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
-                          int smem_bytes, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+                          int smem_bytes, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq,
+                          int job_stride)
 {
   static int attr_set = 0;
   const int smem_max = 160 * 1024;
@@ -349,7 +351,8 @@ cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_or
   if (slices > K1_MAX_SLICES) slices = K1_MAX_SLICES;
   if (smem_bytes > smem_max) smem_bytes = smem_max;
   if (smem_bytes < 1024) smem_bytes = 1024;
-  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes, done_flag, seq);
+  k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes, done_flag, seq,
+                                                                      job_stride ? job_stride : (int)sizeof(HopSearchJob));
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

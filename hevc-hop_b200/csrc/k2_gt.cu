@@ -20,6 +20,7 @@
 #include "hop_common.cuh"
 #include <cstdlib>
 #include "hop_internal.h"
+#include "k5_frac.cuh"
 
 namespace hop {
 
@@ -349,17 +350,15 @@ template <> struct GtCfg<1> { static constexpr int T = 224, B = 2; };
 template <> struct GtCfg<2> { static constexpr int T = 448, B = 1; };
 template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
 
-template <int WS, int CFG>
-__global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
-k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
-             const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out,
-             unsigned* done_flag, unsigned seq)
+// The whole xPatternSearchGT of one PU, executed by one CTA.  `out` is written by thread 0.
+// smem_raw: [GtShared][org rows*cols int32][window (rows+2w) x WS uint32]; when `org_staged` the int32
+// original block is already in place (the fused motion kernel stages it once for all stages).
+template <int WS>
+__device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t* __restrict__ org_buf,
+                                              const int16_t* __restrict__ ref_buf, unsigned char* smem_raw,
+                                              HopGtResult* __restrict__ out, bool org_staged)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
-  const int job_id = blockIdx.x;
-  if (job_id >= n_jobs) return;
-  const HopGtJob job = jobs[job_id];
   const int cols = job.cols, rows = job.rows;
   const int G = 2;                                              // IT_GT_GRID_SIZE
   const int nss_window = ((rows < cols ? rows : cols) >> 1) * G;  // TEncSearch.cpp:4756-4758
@@ -376,8 +375,9 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
   const int dist_shift = job.bit_depth - 8;
   const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
 
-  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
-    s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
+  if (!org_staged)
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+      s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
   if (threadIdx.x == 0) {
     for (int k = 0; k < 8; k++) sh.best_corner[k] = 0;
     sh.dist_best = job.threshold;                               // :4769
@@ -514,11 +514,24 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
       r.mv_int.ver = (int16_t)(sh.best_ss_y >> 2);
       r.best_index = sh.best_index;
     }
-    out[job_id] = r;
-    if (done_flag) {                 // single-call path: result and flag live in mapped host memory
-      __threadfence_system();
-      *(volatile unsigned*)done_flag = seq;
-    }
+    *out = r;
+  }
+}
+
+template <int WS, int CFG>
+__global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
+k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+             const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out,
+             unsigned* done_flag, unsigned seq)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  const HopGtJob job = jobs[job_id];
+  gt_search_cta<WS>(job, org_buf, ref_buf, smem_raw, &out[job_id], false);
+  if (threadIdx.x == 0 && done_flag) {     // single-call path: result and flag live in mapped host memory
+    __threadfence_system();
+    *(volatile unsigned*)done_flag = seq;
   }
 }
 
@@ -824,6 +837,153 @@ cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned 
   k2_sweep_finalize<<<(n + 255) / 256, 256, 0, stream>>>(n, d_jobs, d_keys, d_counts, d_out);
   if (launches) (*launches)++;
   return cudaGetLastError();
+}
+
+// ---- K5 stand-alone and the fused motion search ------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k5_frac_search(int n_jobs, const HopFracJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+               const int16_t* __restrict__ ref_buf, HopFracResult* __restrict__ out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  const HopFracJob job = jobs[job_id];
+  FracShared& fs = *reinterpret_cast<FracShared*>(smem_raw);
+  int* s_org = reinterpret_cast<int*>(smem_raw + 64);
+  const int16_t* org = org_buf + job.org_off;
+  for (int i = threadIdx.x; i < job.rows * job.cols; i += blockDim.x)
+    s_org[i] = org[(i / job.cols) * job.org_stride + (i % job.cols)];
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(s_org + ((job.rows * job.cols + 3) & ~3));
+  const int16_t* ref_pos = ref_buf + job.ref_off + job.mv_int.hor + (long long)job.mv_int.ver * job.ref_stride;
+  const HopFracResult r = frac_search_cta(fs, s_org, scratch, ref_pos, job.ref_stride, job.cols, job.rows,
+                                          job.bit_depth, job.use_had, job.cost, job.mv_int);
+  if (threadIdx.x == 0) out[job_id] = r;
+}
+
+cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                        HopFracResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches)
+{
+  static bool attr_set = false;
+  const size_t worst = 64 + sizeof(int) * HOP_MAX_PU * HOP_MAX_PU + frac_smem_bytes(HOP_MAX_PU, HOP_MAX_PU);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k5_frac_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const size_t smem = 64 + sizeof(int) * (((size_t)max_cols * max_rows + 3) & ~(size_t)3) + frac_smem_bytes(max_cols, max_rows);
+  k5_frac_search<<<n, 128, smem, stream>>>(n, d_jobs, d_org, d_ref, d_out);
+  if (launches) (*launches)++;
+  return cudaGetLastError();
+}
+
+// Second kernel of the fused motion search: one CTA per PU picks up the integer result of k1_search and
+// runs xPatternSearchFracDIF and xPatternSearchGT back to back (TEncSearch.cpp:4601-4642), no host in between.
+template <int WS, int CFG>
+__global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
+k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+              const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
+              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int job_id = blockIdx.x;
+  if (job_id >= n_jobs) return;
+  const HopMotionJob mj = jobs[job_id];
+  const HopSearchJob& sj = mj.search;
+  const HopSearchResult sr = k1[job_id];
+  HopMotionResult* res = &out[job_id];
+  const bool go = sr.found == 1 && !(sr.mv.hor == 0 && sr.mv.ver == 0);      // :4603-4611
+  if (threadIdx.x == 0) {
+    res->search = sr;
+    res->refined = go ? 1 : 0;
+    if (!go) {
+      res->frac.half.hor = 0; res->frac.half.ver = 0; res->frac.qter.hor = 0; res->frac.qter.ver = 0;
+      res->frac.cost = 0; res->frac.cost_half = 0;
+    }
+    if (!go || !mj.use_gt) {
+      res->gt.gt_flag = 0;
+      for (int k = 0; k < 4; k++) { res->gt.gt[k].hor = 0; res->gt.gt[k].ver = 0; }
+      res->gt.cost = 0; res->gt.mv_int.hor = 0; res->gt.mv_int.ver = 0;
+      res->gt.best_index = -1; res->gt.n_candidates = 0;
+    }
+  }
+  if (go) {
+    const int cols = sj.cols, rows = sj.rows;
+    FracShared& fs = *reinterpret_cast<FracShared*>(smem_raw);               // aliases GtShared, used before it
+    int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
+    const int16_t* org = org_buf + sj.org_off;
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+      s_org[i] = org[(i / cols) * sj.org_stride + (i % cols)];
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(s_org + ((rows * cols + 3) & ~3));
+    const int16_t* ref_pos = ref_buf + sj.ref_off + sr.mv.hor + (long long)sr.mv.ver * sj.ref_stride;
+    const HopFracResult fr = frac_search_cta(fs, s_org, scratch, ref_pos, sj.ref_stride, cols, rows, sj.bit_depth,
+                                             mj.use_had, sj.cost, sr.mv);
+    if (threadIdx.x == 0) { res->frac = fr; if (!mj.use_gt) res->gt.cost = fr.cost; }
+    if (mj.use_gt) {
+      HopGtJob gj;
+      gj.org_off = sj.org_off; gj.ref_off = sj.ref_off; gj.org_stride = sj.org_stride; gj.ref_stride = sj.ref_stride;
+      gj.cols = cols; gj.rows = rows;
+      gj.ss_cand = sr.mv;                          // pcCU->getSSBestCand()[0]
+      gj.num_pred = mj.num_pred;
+      for (int k = 0; k < HOP_MAX_PRED; k++) gj.amvp[k] = mj.amvp[k];
+      gj.threshold = fr.cost;                      // ruiCost coming out of the frac stage (:4769)
+      gj.use_had = mj.use_had; gj.bit_depth = sj.bit_depth;
+      gj.cost = sj.cost; gj.cost.cost_scale = 0;   // :4619
+      gt_search_cta<WS>(gj, org_buf, ref_buf, smem_raw, &res->gt, true);
+    }
+  }
+  if (threadIdx.x == 0 && done_flag) {
+    __threadfence_system();
+    *(volatile unsigned*)done_flag = seq;
+  }
+}
+
+static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
+{
+  const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
+  const size_t org = ((size_t)max_cols * max_rows + 3) & ~(size_t)3;
+  const size_t win = sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
+  const size_t fr = frac_smem_bytes(max_cols, max_rows);
+  return GT_SHARED_BYTES + sizeof(int) * org + (win > fr ? win : fr);
+}
+
+template <int WS, int CFG>
+static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                                   const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
+                                   cudaStream_t stream, unsigned* done_flag, unsigned seq)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_motion_tail<WS, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)motion_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
+  const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
+  const int ntiles = (max_cols / tile) * (max_rows / tile);
+  const int max_groups = GtCfg<CFG>::T / per_group;
+  int groups = ntiles < max_groups ? ntiles : max_groups;
+  for (int g = groups - 1; g >= 1; g--)
+    if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
+  int threads = per_group * groups;
+  if (threads < 64) threads = 64;
+  k_motion_tail<WS, CFG><<<n, threads, motion_smem_bytes(WS, max_cols, max_rows), stream>>>(
+      n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq);
+  return cudaGetLastError();
+}
+
+cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                               const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
+                               cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+{
+  const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
+  if (launches) (*launches)++;
+  switch (gt_stride_class(win_w)) {
+    case 33:  return motion_tail_cfg<33, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 65:  return motion_tail_cfg<65, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 97:  return motion_tail_cfg<97, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
+    default:  return motion_tail_cfg<129, 0>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
+  }
 }
 
 }  // namespace hop

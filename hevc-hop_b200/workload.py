@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
+from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, FRAC_JOB_DT, MOTION_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
 from .lenslet import lenslet_luma
 
 SEARCH_RANGE = 128
@@ -109,6 +109,34 @@ class PuBatch:
 
     def passes(self):
         return gt_passes(self.cols, self.rows)
+
+    def frac_jobs(self, mv_int=None):
+        """xPatternSearchFracDIF jobs refining `mv_int` (default: the K2 start vectors, which lie in the
+        fully coded rows above the PU so that the 8-tap support is valid)."""
+        fj = np.zeros(self.n, dtype=FRAC_JOB_DT)
+        for k in ("org_off", "ref_off", "org_stride", "ref_stride", "cols", "rows", "use_had", "bit_depth"):
+            fj[k] = self.gt_jobs[k]
+        mv = (self.gt_jobs["ss_cand"] if mv_int is None else mv_int).copy()
+        if mv_int is None:
+            # the 8-tap support reaches 4 samples beyond the block: keep it inside this PU's plane
+            mv["hor"] = np.maximum(mv["hor"], -self.ox + 4)
+            mv["ver"] = np.maximum(mv["ver"], -self.oy + 4)
+        fj["mv_int"] = mv
+        fj["cost"] = self.gt_jobs["cost"]
+        return fj
+
+    def motion_jobs(self, use_gt=1):
+        mj = np.zeros(self.n, dtype=MOTION_JOB_DT)
+        sj = self.search_jobs.copy()
+        # the frac stage reads 4 samples beyond the matched block: keep the window 4 away from the plane edge
+        sj["rng_left"] = np.maximum(sj["rng_left"], -self.ox + 4)
+        sj["rng_top"] = np.maximum(sj["rng_top"], -self.oy + 4)
+        mj["search"] = sj
+        mj["use_had"] = self.gt_jobs["use_had"]
+        mj["use_gt"] = use_gt
+        mj["num_pred"] = self.gt_jobs["num_pred"]
+        mj["amvp"] = self.gt_jobs["amvp"]
+        return mj
 
 
 def gt_passes(cols, rows):

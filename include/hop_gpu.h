@@ -112,6 +112,51 @@ typedef struct HopGtResult {
 } HopGtResult;
 
 /* ---------------------------------------------------------------------------------------------
+ * K5 -- one xPatternSearchFracDIF call (TEncSearch.cpp:6564-6610): half- then quarter-pel refinement of
+ * the integer vector with the 8-tap DCT-IF planes (xExtDIFUpSamplingH/Q :7818-8011,
+ * TComInterpolationFilter.cpp:92-254) and 2 x 9 Hadamard/SAD costs (xPatternRefinement :709-761).
+ * The cost it returns is the threshold xPatternSearchGT has to beat.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HopFracJob {
+  int64_t  org_off;
+  int64_t  ref_off;        /* piRefY: the PU's own position in the reference plane                  */
+  int32_t  org_stride;
+  int32_t  ref_stride;
+  int32_t  cols, rows;
+  HopMv    mv_int;         /* *pcMvInt, integer pel                                                  */
+  int32_t  use_had;        /* m_pcEncCfg->getUseHADME()                                              */
+  int32_t  bit_depth;
+  HopCostState cost;       /* lambda_cost and pred; cost_scale is set by the stage (1 half, 0 quarter) */
+} HopFracJob;
+
+typedef struct HopFracResult {
+  HopMv    half;           /* rcMvHalf  in {-1,0,1}^2                                                */
+  HopMv    qter;           /* rcMvQter  in {-1,0,1}^2                                                */
+  uint32_t cost;           /* ruiCost after the quarter-pel stage                                    */
+  uint32_t cost_half;      /* extra, for tests: best cost of the half-pel stage                      */
+} HopFracResult;
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole SS motion search of one PU in ONE call: xPatternSearch -> (valid and non-zero vector?) ->
+ * xPatternSearchFracDIF -> xPatternSearchGT, i.e. the GPU part of TEncSearch::xMotionEstimation
+ * (TEncSearch.cpp:4572-4642) without a host round trip between the stages.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HopMotionJob {
+  HopSearchJob search;     /* cost.cost_scale must be 2 (:4560)                                      */
+  int32_t  use_had;        /* getUseHADME(): frac refinement and GT distortion                        */
+  int32_t  use_gt;         /* bUseGT (:4627)                                                          */
+  int32_t  num_pred;       /* AMVPInfo::iN                                                            */
+  HopMv    amvp[HOP_MAX_PRED];
+} HopMotionJob;
+
+typedef struct HopMotionResult {
+  HopSearchResult search;  /* found == 0 or mv == (0,0): the later stages did not run (:4603-4611)    */
+  int32_t  refined;        /* 1 when the frac (and, if use_gt, the GT) stage ran                      */
+  HopFracResult   frac;
+  HopGtResult     gt;      /* threshold = frac.cost, ss_cand = search.mv                              */
+} HopMotionResult;
+
+/* ---------------------------------------------------------------------------------------------
  * K3 -- one DistFunc call (TComRdCost.cpp:513-1010, 1366-1708).
  * ------------------------------------------------------------------------------------------- */
 typedef enum HopDistFunc {
@@ -175,6 +220,14 @@ int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs,
                    const int16_t* org, size_t org_samples,
                    const int16_t* cur, size_t cur_samples,
                    uint32_t* out);
+int hop_frac_search_batch(HopCtx* ctx, int n, const HopFracJob* jobs,
+                          const int16_t* org, size_t org_samples,
+                          const int16_t* ref, size_t ref_samples,
+                          HopFracResult* out);
+int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs,
+                            const int16_t* org, size_t org_samples,
+                            const int16_t* ref, size_t ref_samples,
+                            HopMotionResult* out);
 
 /* ---- device entry points (everything already resident in HBM, asynchronous on `stream`) ---- */
 int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,

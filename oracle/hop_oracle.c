@@ -516,6 +516,143 @@ void orc_gt_sweep_keys_batch(int n, const HopGtJob* jobs, const int16_t* org, co
   for (int i = 0; i < n; i++) keys[i] = orc_gt_sweep_key(&jobs[i], org, ref, cand_begin, cand_end, NULL);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * K5 -- fractional-pel refinement.  The reference materialises 16 planes (xExtDIFUpSamplingH/Q) and
+ * indexes them with pointer fix-ups (xPatternRefinement :728-741); what every tested position reads is
+ * the standard two-stage HEVC luma interpolation at that quarter-pel displacement: horizontal 8-tap
+ * (isFirst, 14-bit intermediate, TComInterpolationFilter.cpp:173-254 / filterCopy :113-132) then
+ * vertical 8-tap (isLast, rounding + clip).  Restated per position; pinned against the compiled
+ * reference in tests/test_frac.py.
+ * ---------------------------------------------------------------------------------------------- */
+static const int16_t LUMA_FILTER[4][8] = {                 /* m_lumaFilter, TComInterpolationFilter.cpp:55-61 */
+  {0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+
+void orc_interp_block(const int16_t* src, int stride, int qx, int qy, int cols, int rows, int bit_depth, int16_t* dst)
+{
+  const int ix = qx >> 2, fx = qx & 3, iy = qy >> 2, fy = qy & 3;   /* floor / fraction of the displacement */
+  const int head = 14 - bit_depth;                                  /* IF_INTERNAL_PREC - bitDepth */
+  const int16_t max_val = (int16_t)((1 << bit_depth) - 1);
+  int16_t* tmp = (int16_t*)malloc(sizeof(int16_t) * (rows + 7) * cols);
+  for (int r = -3; r < rows + 4; r++) {                             /* horizontal stage, isFirst && !isLast */
+    const int16_t* s = src + (r + iy) * stride + ix;
+    for (int c = 0; c < cols; c++) {
+      int16_t v;
+      if (fx == 0) {
+        v = (int16_t)(s[c] << head);                                /* filterCopy isFirst :115-127 */
+        v = (int16_t)(v - (int16_t)8192);
+      } else {
+        int sum = 0;
+        for (int k = 0; k < 8; k++) sum += s[c + k - 3] * LUMA_FILTER[fx][k];
+        const int shift = 6 - head;
+        const int offset = -8192 << shift;
+        v = (int16_t)((sum + offset) >> shift);
+      }
+      tmp[(r + 3) * cols + c] = v;
+    }
+  }
+  for (int r = 0; r < rows; r++) {                                  /* vertical stage, !isFirst && isLast */
+    for (int c = 0; c < cols; c++) {
+      int16_t v;
+      if (fy == 0) {
+        int16_t off = (int16_t)8192;                                /* filterCopy isLast :135-149 */
+        off = (int16_t)(off + (head ? (1 << (head - 1)) : 0));
+        v = (int16_t)((tmp[(r + 3) * cols + c] + off) >> head);
+      } else {
+        int sum = 0;
+        for (int k = 0; k < 8; k++) sum += tmp[(r + k) * cols + c] * LUMA_FILTER[fy][k];
+        const int shift = 6 + head;
+        const int offset = (1 << (shift - 1)) + (8192 << 6);
+        v = (int16_t)((sum + offset) >> shift);
+      }
+      if (v < 0) v = 0;
+      if (v > max_val) v = max_val;
+      dst[r * cols + c] = v;
+    }
+  }
+  free(tmp);
+}
+
+static const int8_t REFINE_H[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};   /* s_acMvRefineH :46-57 */
+static const int8_t REFINE_Q[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};   /* s_acMvRefineQ :59-70 */
+
+void orc_frac_search(const HopFracJob* job, const int16_t* org_buf, const int16_t* ref_buf, HopFracResult* out)
+{
+  const int cols = job->cols, rows = job->rows;
+  const int16_t* org = org_buf + job->org_off;
+  const int16_t* src = ref_buf + job->ref_off + job->mv_int.hor + job->mv_int.ver * job->ref_stride;   /* :6579 */
+  int16_t* blk = (int16_t*)malloc(sizeof(int16_t) * rows * cols);
+  HopCostState cs = job->cost;
+  uint32_t best = HOP_MAX_UINT;
+  int best_i = 0;
+  /* half-pel stage: baseRefMv (0,0), iFrac 2, rcMvFrac = int << 1, cost scale 1 (:4615, 6594-6598) */
+  cs.cost_scale = 1;
+  for (int i = 0; i < 9; i++) {
+    const int hx = REFINE_H[i][0], hy = REFINE_H[i][1];
+    orc_interp_block(src, job->ref_stride, hx * 2, hy * 2, cols, rows, job->bit_depth, blk);
+    uint32_t d = job->use_had ? orc_hads(org, job->org_stride, blk, cols, cols, rows, job->bit_depth)
+                              : orc_sad(org, job->org_stride, blk, cols, cols, rows, 0, job->bit_depth);
+    d += orc_get_cost_xy(&cs, (job->mv_int.hor << 1) + hx, (job->mv_int.ver << 1) + hy);   /* :747 */
+    if (d < best) { best = d; best_i = i; }
+  }
+  const int half_x = REFINE_H[best_i][0], half_y = REFINE_H[best_i][1];
+  out->half.hor = (int16_t)half_x; out->half.ver = (int16_t)half_y;
+  out->cost_half = best;
+  /* quarter-pel stage: baseRefMv = half << 1, iFrac 1, rcMvFrac = ((int << 1) + half) << 1, cost scale 0 (:6600-6608) */
+  cs.cost_scale = 0;
+  best = HOP_MAX_UINT; best_i = 0;
+  const int base_x = half_x << 1, base_y = half_y << 1;
+  const int mvq_x = (((job->mv_int.hor << 1) + half_x) << 1), mvq_y = (((job->mv_int.ver << 1) + half_y) << 1);
+  for (int i = 0; i < 9; i++) {
+    const int qx = REFINE_Q[i][0], qy = REFINE_Q[i][1];
+    orc_interp_block(src, job->ref_stride, base_x + qx, base_y + qy, cols, rows, job->bit_depth, blk);
+    uint32_t d = job->use_had ? orc_hads(org, job->org_stride, blk, cols, cols, rows, job->bit_depth)
+                              : orc_sad(org, job->org_stride, blk, cols, cols, rows, 0, job->bit_depth);
+    d += orc_get_cost_xy(&cs, mvq_x + qx, mvq_y + qy);
+    if (d < best) { best = d; best_i = i; }
+  }
+  out->qter.hor = REFINE_Q[best_i][0]; out->qter.ver = REFINE_Q[best_i][1];
+  out->cost = best;
+  free(blk);
+}
+
+void orc_frac_search_batch(int n, const HopFracJob* jobs, const int16_t* org, const int16_t* ref, HopFracResult* out)
+{
+  for (int i = 0; i < n; i++) orc_frac_search(&jobs[i], org, ref, &out[i]);
+}
+
+void orc_motion_search_batch(int n, const HopMotionJob* jobs, const int16_t* org, const int16_t* ref, HopMotionResult* out)
+{
+  for (int i = 0; i < n; i++) {
+    const HopMotionJob* mj = &jobs[i];
+    HopMotionResult* r = &out[i];
+    memset(r, 0, sizeof(*r));
+    orc_pattern_search(&mj->search, org, ref, &r->search);                      /* :4582 */
+    r->gt.cost = 0; r->gt.best_index = -1;
+    if (!r->search.found || (r->search.mv.hor == 0 && r->search.mv.ver == 0)) continue;   /* :4603-4611 */
+    HopFracJob fj;
+    memset(&fj, 0, sizeof(fj));
+    fj.org_off = mj->search.org_off; fj.ref_off = mj->search.ref_off;
+    fj.org_stride = mj->search.org_stride; fj.ref_stride = mj->search.ref_stride;
+    fj.cols = mj->search.cols; fj.rows = mj->search.rows;
+    fj.mv_int = r->search.mv; fj.use_had = mj->use_had; fj.bit_depth = mj->search.bit_depth;
+    fj.cost = mj->search.cost;
+    orc_frac_search(&fj, org, ref, &r->frac);                                    /* :4617 */
+    r->refined = 1;
+    r->gt.cost = r->frac.cost;
+    if (!mj->use_gt) continue;                                                   /* :4627 */
+    HopGtJob gj;
+    memset(&gj, 0, sizeof(gj));
+    gj.org_off = fj.org_off; gj.ref_off = fj.ref_off; gj.org_stride = fj.org_stride; gj.ref_stride = fj.ref_stride;
+    gj.cols = fj.cols; gj.rows = fj.rows;
+    gj.ss_cand = r->search.mv;                /* pcCU->getSSBestCand()[0] == the integer winner */
+    gj.num_pred = mj->num_pred;
+    for (int k = 0; k < HOP_MAX_PRED; k++) gj.amvp[k] = mj->amvp[k];
+    gj.threshold = r->frac.cost; gj.use_had = mj->use_had; gj.bit_depth = fj.bit_depth;
+    gj.cost = mj->search.cost; gj.cost.cost_scale = 0;                           /* :4619 */
+    orc_pattern_search_gt(&gj, org, ref, &r->gt);
+  }
+}
+
 void orc_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* org, const int16_t* ref,
                               HopSearchResult* out)
 {

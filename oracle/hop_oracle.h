@@ -60,6 +60,15 @@ void orc_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* or
 void orc_pattern_search_gt_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref,
                                  HopGtResult* out);
 
+/* K5: xPatternSearchFracDIF, TEncSearch.cpp:6564-6610 (+ xPatternRefinement :709-761, xExtDIFUpSamplingH/Q
+ * :7818-8011, TComInterpolationFilter.cpp:92-254).  orc_interp_block is the plane the reference would read
+ * for the quarter-pel displacement (qx,qy) from the integer position `src`. */
+void orc_interp_block(const int16_t* src, int stride, int qx, int qy, int cols, int rows, int bit_depth, int16_t* dst);
+void orc_frac_search(const HopFracJob* job, const int16_t* org, const int16_t* ref, HopFracResult* out);
+void orc_frac_search_batch(int n, const HopFracJob* jobs, const int16_t* org, const int16_t* ref, HopFracResult* out);
+/* xMotionEstimation's GPU part in one go: K1 -> frac -> GT (TEncSearch.cpp:4572-4642) */
+void orc_motion_search_batch(int n, const HopMotionJob* jobs, const int16_t* org, const int16_t* ref, HopMotionResult* out);
+
 /* Exhaustive sweep (reference mode IT_GT_SEARCH 1 + IT_GT_GRID_SIZE 1, TEncSearch.cpp:4989-5091): the job's
  * ss_cand is pcMvInt; amvp is ignored.  The slice [cand_begin, cand_end) counts AFFINE candidates in loop
  * order (7200 for N = 2). */

@@ -105,6 +105,31 @@ public:
     out->n_candidates = 0;
   }
 
+  void fracSearch(const HopFracJob* j, const int16_t* org, const int16_t* ref, HopFracResult* out)
+  {
+    g_bitDepthY = j->bit_depth;
+    cfg.setUseHADME(j->use_had != 0);
+    HopCostState cs = j->cost;
+    cs.cost_scale = 1;                         // xMotionEstimation: setCostScale(1) before the call (:4615)
+    setCost(cs);
+    pattern.initPattern((Pel*)org + j->org_off, NULL, NULL, j->cols, j->rows, j->org_stride, 0, 0);
+    TComMv mvInt(j->mv_int.hor, j->mv_int.ver), mvHalf, mvQter;
+    UInt cost = 0;
+    xPatternSearchFracDIF(&cu, &pattern, (Pel*)ref + j->ref_off, j->ref_stride, &mvInt, mvHalf, mvQter, cost, false);
+    memset(out, 0, sizeof(*out));
+    out->half.hor = mvHalf.getHor(); out->half.ver = mvHalf.getVer();
+    out->qter.hor = mvQter.getHor(); out->qter.ver = mvQter.getVer();
+    out->cost = cost;
+  }
+
+  // debugging aid for tests: copy one of the 16 interpolated planes left behind by the last frac search
+  void fracPlane(int ver, int hor, int16_t* dst, int cols, int rows)
+  {
+    Pel* p = m_filteredBlock[ver][hor].getLumaAddr();
+    Int st = m_filteredBlock[ver][hor].getStride();
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) dst[r * cols + c] = p[r * st + c];
+  }
+
   // protected members of TComPrediction (TComPrediction.h:106,110), re-exported
   void calcParam(Int* x, Int* y, Double* h, Int w, Int hh) { calcParamProjective(x, y, h, w, hh); }
   void warp(Pel* r, Pel* aux, Double* h, Int W, Int H, Int stride, Int nss) { ProjectiveTransform(r, aux, h, W, H, stride, nss); }
@@ -155,6 +180,11 @@ void ref_pattern_search_batch(int n, const HopSearchJob* jobs, const int16_t* or
 
 void ref_pattern_search_gt_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* refbuf, HopGtResult* out)
 { for (int i = 0; i < n; i++) ref()->patternSearchGT(&jobs[i], org, refbuf, &out[i]); }
+
+void ref_frac_search_batch(int n, const HopFracJob* jobs, const int16_t* org, const int16_t* refbuf, HopFracResult* out)
+{ for (int i = 0; i < n; i++) ref()->fracSearch(&jobs[i], org, refbuf, &out[i]); }
+
+void ref_frac_plane(int ver, int hor, int16_t* dst, int cols, int rows) { ref()->fracPlane(ver, hor, dst, cols, rows); }
 
 /* TComRdCost::xGetComponentBits is private; getBitsGT (public, TComRdCost.h:204) exposes it. */
 uint32_t ref_bits_gt(int x0, int y0, int x1, int y1, int x2, int y2)

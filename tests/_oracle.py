@@ -95,6 +95,32 @@ def oracle():
     return _cache["orc"]
 
 
+def frac_search(jobs, org, ref, which="orc"):
+    """xPatternSearchFracDIF: C restatement (which="orc") or the compiled reference (which="ref")."""
+    chk = oracle() if which == "orc" else ref_lib()
+    hop = oracle().hop
+    jobs = np.ascontiguousarray(jobs, dtype=hop.FRAC_JOB_DT)
+    out = np.zeros(len(jobs), dtype=hop.FRAC_RES_DT)
+    fn = getattr(chk.lib, ("orc_" if which == "orc" else "ref_") + "frac_search_batch")
+    fn.argtypes = [C.c_int, _P, _P, _P, _P]; fn.restype = None
+    fn(len(jobs), _np(jobs), _np(org), _np(ref), _np(out))
+    return out
+
+
+def motion_search(jobs, org, ref):
+    o = oracle()
+    jobs = np.ascontiguousarray(jobs, dtype=o.hop.MOTION_JOB_DT)
+    out = np.zeros(len(jobs), dtype=o.hop.MOTION_RES_DT)
+    fn = o.lib.orc_motion_search_batch
+    fn.argtypes = [C.c_int, _P, _P, _P, _P]; fn.restype = None
+    fn(len(jobs), _np(jobs), _np(org), _np(ref), _np(out))
+    return out
+
+
+def ref_lib():
+    return ref()
+
+
 def gt_sweep(jobs, org, ref):
     """Oracle statement of the exhaustive sweep (reference mode IT_GT_SEARCH 1 / IT_GT_GRID_SIZE 1)."""
     o = oracle()

@@ -83,6 +83,21 @@ def main():
     sw["n_sweep"] = np.int64(k)
     np.savez_compressed(os.path.join(HERE, "sweep_golden.npz"), **sw)
 
+    # fractional-pel refinement: outputs of the reference's xPatternSearchFracDIF
+    fr = {}
+    k = 0
+    for bit_depth, shapes in ((8, [(8, 8), (16, 16), (8, 4), (4, 8), (16, 12), (32, 8), (32, 32), (64, 64), (24, 32)]), (10, [(8, 8), (16, 8)])):
+        for (c, r) in shapes:
+            for use_had in (1, 0):
+                b = PuBatch(c, r, 3, seed=700 + k, bit_depth=bit_depth, sr=20, use_had=use_had, n_start=1)
+                tag = "f%02d" % k
+                fj = b.frac_jobs()
+                fr[tag + "_org"], fr[tag + "_ref"], fr[tag + "_jobs"] = b.org, b.ref, fj
+                fr[tag + "_out"] = _oracle.frac_search(fj, b.org, b.ref, "ref")
+                k += 1
+    fr["n_frac"] = np.int64(k)
+    np.savez_compressed(os.path.join(HERE, "frac_golden.npz"), **fr)
+
     # border extension: random plane with -1 staircase, reference extendPicBorder (margin 80)
     rng = np.random.default_rng(7)
     pic_w, pic_h, m = 96, 72, 80
