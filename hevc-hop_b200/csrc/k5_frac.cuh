@@ -8,8 +8,8 @@
 // intermediate (isFirst), vertical 8-tap with rounding and clip (isLast); integer arithmetic only.
 //
 // One CTA per PU.  Per stage the 9 positions are 3 horizontal x 3 vertical displacements: the three
-// horizontal intermediates are built once in shared memory, then a task = (position, Hadamard tile)
-// filters its tile vertically into registers, subtracts the original block and runs the butterflies.
+// horizontal intermediates are built once in shared memory; the vertical filter, the difference to the
+// original block and the Hadamard butterflies run in two fine-grained phases (see frac_stage).
 #pragma once
 #include "hop_common.cuh"
 #include "hop_internal.h"
@@ -27,57 +27,32 @@ struct FracShared {
   uint32_t best_cost;
 };
 
+constexpr int FRAC_CHUNK = 3;   // positions handled per shared-memory round (9 positions = 3 rounds)
+
 __host__ __device__ inline size_t frac_smem_bytes(int cols, int rows)
 {
   // [source region (rows+8) x (cols+8) int16][3 horizontal intermediates (rows+8) x cols int16]
-  return (sizeof(int16_t) * ((size_t)(rows + 8) * (cols + 8) + 3 * (size_t)(rows + 8) * cols) + 15) & ~(size_t)15;
+  // [row-transformed differences of FRAC_CHUNK positions, rows x cols int16]
+  return (sizeof(int16_t) * ((size_t)(rows + 8) * (cols + 8) + 3 * (size_t)(rows + 8) * cols +
+                             (size_t)FRAC_CHUNK * rows * cols) + 15) & ~(size_t)15;
 }
 
-template <int N>
-struct FracTile {
-  int d[N * N];
-  __device__ __forceinline__ uint32_t satd()
-  {
-#pragma unroll
-    for (int y = 0; y < N; y++)
-#pragma unroll
-      for (int len = 1; len < N; len <<= 1)
-#pragma unroll
-        for (int i = 0; i < N; i += len << 1)
-#pragma unroll
-          for (int j = i; j < i + len; j++) { int a = d[y * N + j], b = d[y * N + j + len]; d[y * N + j] = a + b; d[y * N + j + len] = a - b; }
-#pragma unroll
-    for (int x = 0; x < N; x++)
-#pragma unroll
-      for (int len = 1; len < N; len <<= 1)
-#pragma unroll
-        for (int i = 0; i < N; i += len << 1)
-#pragma unroll
-          for (int j = i; j < i + len; j++) { int a = d[j * N + x], b = d[(j + len) * N + x]; d[j * N + x] = a + b; d[(j + len) * N + x] = a - b; }
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < N * N; k++) s = __sad(d[k], 0, s);
-    return N == 8 ? (s + 2) >> 2 : (s + 1) >> 1;     // xCalcHADs8x8 / xCalcHADs4x4 rounding
-  }
-  __device__ __forceinline__ uint32_t sad()
-  {
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < N * N; k++) s = __sad(d[k], 0, s);
-    return s;
-  }
-};
-
-// one refinement stage: positions base + 2^scale_shift * refine[i] (quarter-pel units), i = 0..8
+// one refinement stage: positions base + step * refine[i] (quarter-pel units), i = 0..8.
 //   s_org : original block, int32, stride cols          s_src : staged source region
-//   s_tmp : 3 planes, plane index = refine x-component + 1
+//   s_tmp : 3 horizontal intermediates, plane index = refine x-component + 1
+//   s_rt  : row-transformed differences of FRAC_CHUNK positions
+// Two phases per round so that even an 8x8 PU keeps ~70 threads busy: (A) one thread per tile ROW filters
+// its N pixels vertically, subtracts the original and runs the horizontal N-point butterflies; (B) one
+// thread per tile COLUMN runs the vertical butterflies; the N column sums of a tile meet by shuffles for
+// the per-tile rounding.
 template <int N>
 __device__ __forceinline__ void frac_stage(FracShared& fs, const int* __restrict__ s_org, const int16_t* __restrict__ s_src,
-                                           int16_t* __restrict__ s_tmp, int cols, int rows, int bit_depth, int use_had,
-                                           int base_qx, int base_qy, int step, const int8_t (*refine)[2])
+                                           int16_t* __restrict__ s_tmp, int16_t* __restrict__ s_rt, int cols, int rows,
+                                           int bit_depth, int use_had, int base_qx, int base_qy, int step,
+                                           const int8_t (*refine)[2])
 {
   const int head = 14 - bit_depth;                     // IF_INTERNAL_PREC - bitDepth
-  const int src_w = cols + 8, plane = (rows + 8) * cols;
+  const int src_w = cols + 8, plane = (rows + 8) * cols, blk = rows * cols;
   if (threadIdx.x < 9) fs.dist[threadIdx.x] = 0;
   // horizontal intermediates for the three x displacements (isFirst && !isLast)
   for (int i = threadIdx.x; i < 3 * plane; i += blockDim.x) {
@@ -99,40 +74,82 @@ __device__ __forceinline__ void frac_stage(FracShared& fs, const int* __restrict
     s_tmp[i] = v;
   }
   __syncthreads();
-  const int tiles_x = cols / N, ntiles = tiles_x * (rows / N);
+  const int tiles_x = cols / N;
   const int max_val = (1 << bit_depth) - 1;
-  for (int t = threadIdx.x; t < 9 * ntiles; t += blockDim.x) {
-    const int i = t % 9, tile = t / 9;
-    const int tx = (tile % tiles_x) * N, ty = (tile / tiles_x) * N;
-    const int qy = base_qy + step * refine[i][1];
-    const int iy = qy >> 2, fy = qy & 3;
-    const int16_t* tp = s_tmp + (refine[i][0] + 1) * plane;
-    FracTile<N> ft;
-#pragma unroll
-    for (int r = 0; r < N; r++) {
+  for (int i0 = 0; i0 < 9; i0 += FRAC_CHUNK) {
+    // phase A: (position, row y, tile column tx) -> N pixels
+    for (int t = threadIdx.x; t < FRAC_CHUNK * rows * tiles_x; t += blockDim.x) {
+      const int tx = t % tiles_x, y = (t / tiles_x) % rows, il = t / (tiles_x * rows), i = i0 + il;
+      const int qy = base_qy + step * refine[i][1];
+      const int iy = qy >> 2, fy = qy & 3;
+      const int16_t* tp = s_tmp + (refine[i][0] + 1) * plane + (y + iy + 1) * cols + tx * N;   // source row y+iy-3 is tmp row +4
+      int d[N];
 #pragma unroll
       for (int c = 0; c < N; c++) {
-        // tmp row index of source row (ty + r + iy + k - 3) is that + 4
-        const int16_t* col = tp + (ty + r + iy + 1) * cols + tx + c;
         int v;
         if (fy == 0) {
           int16_t off = (int16_t)8192;                 // filterCopy isLast, :135-149
           off = (int16_t)(off + (head ? (1 << (head - 1)) : 0));
-          v = (int16_t)((col[3 * cols] + off) >> head);
+          v = (int16_t)((tp[3 * cols + c] + off) >> head);
         } else {
           int sum = 0;
 #pragma unroll
-          for (int k = 0; k < 8; k++) sum += (int)col[k * cols] * c_luma_filter[fy][k];
+          for (int k = 0; k < 8; k++) sum += (int)tp[k * cols + c] * c_luma_filter[fy][k];
           const int shift = 6 + head;
           v = (int16_t)((sum + (1 << (shift - 1)) + (8192 << 6)) >> shift);
         }
         v = min(max(v, 0), max_val);
-        ft.d[r * N + c] = s_org[(ty + r) * cols + tx + c] - v;
+        d[c] = s_org[y * cols + tx * N + c] - v;
+      }
+      if (use_had) {
+#pragma unroll
+        for (int len = 1; len < N; len <<= 1)
+#pragma unroll
+          for (int a = 0; a < N; a += len << 1)
+#pragma unroll
+            for (int j = a; j < a + len; j++) { const int u = d[j], w = d[j + len]; d[j] = u + w; d[j + len] = u - w; }
+#pragma unroll
+        for (int c = 0; c < N; c++) s_rt[il * blk + y * cols + tx * N + c] = (int16_t)d[c];
+      } else {
+        unsigned sum = 0;
+#pragma unroll
+        for (int c = 0; c < N; c++) sum = __sad(d[c], 0, sum);
+        atomicAdd(&fs.dist[i], sum);
       }
     }
-    atomicAdd(&fs.dist[i], use_had ? ft.satd() : ft.sad());
+    __syncthreads();
+    if (use_had) {
+      // phase B: (position, tile row ty, column x): vertical butterflies; x is the fastest index, so the N
+      // columns of a tile sit in N adjacent lanes
+      const int ntask = FRAC_CHUNK * (rows / N) * cols;
+      for (int t0 = 0; t0 < ntask; t0 += blockDim.x) {
+        const int t = t0 + threadIdx.x;
+        unsigned sum = 0;
+        int i = 0;
+        if (t < ntask) {
+          const int x = t % cols, ty = (t / cols) % (rows / N), il = t / (cols * (rows / N));
+          i = i0 + il;
+          int d[N];
+#pragma unroll
+          for (int r = 0; r < N; r++) d[r] = s_rt[il * blk + (ty * N + r) * cols + x];
+#pragma unroll
+          for (int len = 1; len < N; len <<= 1)
+#pragma unroll
+            for (int a = 0; a < N; a += len << 1)
+#pragma unroll
+              for (int j = a; j < a + len; j++) { const int u = d[j], w = d[j + len]; d[j] = u + w; d[j + len] = u - w; }
+#pragma unroll
+          for (int r = 0; r < N; r++) sum = __sad(d[r], 0, sum);
+        }
+        // tile sum over its N columns (lanes x .. x+N-1 are aligned to N because cols % N == 0)
+#pragma unroll
+        for (int o = 1; o < N; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (t < ntask && (threadIdx.x & (N - 1)) == 0)
+          atomicAdd(&fs.dist[i], N == 8 ? (sum + 2) >> 2 : (sum + 1) >> 1);   // xCalcHADs8x8 / 4x4 rounding
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
 }
 
 // Whole xPatternSearchFracDIF for one PU by one CTA.  s_org must hold the original block (int32, stride
@@ -144,6 +161,7 @@ __device__ __forceinline__ HopFracResult frac_search_cta(FracShared& fs, const i
 {
   int16_t* s_src = reinterpret_cast<int16_t*>(scratch);
   int16_t* s_tmp = s_src + (rows + 8) * (cols + 8);
+  int16_t* s_rt = s_tmp + 3 * (rows + 8) * cols;
   const int src_w = cols + 8;
   // source region: x in [-4, cols+4), y in [-4, rows+4) around the integer position (:6579)
   for (int i = threadIdx.x; i < (rows + 8) * src_w; i += blockDim.x) {
@@ -155,8 +173,8 @@ __device__ __forceinline__ HopFracResult frac_search_cta(FracShared& fs, const i
   const int dist_shift = bit_depth - 8;
   HopFracResult res;
   // half-pel stage: baseRefMv (0,0), iFrac 2, mv cost in half-pel units, cost scale 1 (:4615, 6594-6598)
-  if (tile_n == 8) frac_stage<8>(fs, s_org, s_src, s_tmp, cols, rows, bit_depth, use_had, 0, 0, 2, c_refine_h);
-  else             frac_stage<4>(fs, s_org, s_src, s_tmp, cols, rows, bit_depth, use_had, 0, 0, 2, c_refine_h);
+  if (tile_n == 8) frac_stage<8>(fs, s_org, s_src, s_tmp, s_rt, cols, rows, bit_depth, use_had, 0, 0, 2, c_refine_h);
+  else             frac_stage<4>(fs, s_org, s_src, s_tmp, s_rt, cols, rows, bit_depth, use_had, 0, 0, 2, c_refine_h);
   if (threadIdx.x == 0) {
     cs.cost_scale = 1;
     uint32_t best = HOP_MAX_UINT; int bi = 0;
@@ -172,8 +190,8 @@ __device__ __forceinline__ HopFracResult frac_search_cta(FracShared& fs, const i
   res.cost_half = fs.best_cost;
   __syncthreads();
   // quarter-pel stage: baseRefMv = half << 1, iFrac 1, mv cost in quarter-pel units, cost scale 0 (:6600-6608)
-  if (tile_n == 8) frac_stage<8>(fs, s_org, s_src, s_tmp, cols, rows, bit_depth, use_had, half_x << 1, half_y << 1, 1, c_refine_q);
-  else             frac_stage<4>(fs, s_org, s_src, s_tmp, cols, rows, bit_depth, use_had, half_x << 1, half_y << 1, 1, c_refine_q);
+  if (tile_n == 8) frac_stage<8>(fs, s_org, s_src, s_tmp, s_rt, cols, rows, bit_depth, use_had, half_x << 1, half_y << 1, 1, c_refine_q);
+  else             frac_stage<4>(fs, s_org, s_src, s_tmp, s_rt, cols, rows, bit_depth, use_had, half_x << 1, half_y << 1, 1, c_refine_q);
   if (threadIdx.x == 0) {
     cs.cost_scale = 0;
     const int mx = ((mv_int.hor << 1) + half_x) << 1, my = ((mv_int.ver << 1) + half_y) << 1;

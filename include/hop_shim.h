@@ -113,6 +113,9 @@ inline void refUpdate(TComPicYuv* pic, int x, int y, int w, int h)
         "hop_ref_update");
 }
 
+/* HOP_FUSED=0 keeps the three stages as separate calls (fractional refinement on the host) */
+inline bool fused() { static int f = -1; if (f < 0) { const char* e = getenv("HOP_FUSED"); f = (e && e[0] == '0') ? 0 : 1; } return f != 0; }
+
 inline bool owns(const Pel* p) { const State& s = state(); return s.ctx && p >= s.buf_lo && p < s.buf_hi; }
 
 inline HopCostState costState(TComRdCost* rd)
@@ -193,6 +196,66 @@ inline void xPatternSearchGT(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* p
     rcMvHalf->set(0, 0);
     rcMvQter->set(0, 0);
   }
+}
+
+/* The GPU part of TEncSearch::xMotionEstimation for an SS reference in ONE call (TEncSearch.cpp:4572-4642):
+ * xPatternSearch -> validity check -> xPatternSearchFracDIF -> xPatternSearchGT.  Returns false when the
+ * integer search found nothing valid or the zero vector (the caller then sets bNotValCU, :4603-4611);
+ * outputs are then exactly what the reference leaves at that point. */
+inline bool xMotionSearchSS(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* piRefY, Int iRefStride,
+                            TComMv* pcMvSrchRngLT, TComMv* pcMvSrchRngRB, Int riOffsetX, Int riOffsetY,
+                            Bool useFastEnc, Bool useHADME, Int bitDepth, TComRdCost* rd, Bool bUseGT,
+                            TComMv& rcMv, UInt& ruiCost, TComMv& rcMvHalf, TComMv& rcMvQter,
+                            TComMv& rcGT0, TComMv& rcGT1, TComMv& rcGT2, TComMv& rcGT3, Bool& gtFlag, TComMv* ssBestCand)
+{
+  Timer tm(1, pcPatternKey->getROIYWidth(), pcPatternKey->getROIYHeight());
+  State& s = state();
+  HopMotionJob mj;
+  HopSearchJob& j = mj.search;
+  j.org_off = 0;
+  j.ref_off = piRefY - s.origin;
+  j.org_stride = pcPatternKey->getPatternLStride();
+  j.ref_stride = iRefStride;
+  j.cols = pcPatternKey->getROIYWidth();
+  j.rows = pcPatternKey->getROIYHeight();
+  j.rng_left = pcMvSrchRngLT->getHor(); j.rng_top = pcMvSrchRngLT->getVer();
+  j.rng_right = pcMvSrchRngRB->getHor(); j.rng_bottom = pcMvSrchRngRB->getVer();
+  j.offset_x = riOffsetX; j.offset_y = riOffsetY;
+  j.is_ss = 1;
+  j.fast_enc = useFastEnc ? 1 : 0;
+  j.bit_depth = bitDepth;
+  j.cost = costState(rd);                                   /* cost scale 2 at this point (:4560) */
+  mj.use_had = useHADME ? 1 : 0;
+  mj.use_gt = bUseGT ? 1 : 0;
+  AMVPInfo* amvp = pcCU->getCUMvField(REF_PIC_LIST_0)->getAMVPInfo();     /* :5100-5104 */
+  mj.num_pred = amvp->iN;
+  for (int i = 0; i < HOP_MAX_PRED; i++) {
+    mj.amvp[i].hor = i < amvp->iN ? amvp->m_acMvCand[i].getHor() : 0;
+    mj.amvp[i].ver = i < amvp->iN ? amvp->m_acMvCand[i].getVer() : 0;
+  }
+  HopMotionResult r;
+  const size_t org_samples = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+  check(hop_motion_search_batch(s.ctx, 1, &mj, pcPatternKey->getROIY(), org_samples, NULL, 0, &r), "hop_motion_search_batch");
+  gtFlag = false;
+  rcGT0.set(0, 0); rcGT1.set(0, 0); rcGT2.set(0, 0); rcGT3.set(0, 0);
+  if (!r.search.found) { ruiCost = MAX_UINT; return false; }               /* :6356-6360 */
+  rcMv.set(r.search.mv.hor, r.search.mv.ver);                              /* :6363 */
+  ssBestCand[0].set(r.search.mv.hor, r.search.mv.ver);
+  ruiCost = r.search.sad;                                                   /* :6365 */
+  if (!r.refined) return false;                                             /* zero vector, :4604 */
+  rcMvHalf.set(r.frac.half.hor, r.frac.half.ver);                          /* :6564-6610 */
+  rcMvQter.set(r.frac.qter.hor, r.frac.qter.ver);
+  ruiCost = r.frac.cost;
+  if (bUseGT && r.gt.gt_flag) {                                             /* :5441-5457 */
+    gtFlag = true;
+    rcGT0.set(r.gt.gt[0].hor, r.gt.gt[0].ver); rcGT1.set(r.gt.gt[1].hor, r.gt.gt[1].ver);
+    rcGT2.set(r.gt.gt[2].hor, r.gt.gt[2].ver); rcGT3.set(r.gt.gt[3].hor, r.gt.gt[3].ver);
+    ruiCost = r.gt.cost;
+    rcMv.set(r.gt.mv_int.hor, r.gt.mv_int.ver);
+    rcMvHalf.set(0, 0);
+    rcMvQter.set(0, 0);
+  }
+  return true;
 }
 
 }  // namespace hopshim

@@ -65,6 +65,29 @@ def main():
               "\t\t                           gtFlag, ruiCost, bestSSCand, m_pcEncCfg->getUseHADME(), g_bitDepthY, m_pcRdCost );\n"
               "\t\treturn;\n"
               "\t}\n", where="before")
+    # xMotionEstimation: the three SS stages in one GPU call; the original statements stay for every
+    # other kind of reference
+    t = patch(t, "  if ( !m_iFastSearch || bBi )\n  {\n#if IT_HOLOSS\n    if ( bIsSSE )\n    {\n      xSetSearchRange   (pcCU, cMvSrchRngLT, cMvSrchRngRB, iOffsetX, iOffsetY, bisFirstRow, bisFirstCol);\n    }\n",
+              "  // libhopgpu: integer search, fractional refinement and HOP search of an SS reference in one GPU call\n"
+              "  Bool bHopDone = false;\n"
+              "  if ( bIsSSE && !bBi && !m_iFastSearch && hopshim::owns( piRefY ) && hopshim::fused() )\n"
+              "  {\n"
+              "    xSetSearchRange   (pcCU, cMvSrchRngLT, cMvSrchRngRB, iOffsetX, iOffsetY, bisFirstRow, bisFirstCol);\n"
+              "    Bool bValid = hopshim::xMotionSearchSS( pcCU, pcPatternKey, piRefY, iRefStride, &cMvSrchRngLT, &cMvSrchRngRB, iOffsetX, iOffsetY,\n"
+              "                                            m_pcEncCfg->getUseFastEnc(), m_pcEncCfg->getUseHADME(), g_bitDepthY, m_pcRdCost, bUseGT,\n"
+              "                                            rcMv, ruiCost, cMvHalf, cMvQter, rcGT0, rcGT1, rcGT2, rcGT3, gtFlag, pcCU->getSSBestCand() );\n"
+              "    if ( !bValid || pcCU->getSlice()->getRefPic( eRefPicList, iRefIdxPred )->getPicYuvRec()->getBufY()[0x00] == NOT_VALID )\n"
+              "    {\n"
+              "      bNotValCU = true;\n"
+              "      return;\n"
+              "    }\n"
+              "    m_pcRdCost->getMotionCost( 1, 0 );\n"
+              "    m_pcRdCost->setCostScale ( 0 );\n"
+              "    bHopDone = true;\n"
+              "  }\n"
+              "  if ( !bHopDone )\n"
+              "  {\n", where="before")
+    t = patch(t, "  rcMv <<= 2;\n  rcMv += (cMvHalf <<= 1);\n", "  }  // libhopgpu: !bHopDone\n", where="before")
     wr("TLibEncoder/TEncSearch.cpp", t)
 
     # --- TEncCu.cpp -------------------------------------------------------------------------------
