@@ -49,6 +49,11 @@ struct HopCtx {
   unsigned char* pin_h = nullptr;   // mapped pinned host memory (zero-copy): the GPU reads job + block from it
   unsigned char* pin_d = nullptr;   // ... through this device alias, and writes result + completion flag back
   unsigned       pin_seq = 0;
+  // asynchronous batches: a copy stream and a ring of scratch sets
+  cudaStream_t copy_stream = nullptr;
+  struct Slot { Scratch jobs, org, ref, out; cudaEvent_t h2d = nullptr, done = nullptr; bool busy = false; };
+  Slot         slots[HOP_ASYNC_SLOTS];
+  unsigned     next_slot = 0;
   // SS reference mirror
   int16_t*     plane = nullptr;
   int          pic_w = 0, pic_h = 0, margin = 0, stride = 0;
@@ -160,6 +165,13 @@ void hop_ctx_destroy(HopCtx* ctx)
   Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->done, &ctx->sweep_keys, &ctx->k1res, &ctx->sink};
   for (Scratch* s : all) if (s->p) cudaFree(s->p);
   if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (auto& sl : ctx->slots) {
+    Scratch* ss[] = {&sl.jobs, &sl.org, &sl.ref, &sl.out};
+    for (Scratch* q : ss) if (q->p) cudaFree(q->p);
+    if (sl.h2d) cudaEventDestroy(sl.h2d);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   if (ctx->plane) cudaFree(ctx->plane);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -169,7 +181,9 @@ int hop_ctx_sync(HopCtx* ctx)
 {
   int st = bind(ctx);
   if (st) return st;
+  if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& sl : ctx->slots) sl.busy = false;
   return HOP_OK;
 }
 
@@ -493,6 +507,43 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
   if (st) return st;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopGtResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+int hop_pattern_search_gt_batch_async(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* org, size_t org_samples,
+                                      const int16_t* ref, size_t ref_samples, HopGtResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !ref || !out))) return fail(HOP_ERR_ARG, "NULL argument (the async form needs an explicit ref buffer)");
+  if (n == 0) return HOP_OK;
+  int max_cols = 4, max_rows = 4;
+  for (int i = 0; i < n; i++) {
+    const HopGtJob& j = jobs[i];
+    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 14 || j.num_pred < 0 || j.num_pred > HOP_MAX_PRED)
+      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / num_pred %d", i, j.cols, j.rows, j.bit_depth, j.num_pred);
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+  }
+  if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  HopCtx::Slot& sl = ctx->slots[ctx->next_slot++ % HOP_ASYNC_SLOTS];
+  if (!sl.h2d) { CU(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
+  if (sl.busy) CU(cudaEventSynchronize(sl.done));          // the batch that used this slot HOP_ASYNC_SLOTS calls ago
+  if ((st = ensure(ctx, sl.jobs, sizeof(HopGtJob) * (size_t)n))) return st;
+  if ((st = ensure(ctx, sl.org, org_samples * sizeof(int16_t)))) return st;
+  if ((st = ensure(ctx, sl.ref, ref_samples * sizeof(int16_t)))) return st;
+  if ((st = ensure(ctx, sl.out, sizeof(HopGtResult) * (size_t)n))) return st;
+  CU(cudaMemcpyAsync(sl.jobs.p, jobs, sizeof(HopGtJob) * (size_t)n, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU(cudaMemcpyAsync(sl.org.p, org, org_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU(cudaMemcpyAsync(sl.ref.p, ref, ref_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+  CU(cudaEventRecord(sl.h2d, ctx->copy_stream));
+  CU(cudaStreamWaitEvent(ctx->stream, sl.h2d, 0));
+  st = hop_pattern_search_gt_batch_dev(ctx, n, (const HopGtJob*)sl.jobs.p, (const int16_t*)sl.org.p, (const int16_t*)sl.ref.p,
+                                       (HopGtResult*)sl.out.p, max_cols, max_rows, ctx->stream);
+  if (st) return st;
+  CU(cudaMemcpyAsync(out, sl.out.p, sizeof(HopGtResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(sl.done, ctx->stream));
+  sl.busy = true;
   return HOP_OK;
 }
 

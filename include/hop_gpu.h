@@ -216,6 +216,15 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs,
                                 const int16_t* org, size_t org_samples,
                                 const int16_t* ref, size_t ref_samples,
                                 HopGtResult* out);
+/* Asynchronous form of hop_pattern_search_gt_batch for callers that stream many batches: the call only
+ * enqueues (input copies on a copy stream, kernel and result copy on the context stream) and returns; up
+ * to HOP_ASYNC_SLOTS batches are in flight, so the input copy of batch k+1 overlaps the kernel of batch k.
+ * jobs/org/ref/out must stay valid (and should be page-locked) until hop_ctx_sync() returns. */
+#define HOP_ASYNC_SLOTS 4
+int hop_pattern_search_gt_batch_async(HopCtx* ctx, int n, const HopGtJob* jobs,
+                                      const int16_t* org, size_t org_samples,
+                                      const int16_t* ref, size_t ref_samples,
+                                      HopGtResult* out);
 int hop_dist_batch(HopCtx* ctx, int n, const HopDistJob* jobs,
                    const int16_t* org, size_t org_samples,
                    const int16_t* cur, size_t cur_samples,

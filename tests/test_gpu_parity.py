@@ -243,3 +243,18 @@ def test_device_entry_points_with_torch_buffers(ctx):
     go = d_go.cpu().numpy().view(hop.GT_RES_DT)
     assert so.tobytes() == orc.pattern_search(b.search_jobs, b.org, b.ref).tobytes()
     assert go.tobytes() == orc.pattern_search_gt(b.gt_jobs, b.org, b.ref).tobytes()
+
+
+def test_async_batches_match_sync(ctx):
+    """hop_pattern_search_gt_batch_async: several batches in flight (more than the slot ring holds), results
+    land in the callers' buffers after hop_ctx_sync and equal the synchronous call."""
+    orc = _oracle.oracle()
+    batches = [PuBatch(c, r, 6, seed=40 + i, sr=24, n_start=2) for i, (c, r) in enumerate(
+        [(8, 8), (16, 16), (8, 4), (32, 32), (16, 8), (16, 12)])]
+    outs = [np.zeros(b.n, dtype=hop.GT_RES_DT) for b in batches]
+    for b, o in zip(batches, outs):
+        ctx._check(ctx.lib.hop_pattern_search_gt_batch_async(ctx.h, b.n, b.gt_jobs.ctypes.data, b.org.ctypes.data, b.org.size,
+                                                             b.ref.ctypes.data, b.ref.size, o.ctypes.data))
+    ctx.sync()
+    for b, o in zip(batches, outs):
+        assert o.tobytes() == orc.pattern_search_gt(b.gt_jobs, b.org, b.ref).tobytes()
