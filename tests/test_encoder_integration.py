@@ -13,7 +13,8 @@ have = os.path.exists(encoder.HOP_ENCODER) and os.path.exists(encoder.REF_ENCODE
 
 
 @pytest.mark.skipif(not have, reason="encoder binaries not built (need /root/reference at build time)")
-@pytest.mark.parametrize("size,bit_depth,qp", [((128, 128), 8, 32), ((128, 64), 8, 22), ((64, 64), 10, 32)])
+@pytest.mark.parametrize("size,bit_depth,qp", [((128, 128), 8, 32), ((128, 64), 8, 22), ((64, 64), 10, 32),
+                                               ((136, 104), 8, 37)])      # partial CTUs at the right / bottom edge
 def test_bitstream_identical_to_reference(size, bit_depth, qp):
     w, h = size
     ref = encoder.encode(encoder.REF_ENCODER, w, h, seed=1, qp=qp, bit_depth=bit_depth)
@@ -22,3 +23,12 @@ def test_bitstream_identical_to_reference(size, bit_depth, qp):
     assert hop["rec"] == ref["rec"]
     assert hop["trace"] == ref["trace"]          # per-PU mvL0 / GT_FLAG / GT0L0..GT3L0 and bit counts
     assert len(hop["bitstream"]) > 100
+
+
+@pytest.mark.skipif(not have, reason="encoder binaries not built (need /root/reference at build time)")
+def test_unfused_call_path_is_identical_too(monkeypatch):
+    """HOP_FUSED=0: xPatternSearch and xPatternSearchGT as separate GPU calls, fractional refinement on the host."""
+    ref = encoder.encode(encoder.REF_ENCODER, 128, 64, seed=3)
+    monkeypatch.setenv("HOP_FUSED", "0")
+    hop = encoder.encode(encoder.HOP_ENCODER, 128, 64, seed=3)
+    assert hop["bitstream"] == ref["bitstream"] and hop["rec"] == ref["rec"] and hop["trace"] == ref["trace"]
