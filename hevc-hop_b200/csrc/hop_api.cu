@@ -4,6 +4,7 @@
 // an error status.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -49,6 +50,7 @@ struct HopCtx {
   unsigned char* pin_h = nullptr;   // mapped pinned host memory (zero-copy): the GPU reads job + block from it
   unsigned char* pin_d = nullptr;   // ... through this device alias, and writes result + completion flag back
   unsigned       pin_seq = 0;
+  bool           use_clusters = true;   // HOP_CLUSTERS=0 turns the cluster form of the latency path off
   // asynchronous batches: a copy stream and a ring of scratch sets
   cudaStream_t copy_stream = nullptr;
   struct Slot { Scratch jobs, org, ref, out; cudaEvent_t h2d = nullptr, done = nullptr; bool busy = false; };
@@ -142,6 +144,7 @@ int hop_ctx_create(int device, HopCtx** out)
   if (!ctx) return fail(HOP_ERR_NOMEM, "out of host memory");
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  { const char* e = getenv("HOP_CLUSTERS"); ctx->use_clusters = !(e && e[0] == '0'); }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete ctx; return fail(HOP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   if (device < 64 && !g_table_ready[device]) {
@@ -493,8 +496,14 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
     if ((st = pack_single(ctx, jobs[0], org, org_samples))) return st;
     const unsigned seq = ++ctx->pin_seq;
     int l = 0;
-    CU(gt_launch(1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                 (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l, pin_flag_dev(ctx), seq));
+    cudaError_t ce = ctx->use_clusters
+        ? gt_single_launch((const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
+                           (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l, pin_flag_dev(ctx), seq)
+        : cudaErrorNotSupported;
+    if (ce == cudaErrorNotSupported)
+      ce = gt_launch(1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
+                     (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l, pin_flag_dev(ctx), seq);
+    CU(ce);
     ctx->launches += l;
     return unpack_single(ctx, seq, out);
   }
@@ -641,9 +650,16 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
                     nullptr, 0, (int)sizeof(HopMotionJob));
     if (st) return st;
     int l = 0;
-    CU(motion_tail_launch(1, (const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
-                          (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                          pin_flag_dev(ctx), seq));
+    cudaError_t ce = ctx->use_clusters
+        ? motion_single_launch((const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
+                               (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
+                               pin_flag_dev(ctx), seq)
+        : cudaErrorNotSupported;
+    if (ce == cudaErrorNotSupported)
+      ce = motion_tail_launch(1, (const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
+                              (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
+                              pin_flag_dev(ctx), seq);
+    CU(ce);
     ctx->launches += l;
     return unpack_single(ctx, seq, out);
   }

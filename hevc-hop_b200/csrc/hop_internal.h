@@ -28,6 +28,12 @@ cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_or
                               unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches);
 cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,
                                   const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches);
+// latency path: one PU searched by a thread-block cluster; cudaErrorNotSupported for single-tile shapes
+cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
+                             int cols, int rows, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq);
+cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
+                                 const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows,
+                                 cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq);
 // K1
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,

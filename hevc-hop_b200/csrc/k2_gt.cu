@@ -19,10 +19,13 @@
 //     which carries across passes and start vectors exactly as uiDistBest does.
 #include "hop_common.cuh"
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "hop_internal.h"
 #include "k5_frac.cuh"
 
 namespace hop {
+
+namespace cg = cooperative_groups;
 
 __constant__ int8_t c_gt_offsets[GT_CANDS][8];   // x0,y0,x1,y1,x2,y2,x3,y3 in {-1,0,1}, loop order
 
@@ -286,7 +289,7 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
 // A thread keeps its candidate (and the six map coefficients) for the whole pass.
 template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int w, int cols, int rows, int off_x, int off_y)
+                                           int w, int cols, int rows, int off_x, int off_y, int crank, int csize)
 {
   const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
   if (g >= groups || !sh.valid[c]) return;
@@ -294,7 +297,7 @@ __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
   uint32_t acc = 0;
-  for (int tile = g; tile < ntiles; tile += groups) {
+  for (int tile = g + groups * crank; tile < ntiles; tile += groups * csize) {   // cluster: CTAs interleave tiles
     const int tx = (tile % tiles_x) * 4, ty = (tile / tiles_x) * 4;
     acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, w, cols, rows, off_x, off_y);
   }
@@ -303,7 +306,7 @@ __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const
 
 template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int w, int cols, int rows, int off_x, int off_y)
+                                           int w, int cols, int rows, int off_x, int off_y, int crank, int csize)
 {
   const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
   const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = blockDim.x / (2 * GT_CANDS);
@@ -313,7 +316,7 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
   uint32_t acc = 0;
-  for (int tile = g; tile < ntiles; tile += groups) {
+  for (int tile = g + groups * crank; tile < ntiles; tile += groups * csize) {   // cluster: CTAs interleave tiles
     const int tx = (tile % tiles_x) * 8, ty = (tile / tiles_x) * 8;
     acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, w, cols, rows, off_x, off_y);
   }
@@ -322,14 +325,15 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
 
 template <int WS>
 __device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const uint32_t* s_win, int w,
-                                          int cols, int rows, int off_x, int off_y, int tile_n, int use_had)
+                                          int cols, int rows, int off_x, int off_y, int tile_n, int use_had,
+                                          int crank = 0, int csize = 1)
 {
   if (tile_n == 8) {
-    if (use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
-    else         run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
+    if (use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
+    else         run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
   } else {
-    if (use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
-    else         run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y);
+    if (use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
+    else         run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
   }
 }
 
@@ -353,12 +357,19 @@ template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
 // The whole xPatternSearchGT of one PU, executed by one CTA.  `out` is written by thread 0.
 // smem_raw: [GtShared][org rows*cols int32][window (rows+2w) x WS uint32]; when `org_staged` the int32
 // original block is already in place (the fused motion kernel stages it once for all stages).
-template <int WS>
+//
+// CL = true: the PU is searched by a thread-block CLUSTER (single-call latency path for large PUs): every
+// CTA stages the same window and walks the same passes, but evaluates only its share of the Hadamard tiles;
+// after a pass the per-candidate partial sums are gathered through distributed shared memory and every CTA
+// takes the same argmin decision, so no state has to be broadcast.  Rank 0 writes the result.
+template <int WS, bool CL = false>
 __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t* __restrict__ org_buf,
                                               const int16_t* __restrict__ ref_buf, unsigned char* smem_raw,
                                               HopGtResult* __restrict__ out, bool org_staged)
 {
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
+  int crank = 0, csize = 1;
+  if (CL) { cg::cluster_group cl = cg::this_cluster(); crank = (int)cl.block_rank(); csize = (int)cl.num_blocks(); }
   const int cols = job.cols, rows = job.rows;
   const int G = 2;                                              // IT_GT_GRID_SIZE
   const int nss_window = ((rows < cols ? rows : cols) >> 1) * G;  // TEncSearch.cpp:4756-4758
@@ -455,15 +466,24 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
         }
       }
       __syncthreads();
-      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had);
-      __syncthreads();
+      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize);
+      if (CL) cg::this_cluster().sync(); else __syncthreads();
       if (threadIdx.x < 64) {
         // ordered argmin with the carried threshold: the serial loop keeps the FIRST strict minimum in
         // loop order (:5361) == the minimum of (cost, loop index) over the pass, accepted iff it beats
         // the running best
         const int c = threadIdx.x;
         const bool ok = c < GT_CANDS && sh.valid[c];
-        unsigned long long key = ok ? ((unsigned long long)((sh.dist[c] >> dist_shift) + sh.add_cost[c]) << 8) | (unsigned)c
+        uint32_t dsum = 0;
+        if (ok) {
+          if (CL) {
+            cg::cluster_group cl = cg::this_cluster();
+            for (int r = 0; r < csize; r++) dsum += *cl.map_shared_rank(&sh.dist[c], r);   // tile sums of all CTAs
+          } else {
+            dsum = sh.dist[c];
+          }
+        }
+        unsigned long long key = ok ? ((unsigned long long)((dsum >> dist_shift) + sh.add_cost[c]) << 8) | (unsigned)c
                                     : ~0ull;
         const unsigned n_ok = __popc(__ballot_sync(0xffffffffu, ok));
 #pragma unroll
@@ -473,7 +493,8 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
         }
         if ((threadIdx.x & 31) == 0) { sh.red_key[threadIdx.x >> 5] = key; sh.red_cnt[threadIdx.x >> 5] = n_ok; }
       }
-      __syncthreads();
+      // cluster: nobody may zero its partial sums (next set-up) before every CTA has gathered them
+      if (CL) cg::this_cluster().sync(); else __syncthreads();
       if (threadIdx.x == 0) {
         const unsigned long long key = sh.red_key[0] < sh.red_key[1] ? sh.red_key[0] : sh.red_key[1];
         sh.n_cand += sh.red_cnt[0] + sh.red_cnt[1];
@@ -492,7 +513,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && crank == 0) {
     HopGtResult r;
     r.gt_flag = 0;
     for (int k = 0; k < 4; k++) { r.gt[k].hor = 0; r.gt[k].ver = 0; }
@@ -878,21 +899,23 @@ cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, c
 
 // Second kernel of the fused motion search: one CTA per PU picks up the integer result of k1_search and
 // runs xPatternSearchFracDIF and xPatternSearchGT back to back (TEncSearch.cpp:4601-4642), no host in between.
-template <int WS, int CFG>
-__global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
-k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
-              const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
-              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+template <int WS, int CFG, bool CL>
+__device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob* __restrict__ jobs,
+                                                 const int16_t* __restrict__ org_buf, const int16_t* __restrict__ ref_buf,
+                                                 const HopSearchResult* __restrict__ k1, HopMotionResult* __restrict__ out,
+                                                 unsigned* done_flag, unsigned seq)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int job_id = blockIdx.x;
+  int crank = 0, csize = 1;
+  if (CL) { cg::cluster_group cl = cg::this_cluster(); crank = (int)cl.block_rank(); csize = (int)cl.num_blocks(); }
+  const int job_id = blockIdx.x / csize;
   if (job_id >= n_jobs) return;
   const HopMotionJob mj = jobs[job_id];
   const HopSearchJob& sj = mj.search;
   const HopSearchResult sr = k1[job_id];
   HopMotionResult* res = &out[job_id];
   const bool go = sr.found == 1 && !(sr.mv.hor == 0 && sr.mv.ver == 0);      // :4603-4611
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && crank == 0) {
     res->search = sr;
     res->refined = go ? 1 : 0;
     if (!go) {
@@ -917,7 +940,7 @@ k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* 
     const int16_t* ref_pos = ref_buf + sj.ref_off + sr.mv.hor + (long long)sr.mv.ver * sj.ref_stride;
     const HopFracResult fr = frac_search_cta(fs, s_org, scratch, ref_pos, sj.ref_stride, cols, rows, sj.bit_depth,
                                              mj.use_had, sj.cost, sr.mv);
-    if (threadIdx.x == 0) { res->frac = fr; if (!mj.use_gt) res->gt.cost = fr.cost; }
+    if (threadIdx.x == 0 && crank == 0) { res->frac = fr; if (!mj.use_gt) res->gt.cost = fr.cost; }
     if (mj.use_gt) {
       HopGtJob gj;
       gj.org_off = sj.org_off; gj.ref_off = sj.ref_off; gj.org_stride = sj.org_stride; gj.ref_stride = sj.ref_stride;
@@ -928,13 +951,82 @@ k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* 
       gj.threshold = fr.cost;                      // ruiCost coming out of the frac stage (:4769)
       gj.use_had = mj.use_had; gj.bit_depth = sj.bit_depth;
       gj.cost = sj.cost; gj.cost.cost_scale = 0;   // :4619
-      gt_search_cta<WS>(gj, org_buf, ref_buf, smem_raw, &res->gt, true);
+      gt_search_cta<WS, CL>(gj, org_buf, ref_buf, smem_raw, &res->gt, true);
     }
   }
-  if (threadIdx.x == 0 && done_flag) {
+  if (threadIdx.x == 0 && crank == 0 && done_flag) {
     __threadfence_system();
     *(volatile unsigned*)done_flag = seq;
   }
+}
+
+template <int WS, int CFG>
+__global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
+k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+              const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
+              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+{
+  motion_tail_body<WS, CFG, false>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq);
+}
+
+// cluster forms (single-call latency path for PUs with several Hadamard tiles): launched with a cluster
+// dimension of 2, 4 or 8 CTAs per PU
+template <int WS>
+__global__ void __launch_bounds__(GtCfg<0>::T, 1)
+k_motion_tail_cl(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+                 const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
+                 HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+{
+  motion_tail_body<WS, 0, true>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq);
+}
+
+template <int WS>
+__global__ void __launch_bounds__(GtCfg<0>::T, 1)
+k2_gt_search_cl(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+                const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cl = cg::this_cluster();
+  const int job_id = blockIdx.x / (int)cl.num_blocks();
+  if (job_id >= n_jobs) return;
+  const HopGtJob job = jobs[job_id];
+  gt_search_cta<WS, true>(job, org_buf, ref_buf, smem_raw, &out[job_id], false);
+  if (threadIdx.x == 0 && cl.block_rank() == 0 && done_flag) {
+    __threadfence_system();
+    *(volatile unsigned*)done_flag = seq;
+  }
+}
+
+// cluster size and CTA size for a PU shape on the latency path
+static void cluster_geometry(int cols, int rows, int* csize, int* threads)
+{
+  const int tile = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
+  const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
+  const int ntiles = (cols / tile) * (rows / tile);
+  int cs = ntiles >= 8 ? 8 : ntiles >= 4 ? 4 : ntiles >= 2 ? 2 : 1;
+  const int per_cta = (ntiles + cs - 1) / cs;
+  const int max_groups = GtCfg<0>::T / per_group;
+  int groups = per_cta < max_groups ? per_cta : max_groups;
+  for (int g = groups - 1; g >= 1; g--)
+    if ((per_cta + g - 1) / g <= (per_cta + groups - 1) / groups) groups = g;
+  int t = per_group * groups;
+  if (t < 64) t = 64;
+  *csize = cs; *threads = t;
+}
+
+template <typename K, typename... Args>
+static cudaError_t launch_cluster(K kernel, int n, int csize, int threads, size_t smem, cudaStream_t stream, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n * csize);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
@@ -983,6 +1075,70 @@ cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t*
     case 65:  return motion_tail_cfg<65, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
     case 97:  return motion_tail_cfg<97, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
     default:  return motion_tail_cfg<129, 0>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
+  }
+}
+
+template <int WS>
+static cudaError_t gt_cluster_class(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
+                                    int cols, int rows, int csize, int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k2_gt_search_cl<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_cluster(k2_gt_search_cl<WS>, 1, csize, threads, gt_smem_bytes(WS, cols, rows), stream,
+                        1, d_job, d_org, d_ref, d_out, done_flag, seq);
+}
+
+template <int WS>
+static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
+                                        const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows, int csize,
+                                        int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_motion_tail_cl<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)motion_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_cluster(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_bytes(WS, cols, rows), stream,
+                        1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq);
+}
+
+// Latency path: ONE PU, searched by a cluster of CTAs when it has at least two Hadamard tiles.
+// Returns cudaErrorNotSupported when the shape is too small for a cluster (the caller uses the plain kernel).
+cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
+                             int cols, int rows, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+{
+  int csize, threads;
+  cluster_geometry(cols, rows, &csize, &threads);
+  if (csize < 2) return cudaErrorNotSupported;
+  if (launches) (*launches)++;
+  switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
+    case 33:  return gt_cluster_class<33>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    case 65:  return gt_cluster_class<65>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    case 97:  return gt_cluster_class<97>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    default:  return gt_cluster_class<129>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+  }
+}
+
+cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
+                                 const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows,
+                                 cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+{
+  int csize, threads;
+  cluster_geometry(cols, rows, &csize, &threads);
+  if (csize < 2) return cudaErrorNotSupported;
+  if (launches) (*launches)++;
+  switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
+    case 33:  return motion_cluster_class<33>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    case 65:  return motion_cluster_class<65>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    case 97:  return motion_cluster_class<97>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    default:  return motion_cluster_class<129>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
   }
 }
 

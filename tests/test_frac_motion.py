@@ -110,7 +110,8 @@ def test_gpu_motion_search_on_the_mirror_single_call(ctx):
     _oracle.extend_border_oracle(host, pic_w, pic_h, m)
     ctx.ref_upload(host)
     stride = pic_w + 2 * m
-    for (c, r) in [(16, 16), (8, 4), (32, 32)]:
+    # multi-tile shapes take the thread-block-cluster form of the latency path (2, 4 or 8 CTAs per PU)
+    for (c, r) in [(16, 16), (8, 4), (32, 32), (64, 64), (16, 12), (32, 8), (16, 8), (8, 8), (64, 32), (24, 32)]:
         b = PuBatch(c, r, 1, seed=c, sr=16, n_start=2)
         mj = b.motion_jobs()
         s = mj["search"]
@@ -121,4 +122,11 @@ def test_gpu_motion_search_on_the_mirror_single_call(ctx):
         mj["amvp"]["hor"][:, 1] = 0; mj["amvp"]["ver"][:, 1] = 0
         got = ctx.motion_search(mj, b.org, None)
         m2 = mj.copy(); s2 = m2["search"]; s2["ref_off"] += m * stride + m; m2["search"] = s2
-        assert got.tobytes() == _oracle.motion_search(m2, b.org, host.reshape(-1)).tobytes()
+        want = _oracle.motion_search(m2, b.org, host.reshape(-1))
+        assert got.tobytes() == want.tobytes(), (c, r)
+        # the split calls of the same PU (K2 alone through the cluster form)
+        if want["refined"][0]:
+            gj = b.gt_jobs.copy()
+            gj["ref_stride"] = stride; gj["ref_off"] = 64 * stride + 64
+            gj["ss_cand"] = want["search"]["mv"]; gj["threshold"] = want["frac"]["cost"]; gj["amvp"] = mj["amvp"]
+            assert ctx.pattern_search_gt(gj, b.org, None).tobytes() == want["gt"].tobytes(), (c, r)
