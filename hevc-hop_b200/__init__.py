@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhopgpu.so")
+LIB_PATH = os.environ.get("HOP_LIB", os.path.join(_HERE, "libhopgpu.so"))   # HOP_LIB: experimental builds
 
 HOP_MAX_UINT = 0xFFFFFFFF
 HOP_NOT_VALID = -1
