@@ -277,6 +277,30 @@ const int16_t* hop_ref_origin_dev(HopCtx* ctx)
 // device entry points
 // ---------------------------------------------------------------------------------------------
 namespace {
+// sample offsets (relative to the pointer the kernels get) that may be dereferenced
+RefBounds bounds_for(const HopCtx* ctx, bool mirror, size_t ref_samples)
+{
+  RefBounds rb;
+  if (mirror) {
+    const long long before = (long long)ctx->margin * ctx->stride + ctx->margin;       // samples in front of (0,0)
+    rb.lo = -before;
+    rb.hi = (long long)ctx->stride * (ctx->pic_h + 2 * ctx->margin) - 1 - before;
+  } else {
+    rb.lo = 0;
+    rb.hi = (long long)ref_samples - 1;
+  }
+  return rb;
+}
+
+int gt_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
+           int max_cols, int max_rows, cudaStream_t s, RefBounds rb)
+{
+  int l = 0;
+  CU(gt_launch(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, s, &l, rb));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
 int k1_slices(const HopCtx* ctx, int n)
 {
   // enough CTAs to cover the machine a few times: a single in-encoder call spreads one PU's window
@@ -498,11 +522,13 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
     int l = 0;
     cudaError_t ce = ctx->use_clusters
         ? gt_single_launch((const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                           (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l, pin_flag_dev(ctx), seq)
+                           (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
+                           bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq)
         : cudaErrorNotSupported;
     if (ce == cudaErrorNotSupported)
       ce = gt_launch(1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                     (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l, pin_flag_dev(ctx), seq);
+                     (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
+                     bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq);
     CU(ce);
     ctx->launches += l;
     return unpack_single(ctx, seq, out);
@@ -511,8 +537,8 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
   st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,
                     sizeof(HopGtResult) * (size_t)n, &d_ref);
   if (st) return st;
-  st = hop_pattern_search_gt_batch_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref,
-                                       (HopGtResult*)ctx->out.p, max_cols, max_rows, ctx->stream);
+  st = gt_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, (HopGtResult*)ctx->out.p,
+              max_cols, max_rows, ctx->stream, bounds_for(ctx, ref == nullptr, ref_samples));
   if (st) return st;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopGtResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -547,8 +573,8 @@ int hop_pattern_search_gt_batch_async(HopCtx* ctx, int n, const HopGtJob* jobs, 
   CU(cudaMemcpyAsync(sl.ref.p, ref, ref_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
   CU(cudaEventRecord(sl.h2d, ctx->copy_stream));
   CU(cudaStreamWaitEvent(ctx->stream, sl.h2d, 0));
-  st = hop_pattern_search_gt_batch_dev(ctx, n, (const HopGtJob*)sl.jobs.p, (const int16_t*)sl.org.p, (const int16_t*)sl.ref.p,
-                                       (HopGtResult*)sl.out.p, max_cols, max_rows, ctx->stream);
+  st = gt_dev(ctx, n, (const HopGtJob*)sl.jobs.p, (const int16_t*)sl.org.p, (const int16_t*)sl.ref.p,
+              (HopGtResult*)sl.out.p, max_cols, max_rows, ctx->stream, bounds_for(ctx, false, ref_samples));
   if (st) return st;
   CU(cudaMemcpyAsync(out, sl.out.p, sizeof(HopGtResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(sl.done, ctx->stream));
@@ -653,12 +679,12 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
     cudaError_t ce = ctx->use_clusters
         ? motion_single_launch((const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
                                (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                               pin_flag_dev(ctx), seq)
+                               bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq)
         : cudaErrorNotSupported;
     if (ce == cudaErrorNotSupported)
       ce = motion_tail_launch(1, (const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
                               (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                              pin_flag_dev(ctx), seq);
+                              bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq);
     CU(ce);
     ctx->launches += l;
     return unpack_single(ctx, seq, out);
@@ -671,7 +697,8 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
   if (st) return st;
   int l = 0;
   CU(motion_tail_launch(n, (const HopMotionJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, d_k1,
-                        (HopMotionResult*)ctx->out.p, max_cols, max_rows, ctx->stream, &l));
+                        (HopMotionResult*)ctx->out.p, max_cols, max_rows, ctx->stream, &l,
+                        bounds_for(ctx, ref == nullptr, ref_samples)));
   ctx->launches += l;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopMotionResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

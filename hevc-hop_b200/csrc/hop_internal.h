@@ -6,6 +6,10 @@
 
 namespace hop {
 
+// addressable sample offsets of the reference buffer handed to a kernel (relative to its base pointer)
+struct RefBounds { long long lo, hi; };
+constexpr RefBounds REF_UNBOUNDED = {-(1ll << 62), (1ll << 62)};
+
 constexpr int GT_CANDS   = 56;    // affine corner sets per diamond pass
 constexpr int GT_THREADS = 336;   // K2 CTA size upper bound: 56 candidates x 2 lanes x 3 tile groups
 constexpr int K1_THREADS = 256;
@@ -16,7 +20,7 @@ void        gt_build_offset_table(int8_t table[GT_CANDS][8], int* count);
 cudaError_t gt_upload_offset_table(const int8_t table[GT_CANDS][8]);
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                       HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches,
-                      unsigned* done_flag = nullptr, unsigned seq = 0);
+                      RefBounds rb = REF_UNBOUNDED, unsigned* done_flag = nullptr, unsigned seq = 0);
 // exhaustive sweep (reference mode IT_GT_SEARCH 1, N = 2): 85^2 - 25 parallelogram offset patterns
 constexpr int SWEEP_CANDS = 7200;
 struct SweepCand { int8_t o[8]; uint32_t flat; };   // x0,y0,...,x3,y3 in [-2,2]; flat 8-deep loop index
@@ -25,15 +29,16 @@ cudaError_t sweep_upload_table(const SweepCand* table);
 cudaError_t sweep_init_launch(int n, unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches);
 cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                               int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
-                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches);
+                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches,
+                              RefBounds rb = REF_UNBOUNDED);
 cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,
                                   const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches);
 // latency path: one PU searched by a thread-block cluster; cudaErrorNotSupported for single-tile shapes
 cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
-                             int cols, int rows, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq);
+                             int cols, int rows, cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq);
 cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
                                  const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows,
-                                 cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq);
+                                 cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq);
 // K1
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
@@ -44,7 +49,8 @@ cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, c
                         HopFracResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);
 cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
-                               cudaStream_t stream, int* launches, unsigned* done_flag = nullptr, unsigned seq = 0);
+                               cudaStream_t stream, int* launches, RefBounds rb = REF_UNBOUNDED,
+                               unsigned* done_flag = nullptr, unsigned seq = 0);
 size_t      search_smem_bytes(const HopSearchJob& job, int slices);
 constexpr int K1_DEFAULT_SMEM = 96 * 1024;   // byte-path budget when the job shapes are not known on the host
 // K3

@@ -367,7 +367,7 @@ template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
 template <int WS, bool CL = false>
 __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t* __restrict__ org_buf,
                                               const int16_t* __restrict__ ref_buf, unsigned char* smem_raw,
-                                              HopGtResult* __restrict__ out, bool org_staged)
+                                              HopGtResult* __restrict__ out, bool org_staged, RefBounds rb)
 {
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
   int crank = 0, csize = 1;
@@ -415,7 +415,11 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
     // the high word of their binary64 value (converted once, exact)
     for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
       const int wy = i / win_w, wx = i - wy * win_w;
-      int v = ref_y[(Hy - w + wy) * job.ref_stride + (Hx - w + wx)];
+      // AMVP start vectors are raw neighbour vectors: their window may leave the reference buffer (the
+      // reference then reads whatever lies beyond its plane); keep the read inside the buffer
+      long long o = job.ref_off + (long long)(Hy - w + wy) * job.ref_stride + (Hx - w + wx);
+      o = o < rb.lo ? rb.lo : (o > rb.hi ? rb.hi : o);
+      int v = ref_buf[o];
       v = min(max(v, 0), max_val);
       s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
     }
@@ -545,13 +549,13 @@ template <int WS, int CFG>
 __global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
 k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
              const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out,
-             unsigned* done_flag, unsigned seq)
+             unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int job_id = blockIdx.x;
   if (job_id >= n_jobs) return;
   const HopGtJob job = jobs[job_id];
-  gt_search_cta<WS>(job, org_buf, ref_buf, smem_raw, &out[job_id], false);
+  gt_search_cta<WS>(job, org_buf, ref_buf, smem_raw, &out[job_id], false, rb);
   if (threadIdx.x == 0 && done_flag) {     // single-call path: result and flag live in mapped host memory
     __threadfence_system();
     *(volatile unsigned*)done_flag = seq;
@@ -596,7 +600,7 @@ template <int WS>
 __global__ void __launch_bounds__(gt_class_threads(WS), 2)
 k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
             const int16_t* __restrict__ ref_buf, int cand_begin, int cand_end,
-            unsigned long long* __restrict__ keys, unsigned int* __restrict__ counts)
+            unsigned long long* __restrict__ keys, unsigned int* __restrict__ counts, RefBounds rb)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
@@ -622,7 +626,9 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
     s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
   for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
     const int wy = i / win_w, wx = i - wy * win_w;
-    int v = ref_y[(mvy - w + wy) * job.ref_stride + (mvx - w + wx)];
+    long long o = job.ref_off + (long long)(mvy - w + wy) * job.ref_stride + (mvx - w + wx);
+    o = o < rb.lo ? rb.lo : (o > rb.hi ? rb.hi : o);
+    int v = ref_buf[o];
     v = min(max(v, 0), max_val);
     s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
   }
@@ -751,7 +757,7 @@ static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
 template <int WS, int CFG>
 static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                  HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
-                                 unsigned* done_flag, unsigned seq)
+                                 unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -771,14 +777,14 @@ static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
-  k2_gt_search<WS, CFG><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq);
+  k2_gt_search<WS, CFG><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq, rb);
   return cudaGetLastError();
 }
 
 template <int WS>
 static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                    HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
-                                   unsigned* done_flag, unsigned seq)
+                                   unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   // measured on B200 (profiles/r01_k2_launch_cfg.txt): 3 CTAs x 224 threads win for the small stride
   // classes, 2 CTAs x 336 threads for the 64x64 class (shared memory allows only two CTAs there)
@@ -786,31 +792,31 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
   if (env_cfg == -2) { const char* e = getenv("HOP_K2_CFG"); env_cfg = e ? atoi(e) : -1; }
   const int cfg = env_cfg >= 0 ? env_cfg : (WS == 129 ? 0 : 3);
   switch (cfg) {
-    case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
-    case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
-    case 3:  return gt_launch_cfg<WS, 3>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
-    default: return gt_launch_cfg<WS, 0>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 3:  return gt_launch_cfg<WS, 3>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    default: return gt_launch_cfg<WS, 0>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
 
 cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                       HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches,
-                      unsigned* done_flag, unsigned seq)
+                      RefBounds rb, unsigned* done_flag, unsigned seq)
 {
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return gt_launch_class<33>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
-    case 65:  return gt_launch_class<65>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
-    case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
-    default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 33:  return gt_launch_class<33>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 65:  return gt_launch_class<65>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
 
 template <int WS>
 static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                       int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
-                                      unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream)
+                                      unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, RefBounds rb)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -829,7 +835,7 @@ static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
   k2_gt_sweep<WS><<<dim3(n, chunks), threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(
-      n, d_jobs, d_org, d_ref, cand_begin, cand_end, d_keys, d_counts);
+      n, d_jobs, d_org, d_ref, cand_begin, cand_end, d_keys, d_counts, rb);
   return cudaGetLastError();
 }
 
@@ -842,15 +848,15 @@ cudaError_t sweep_init_launch(int n, unsigned long long* d_keys, unsigned int* d
 
 cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                               int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
-                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches)
+                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches, RefBounds rb)
 {
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return sweep_launch_class<33>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
-    case 65:  return sweep_launch_class<65>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
-    case 97:  return sweep_launch_class<97>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
-    default:  return sweep_launch_class<129>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream);
+    case 33:  return sweep_launch_class<33>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    case 65:  return sweep_launch_class<65>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    case 97:  return sweep_launch_class<97>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    default:  return sweep_launch_class<129>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
   }
 }
 
@@ -905,7 +911,7 @@ template <int WS, int CFG, bool CL>
 __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob* __restrict__ jobs,
                                                  const int16_t* __restrict__ org_buf, const int16_t* __restrict__ ref_buf,
                                                  const HopSearchResult* __restrict__ k1, HopMotionResult* __restrict__ out,
-                                                 unsigned* done_flag, unsigned seq)
+                                                 unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int crank = 0, csize = 1;
@@ -953,7 +959,7 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
       gj.threshold = fr.cost;                      // ruiCost coming out of the frac stage (:4769)
       gj.use_had = mj.use_had; gj.bit_depth = sj.bit_depth;
       gj.cost = sj.cost; gj.cost.cost_scale = 0;   // :4619
-      gt_search_cta<WS, CL>(gj, org_buf, ref_buf, smem_raw, &res->gt, true);
+      gt_search_cta<WS, CL>(gj, org_buf, ref_buf, smem_raw, &res->gt, true, rb);
     }
   }
   if (threadIdx.x == 0 && crank == 0 && done_flag) {
@@ -966,9 +972,9 @@ template <int WS, int CFG>
 __global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
 k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
               const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
-              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb)
 {
-  motion_tail_body<WS, CFG, false>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq);
+  motion_tail_body<WS, CFG, false>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq, rb);
 }
 
 // cluster forms (single-call latency path for PUs with several Hadamard tiles): launched with a cluster
@@ -977,22 +983,23 @@ template <int WS>
 __global__ void __launch_bounds__(GtCfg<0>::T, 1)
 k_motion_tail_cl(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
                  const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
-                 HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+                 HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb)
 {
-  motion_tail_body<WS, 0, true>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq);
+  motion_tail_body<WS, 0, true>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq, rb);
 }
 
 template <int WS>
 __global__ void __launch_bounds__(GtCfg<0>::T, 1)
 k2_gt_search_cl(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
-                const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out, unsigned* done_flag, unsigned seq)
+                const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out, unsigned* done_flag, unsigned seq,
+                RefBounds rb)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cl = cg::this_cluster();
   const int job_id = blockIdx.x / (int)cl.num_blocks();
   if (job_id >= n_jobs) return;
   const HopGtJob job = jobs[job_id];
-  gt_search_cta<WS, true>(job, org_buf, ref_buf, smem_raw, &out[job_id], false);
+  gt_search_cta<WS, true>(job, org_buf, ref_buf, smem_raw, &out[job_id], false, rb);
   if (threadIdx.x == 0 && cl.block_rank() == 0 && done_flag) {
     __threadfence_system();
     *(volatile unsigned*)done_flag = seq;
@@ -1043,7 +1050,7 @@ static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
 template <int WS, int CFG>
 static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                    const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
-                                   cudaStream_t stream, unsigned* done_flag, unsigned seq)
+                                   cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1062,27 +1069,27 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
   k_motion_tail<WS, CFG><<<n, threads, motion_smem_bytes(WS, max_cols, max_rows), stream>>>(
-      n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq);
+      n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb);
   return cudaGetLastError();
 }
 
 cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
-                               cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+                               cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq)
 {
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return motion_tail_cfg<33, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
-    case 65:  return motion_tail_cfg<65, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
-    case 97:  return motion_tail_cfg<97, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
-    default:  return motion_tail_cfg<129, 0>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq);
+    case 33:  return motion_tail_cfg<33, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 65:  return motion_tail_cfg<65, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 97:  return motion_tail_cfg<97, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    default:  return motion_tail_cfg<129, 0>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
 
 template <int WS>
 static cudaError_t gt_cluster_class(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
-                                    int cols, int rows, int csize, int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq)
+                                    int cols, int rows, int csize, int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1092,13 +1099,13 @@ static cudaError_t gt_cluster_class(const HopGtJob* d_job, const int16_t* d_org,
     attr_set = true;
   }
   return launch_cluster(k2_gt_search_cl<WS>, 1, csize, threads, gt_smem_bytes(WS, cols, rows), stream,
-                        1, d_job, d_org, d_ref, d_out, done_flag, seq);
+                        1, d_job, d_org, d_ref, d_out, done_flag, seq, rb);
 }
 
 template <int WS>
 static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
                                         const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows, int csize,
-                                        int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq)
+                                        int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1108,39 +1115,39 @@ static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t
     attr_set = true;
   }
   return launch_cluster(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_bytes(WS, cols, rows), stream,
-                        1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq);
+                        1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb);
 }
 
 // Latency path: ONE PU, searched by a cluster of CTAs when it has at least two Hadamard tiles.
 // Returns cudaErrorNotSupported when the shape is too small for a cluster (the caller uses the plain kernel).
 cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
-                             int cols, int rows, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+                             int cols, int rows, cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq)
 {
   int csize, threads;
   cluster_geometry(cols, rows, &csize, &threads);
   if (csize < 2) return cudaErrorNotSupported;
   if (launches) (*launches)++;
   switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
-    case 33:  return gt_cluster_class<33>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
-    case 65:  return gt_cluster_class<65>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
-    case 97:  return gt_cluster_class<97>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
-    default:  return gt_cluster_class<129>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    case 33:  return gt_cluster_class<33>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case 65:  return gt_cluster_class<65>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case 97:  return gt_cluster_class<97>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    default:  return gt_cluster_class<129>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
   }
 }
 
 cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
                                  const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows,
-                                 cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq)
+                                 cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq)
 {
   int csize, threads;
   cluster_geometry(cols, rows, &csize, &threads);
   if (csize < 2) return cudaErrorNotSupported;
   if (launches) (*launches)++;
   switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
-    case 33:  return motion_cluster_class<33>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
-    case 65:  return motion_cluster_class<65>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
-    case 97:  return motion_cluster_class<97>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
-    default:  return motion_cluster_class<129>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq);
+    case 33:  return motion_cluster_class<33>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case 65:  return motion_cluster_class<65>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case 97:  return motion_cluster_class<97>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    default:  return motion_cluster_class<129>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
   }
 }
 

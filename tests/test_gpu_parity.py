@@ -258,3 +258,31 @@ def test_async_batches_match_sync(ctx):
     ctx.sync()
     for b, o in zip(batches, outs):
         assert o.tobytes() == orc.pattern_search_gt(b.gt_jobs, b.org, b.ref).tobytes()
+
+
+def test_wild_amvp_vector_cannot_leave_the_mirror(ctx):
+    """AMVP start vectors are raw neighbour vectors; one that points far outside the SS plane (the
+    reference would read beyond its buffer) must not fault on the device: reads are kept inside the mirror."""
+    rng = np.random.default_rng(9)
+    pic_w, pic_h, m = 128, 128, 80
+    ctx.ref_create(pic_w, pic_h, m)
+    host = rng.integers(0, 256, size=(pic_h + 2 * m, pic_w + 2 * m)).astype(np.int16)
+    ctx.ref_upload(host)
+    stride = pic_w + 2 * m
+    b = PuBatch(16, 16, 1, seed=2, sr=16, n_start=3)
+    gj = b.gt_jobs.copy()
+    gj["ref_stride"] = stride; gj["ref_off"] = 64 * stride + 64
+    gj["ss_cand"]["hor"] = -20; gj["ss_cand"]["ver"] = -30
+    gj["amvp"]["hor"][:, 0] = -3000 * 4; gj["amvp"]["ver"][:, 0] = -3000 * 4       # far above / left of the plane
+    gj["amvp"]["hor"][:, 1] = 3000 * 4; gj["amvp"]["ver"][:, 1] = 3000 * 4         # far below / right of it
+    a = ctx.pattern_search_gt(gj, b.org, None)
+    assert ctx.pattern_search_gt(gj, b.org, None).tobytes() == a.tobytes()
+    assert a["n_candidates"][0] == 3 * 4 * 56
+    mj = b.motion_jobs()
+    s = mj["search"]; s["ref_stride"] = stride; s["ref_off"] = 64 * stride + 64
+    s["rng_left"], s["rng_right"], s["rng_top"], s["rng_bottom"] = -40, 30, -40, -4
+    s["is_ss"] = 0
+    mj["search"] = s
+    mj["amvp"] = gj["amvp"]
+    r = ctx.motion_search(mj, b.org, None)
+    assert r["refined"][0] == 1 and ctx.motion_search(mj, b.org, None).tobytes() == r.tobytes()
