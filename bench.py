@@ -207,9 +207,11 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
            "s_per_image": float(t.item()), "images_per_s": world / float(t.item()), "ctus_per_image": ctus,
            "s_per_ctu": float(t.item()) / ctus, "bytes": len(r["bitstream"]),
            "note": "wall clock of the encoder process incl. CUDA context creation; max over ranks"}
-    if world == 1 and not args.no_cpu_baseline and os.path.exists(encoder.REF_ENCODER):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(_oracle.REF_ENCODER):
         # bounded CPU sample: the unmodified reference on a 256x256 image, the patched encoder on the same image
-        ref = encoder.encode(encoder.REF_ENCODER, 256, 256, seed=7)
+        ref = _oracle.encode_reference(256, 256, seed=7)
         hop = encoder.encode(encoder.HOP_ENCODER, 256, 256, seed=7, device=local)
         enc["cpu_reference_256x256"] = {"s_per_image": ref["seconds"], "s_per_ctu": ref["seconds"] / 16, "cores": 1,
                                         "gpu_s_per_image_same_input": hop["seconds"],

@@ -164,6 +164,16 @@ def ref_sweep():
     return _cache["ref_sweep"]
 
 
+REF_ENCODER = os.path.join(ORACLE_DIR, "_ref", "TAppEncoderRef")   # the unmodified CPU reference encoder
+REF_DECODER = os.path.join(ORACLE_DIR, "_ref", "TAppDecoderRef")
+
+
+def encode_reference(width, height, **kw):
+    """Encode a synthetic lenslet frame with the unmodified CPU reference (checker / baseline only)."""
+    from hevc_hop_b200 import encoder
+    return encoder.encode(REF_ENCODER, width, height, retries=1, **kw)
+
+
 def ref_path():
     return os.path.join(ORACLE_DIR, "_ref", "libhopref.so")
 

@@ -6,10 +6,11 @@ import os
 
 import pytest
 
+import _oracle
 from hevc_hop_b200 import encoder
 
 pytestmark = pytest.mark.gpu
-have = os.path.exists(encoder.HOP_ENCODER) and os.path.exists(encoder.REF_ENCODER)
+have = os.path.exists(encoder.HOP_ENCODER) and os.path.exists(_oracle.REF_ENCODER)
 
 
 @pytest.mark.skipif(not have, reason="encoder binaries not built (need /root/reference at build time)")
@@ -17,7 +18,7 @@ have = os.path.exists(encoder.HOP_ENCODER) and os.path.exists(encoder.REF_ENCODE
                                                ((136, 104), 8, 37)])      # partial CTUs at the right / bottom edge
 def test_bitstream_identical_to_reference(size, bit_depth, qp):
     w, h = size
-    ref = encoder.encode(encoder.REF_ENCODER, w, h, seed=1, qp=qp, bit_depth=bit_depth)
+    ref = _oracle.encode_reference(w, h, seed=1, qp=qp, bit_depth=bit_depth)
     hop = encoder.encode(encoder.HOP_ENCODER, w, h, seed=1, qp=qp, bit_depth=bit_depth)
     assert hashlib.md5(hop["bitstream"]).hexdigest() == hashlib.md5(ref["bitstream"]).hexdigest()
     assert hop["rec"] == ref["rec"]
@@ -28,7 +29,7 @@ def test_bitstream_identical_to_reference(size, bit_depth, qp):
 @pytest.mark.skipif(not have, reason="encoder binaries not built (need /root/reference at build time)")
 def test_unfused_call_path_is_identical_too(monkeypatch):
     """HOP_FUSED=0: xPatternSearch and xPatternSearchGT as separate GPU calls, fractional refinement on the host."""
-    ref = encoder.encode(encoder.REF_ENCODER, 128, 64, seed=3)
+    ref = _oracle.encode_reference(128, 64, seed=3)
     monkeypatch.setenv("HOP_FUSED", "0")
     hop = encoder.encode(encoder.HOP_ENCODER, 128, 64, seed=3)
     assert hop["bitstream"] == ref["bitstream"] and hop["rec"] == ref["rec"] and hop["trace"] == ref["trace"]
