@@ -286,3 +286,41 @@ def test_wild_amvp_vector_cannot_leave_the_mirror(ctx):
     mj["amvp"] = gj["amvp"]
     r = ctx.motion_search(mj, b.org, None)
     assert r["refined"][0] == 1 and ctx.motion_search(mj, b.org, None).tobytes() == r.tobytes()
+
+
+def test_randomised_content_and_parameters(ctx):
+    """Many small random cases: extreme sample values (0 / max checkerboards, flat, noise), random lambda,
+    predictors, thresholds, start vectors and staircase positions, both bit depths."""
+    orc = _oracle.oracle()
+    rng = np.random.default_rng(2026)
+    shapes = [(8, 8), (8, 4), (4, 8), (16, 8), (16, 16), (16, 12), (12, 16), (32, 8)]
+    for it in range(40):
+        c, r = shapes[it % len(shapes)]
+        bd = 8 if it % 3 else 10
+        maxv = (1 << bd) - 1
+        b = PuBatch(c, r, 3, seed=1000 + it, bit_depth=bd, sr=24, use_had=it % 2, n_start=1 + it % 3)
+        kind = it % 4
+        if kind == 0:      # 0 / max checkerboard
+            ref = np.where(b.ref < 0, b.ref, ((np.arange(b.ref.size) + np.arange(b.ref.size) // b.pw) % 2) * maxv).astype(np.int16)
+            org = rng.integers(0, 2, size=b.org.size).astype(np.int16) * maxv
+        elif kind == 1:    # uniform noise over the full range
+            ref = np.where(b.ref < 0, b.ref, rng.integers(0, maxv + 1, size=b.ref.size)).astype(np.int16)
+            org = rng.integers(0, maxv + 1, size=b.org.size).astype(np.int16)
+        elif kind == 2:    # flat
+            ref = np.where(b.ref < 0, b.ref, maxv // 3).astype(np.int16)
+            org = np.full(b.org.size, maxv // 3 + 1, dtype=np.int16)
+        else:
+            ref, org = b.ref, b.org
+        sj, gj = b.search_jobs.copy(), b.gt_jobs.copy()
+        lam = int(rng.integers(1000, 4000000))
+        for j in (sj, gj):
+            j["cost"]["lambda_cost"] = lam
+            j["cost"]["pred"]["hor"] = rng.integers(-600, 600, size=3).astype(np.int16)
+            j["cost"]["pred"]["ver"] = rng.integers(-600, 600, size=3).astype(np.int16)
+        gj["threshold"] = rng.choice([0xFFFFFFFE, 500, 5000, 50000], size=3)
+        assert ctx.pattern_search(sj, org, ref).tobytes() == orc.pattern_search(sj, org, ref).tobytes(), it
+        gt_assert_equal(ctx.pattern_search_gt(gj, org, ref), orc.pattern_search_gt(gj, org, ref))
+        fj = b.frac_jobs()
+        fj["cost"] = gj["cost"]
+        got, want = ctx.frac_search(fj, org, ref), _oracle.frac_search(fj, org, ref)
+        assert got.tobytes() == want.tobytes(), it
