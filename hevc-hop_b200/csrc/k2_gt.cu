@@ -133,34 +133,51 @@ __device__ __forceinline__ double small_int_to_double(int n)
 //            have a zero low word), so reading a sample costs no int->double conversion;
 //            win[Yc * WS + Xc] with Yc = Y + w, Xc = X + w
 //   lim_xw : (w + cols - 1) - 1 + w, lim_yw likewise -- the upper clamp in window coordinates
+//
+// What is bit-for-bit the reference's: Fx, Fy (computed by the callers with the reference's operation order)
+// and their C truncation -- the sample POSITION is a discontinuous function of them.  What is NOT replayed
+// operation by operation is the interpolation weight and the bilinear blend, because only the rounded 8-bit
+// result is observable and it cannot depend on the last bits ("warp rounding"):
+//  (1) p, q are rationals with the ODD denominator D = (2*cols-1)(2*rows-1) <= 127^2, so the exact blend of
+//      four integers has denominator D^2 and stays >= 1/(2*D^2) >= 1.9e-9 away from every half-integer;
+//  (2) the reference's own binary64 evaluation and the one below both stay within 2e-10 of that exact value
+//      (weights within 8e-14 of the exact rationals, samples <= 1023, a handful of roundings at 2^-44);
+//  (3) hence round-to-nearest of either is the same integer, and the 0/255 clip commutes with the rounding.
+//  The reference's literal sequence is kept under HOP_WARP_REFERENCE_OPS for A/B parity runs.
 template <int WS>
-__device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int w,
-                                           double Fx, double Fy, int off_x, int off_y, double off_xd,
-                                           double off_yd, int lim_xw, int lim_yw)
+__device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int w, double Fx, double Fy,
+                                           int off_x, int off_y, int lim_xw, int lim_yw)
 {
-  const int Y = __double2int_rz(Fy) - off_y;     // C truncation toward zero
-  const int X = __double2int_rz(Fx) - off_x;
-  // (double)Y / (double)X stay I2F conversions: the kernel is issue bound, and the conversion-free form
-  // (2^52 magic: LOP + MOV + DADD) measured 4 % slower (profiles/r01_k2_experiments.txt)
-  const double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)Y);
-  const double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)X);
+  const int wox = w - off_x, woy = w - off_y;    // loop invariant
+  const int Yt = __double2int_rz(Fy);            // C truncation toward zero
+  const int Xt = __double2int_rz(Fx);
   // the six ordered clamps of :950-961 collapse to [-w, lim-1]: after the first four the value is in
   // [-w, lim]; the last two map lim to lim-1.  In window coordinates: max(min(Y + w, lim_yw), 0).
-  const int Yc = __vimin_s32_relu(Y + w, lim_yw);
-  const int Xc = __vimin_s32_relu(X + w, lim_xw);
+  const int Yc = __vimin_s32_relu(Yt + woy, lim_yw);
+  const int Xc = __vimin_s32_relu(Xt + wox, lim_xw);
   const uint32_t* r0 = win + Yc * WS + Xc;
   const double A = __hiloint2double((int)r0[0], 0), B = __hiloint2double((int)r0[1], 0);
   const double C = __hiloint2double((int)r0[WS], 0), D = __hiloint2double((int)r0[WS + 1], 0);
+  // (double)Yt / (double)Xt stay I2F conversions: the kernel is issue bound, and the conversion-free form
+  // (2^52 magic: LOP + MOV + DADD) measured 4 % slower (profiles/r01_k2_experiments.txt)
+#ifdef HOP_WARP_REFERENCE_OPS
+  const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
+  const double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)(Yt - off_y));
+  const double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)(Xt - off_x));
   const double omp = __dsub_rn(1.0, p), omq = __dsub_rn(1.0, q);
   double aux = __dmul_rn(omq, __dadd_rn(__dmul_rn(omp, A), __dmul_rn(p, B)));
   aux = __dadd_rn(aux, __dmul_rn(q, __dadd_rn(__dmul_rn(omp, C), __dmul_rn(p, D))));
-  // "if (aux > 255) aux = 255; if (aux < 0) aux = 0; (Pel)(aux + 0.5)":
-  //  (1) the clip commutes with the rounding: clamping the rounded integer to [0,255] is the same;
-  //  (2) trunc(fl(aux + 0.5)) == round-to-nearest(aux): p and q are rationals with the ODD denominator
-  //      D = (2*cols-1)(2*rows-1), so the exact bilinear value has denominator D^2 and stays at least
-  //      1/(2*D^2) >= 1.9e-9 away from every half-integer, four orders of magnitude more than the
-  //      accumulated binary64 rounding error (< 1e-12) -- ties never occur (warp rounding).
-  //  Adding 1.5*2^52 leaves round-to-nearest(aux) in the low word: no double->int conversion.
+#else
+  // fractional parts: Fx - trunc(Fx) is exact (Sterbenz); the reference's (Fx - off) - X differs from it by
+  // the rounding of Fx - off only (<= 2^-46)
+  const double q = __dsub_rn(Fy, (double)Yt);
+  const double p = __dsub_rn(Fx, (double)Xt);
+  // three lerps: top = A + p(B-A), bot = C + p(D-C), aux = top + q(bot-top)   (6 fp64 ops instead of 11)
+  const double top = __fma_rn(p, __dsub_rn(B, A), A);
+  const double bot = __fma_rn(p, __dsub_rn(D, C), C);
+  const double aux = __fma_rn(q, __dsub_rn(bot, top), top);
+#endif
+  // Adding 1.5*2^52 leaves round-to-nearest(aux) in the low word: no double->int conversion.
   const int v = __double2loint(__dadd_rn(aux, 6755399441055744.0));
   return __vimin_s32_relu(v, 255);
 }
@@ -173,7 +190,6 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
                                                int off_x, int off_y)
 {
   constexpr int N = 4;   // off_x/off_y: W/2 - W/4 with W = 2*cols on the 2x grid, 0 on the 1x grid (sweep)
-  const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
   const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
   double h0x[N], h1x[N];
 #pragma unroll
@@ -193,7 +209,7 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
     for (int k = 0; k < N; k++) {
       const double Fx = __dadd_rn(__dadd_rn(h0x[k], h3y), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x[k], h4y), h7);
-      t.d[r * N + k] = o[k] - warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_xw, lim_yw);
+      t.d[r * N + k] = o[k] - warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, lim_xw, lim_yw);
     }
     if (HAD) t.row_transform(r);
   }
@@ -212,7 +228,6 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
                                                     const uint32_t* __restrict__ win, int w, int cols, int rows,
                                                     int off_x, int off_y)
 {
-  const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
   const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
   const int y0 = ty + 4 * half;
   double h3y[4], h4y[4];
@@ -238,7 +253,7 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
     for (int r = 0; r < 4; r++) {
       const double Fx = __dadd_rn(__dadd_rn(h0x, h3y[r]), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x, h4y[r]), h7);
-      d[r * 8 + k] -= warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, off_xd, off_yd, lim_xw, lim_yw);
+      d[r * 8 + k] -= warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, lim_xw, lim_yw);
     }
   }
   if (!HAD) {
@@ -355,6 +370,8 @@ template <> struct GtCfg<0> { static constexpr int T = 336, B = 2; };
 template <> struct GtCfg<1> { static constexpr int T = 224, B = 2; };
 template <> struct GtCfg<2> { static constexpr int T = 448, B = 1; };
 template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
+template <> struct GtCfg<4> { static constexpr int T = 448, B = 2; };
+template <> struct GtCfg<5> { static constexpr int T = 224, B = 4; };
 
 // The whole xPatternSearchGT of one PU, executed by one CTA.  `out` is written by thread 0.
 // smem_raw: [GtShared][org rows*cols int32][window (rows+2w) x WS uint32]; when `org_staged` the int32
@@ -786,15 +803,18 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
                                    HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
                                    unsigned* done_flag, unsigned seq, RefBounds rb)
 {
-  // measured on B200 (profiles/r01_k2_launch_cfg.txt): 3 CTAs x 224 threads win for the small stride
-  // classes, 2 CTAs x 336 threads for the 64x64 class (shared memory allows only two CTAs there)
+  // measured on B200 (profiles/r01_k2_launch_cfg.txt): the kernel wants resident warps more than registers --
+  // 4 CTAs x 224 threads (72 registers, a few spills outside the pixel loop) win for the small stride classes,
+  // 2 CTAs x 448 threads for the 64x64 class (shared memory allows only two CTAs there)
   static int env_cfg = -2;
   if (env_cfg == -2) { const char* e = getenv("HOP_K2_CFG"); env_cfg = e ? atoi(e) : -1; }
-  const int cfg = env_cfg >= 0 ? env_cfg : (WS == 129 ? 0 : 3);
+  const int cfg = env_cfg >= 0 ? env_cfg : (WS == 129 ? 4 : 5);
   switch (cfg) {
     case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 3:  return gt_launch_cfg<WS, 3>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 4:  return gt_launch_cfg<WS, 4>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 5:  return gt_launch_cfg<WS, 5>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     default: return gt_launch_cfg<WS, 0>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
@@ -1080,10 +1100,10 @@ cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t*
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return motion_tail_cfg<33, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case 65:  return motion_tail_cfg<65, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case 97:  return motion_tail_cfg<97, 3>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    default:  return motion_tail_cfg<129, 0>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 33:  return motion_tail_cfg<33, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 65:  return motion_tail_cfg<65, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case 97:  return motion_tail_cfg<97, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    default:  return motion_tail_cfg<129, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
 
