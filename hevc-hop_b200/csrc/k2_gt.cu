@@ -127,12 +127,29 @@ __device__ __forceinline__ double small_int_to_double(int n)
   return __dsub_rn(__hiloint2double(0x43300000, n), 4503599627370496.0);
 }
 
+// Per-thread constants of the sampling loop.  wox/woy go through an opaque move so that they live in ordinary
+// registers: the fused add-min-max instruction takes its addend from a register, and a value the compiler knows
+// to be CTA-uniform would be re-materialised from the uniform register file for every pixel.
+struct WarpCtx {
+  unsigned win_sa;          // shared-memory address of the window
+  int wox, woy;             // w - off_x, w - off_y: window coordinate of X = trunc(Fx) - off_x is trunc(Fx) + wox
+  int lim_xw, lim_yw;       // (w + cols - 1) - 1 + w, likewise for rows: the upper clamp in window coordinates
+  int off_x, off_y;
+  __device__ __forceinline__ WarpCtx(const uint32_t* win, int w, int cols, int rows, int ox, int oy)
+  {
+    win_sa = (unsigned)__cvta_generic_to_shared(win);
+    asm("mov.b32 %0, %1;" : "=r"(wox) : "r"(w - ox));
+    asm("mov.b32 %0, %1;" : "=r"(woy) : "r"(w - oy));
+    lim_xw = 2 * w + cols - 2; lim_yw = 2 * w + rows - 2;
+    off_x = ox; off_y = oy;
+  }
+};
+
 // One warped sample: ProjectiveTransform body for the affine case (h2 == h5 == 0 => denominator is
 // exactly 1.0, so the reference's division returns its numerator unchanged), TComPrediction.cpp:925-972,1025.
 //   win    : the clamped window samples as the HIGH 32-bit word of their binary64 value (integers < 2^20
 //            have a zero low word), so reading a sample costs no int->double conversion;
 //            win[Yc * WS + Xc] with Yc = Y + w, Xc = X + w
-//   lim_xw : (w + cols - 1) - 1 + w, lim_yw likewise -- the upper clamp in window coordinates
 //
 // What is bit-for-bit the reference's: Fx, Fy (computed by the callers with the reference's operation order)
 // and their C truncation -- the sample POSITION is a discontinuous function of them.  What is NOT replayed
@@ -145,25 +162,31 @@ __device__ __forceinline__ double small_int_to_double(int n)
 //  (3) hence round-to-nearest of either is the same integer, and the 0/255 clip commutes with the rounding.
 //  The reference's literal sequence is kept under HOP_WARP_REFERENCE_OPS for A/B parity runs.
 template <int WS>
-__device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int w, double Fx, double Fy,
-                                           int off_x, int off_y, int lim_xw, int lim_yw)
+__device__ __forceinline__ int warp_sample(const WarpCtx& wc, double Fx, double Fy)
 {
-  const int wox = w - off_x, woy = w - off_y;    // loop invariant
+  const int wox = wc.wox, woy = wc.woy, lim_xw = wc.lim_xw, lim_yw = wc.lim_yw;
   const int Yt = __double2int_rz(Fy);            // C truncation toward zero
   const int Xt = __double2int_rz(Fx);
   // the six ordered clamps of :950-961 collapse to [-w, lim-1]: after the first four the value is in
   // [-w, lim]; the last two map lim to lim-1.  In window coordinates: max(min(Y + w, lim_yw), 0).
   const int Yc = __vimin_s32_relu(Yt + woy, lim_yw);
   const int Xc = __vimin_s32_relu(Xt + wox, lim_xw);
-  const uint32_t* r0 = win + Yc * WS + Xc;
-  const double A = __hiloint2double((int)r0[0], 0), B = __hiloint2double((int)r0[1], 0);
-  const double C = __hiloint2double((int)r0[WS], 0), D = __hiloint2double((int)r0[WS + 1], 0);
+  // one IMAD + one LEA: the window's 32-bit shared-memory address is kept as an integer so that the word
+  // offset of the window inside the CTA's dynamic shared memory is folded into the base once per pass
+  const unsigned a = wc.win_sa + 4u * (unsigned)(Yc * WS + Xc);
+  unsigned hA, hB, hC, hD;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(hA) : "r"(a));
+  asm("ld.shared.u32 %0, [%1+4];" : "=r"(hB) : "r"(a));
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hC) : "r"(a), "n"(WS * 4));
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hD) : "r"(a), "n"(WS * 4 + 4));
+  const double A = __hiloint2double((int)hA, 0), B = __hiloint2double((int)hB, 0);
+  const double C = __hiloint2double((int)hC, 0), D = __hiloint2double((int)hD, 0);
   // (double)Yt / (double)Xt stay I2F conversions: the kernel is issue bound, and the conversion-free form
   // (2^52 magic: LOP + MOV + DADD) measured 4 % slower (profiles/r01_k2_experiments.txt)
 #ifdef HOP_WARP_REFERENCE_OPS
-  const double off_xd = small_int_to_double(off_x), off_yd = small_int_to_double(off_y);
-  const double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)(Yt - off_y));
-  const double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)(Xt - off_x));
+  const double off_xd = small_int_to_double(wc.off_x), off_yd = small_int_to_double(wc.off_y);
+  const double q = __dsub_rn(__dsub_rn(Fy, off_yd), (double)(Yt - wc.off_y));
+  const double p = __dsub_rn(__dsub_rn(Fx, off_xd), (double)(Xt - wc.off_x));
   const double omp = __dsub_rn(1.0, p), omq = __dsub_rn(1.0, q);
   double aux = __dmul_rn(omq, __dadd_rn(__dmul_rn(omp, A), __dmul_rn(p, B)));
   aux = __dadd_rn(aux, __dmul_rn(q, __dadd_rn(__dmul_rn(omp, C), __dmul_rn(p, D))));
@@ -186,11 +209,10 @@ __device__ __forceinline__ int warp_sample(const uint32_t* __restrict__ win, int
 template <int WS, bool HAD>
 __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, double h1, double h4, double h7,
                                                int tx, int ty, const int* __restrict__ org,
-                                               const uint32_t* __restrict__ win, int w, int cols, int rows,
-                                               int off_x, int off_y)
+                                               const WarpCtx& wc, int cols)
 {
   constexpr int N = 4;   // off_x/off_y: W/2 - W/4 with W = 2*cols on the 2x grid, 0 on the 1x grid (sweep)
-  const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
+  const int off_x = wc.off_x, off_y = wc.off_y;
   double h0x[N], h1x[N];
 #pragma unroll
   for (int k = 0; k < N; k++) {
@@ -209,7 +231,7 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
     for (int k = 0; k < N; k++) {
       const double Fx = __dadd_rn(__dadd_rn(h0x[k], h3y), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x[k], h4y), h7);
-      t.d[r * N + k] = o[k] - warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, lim_xw, lim_yw);
+      t.d[r * N + k] = o[k] - warp_sample<WS>(wc, Fx, Fy);
     }
     if (HAD) t.row_transform(r);
   }
@@ -225,10 +247,9 @@ __device__ __forceinline__ uint32_t eval_tile4(double h0, double h3, double h6, 
 template <int WS, bool HAD>
 __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double h6, double h1, double h4, double h7,
                                                     int tx, int ty, int half, const int* __restrict__ org,
-                                                    const uint32_t* __restrict__ win, int w, int cols, int rows,
-                                                    int off_x, int off_y)
+                                                    const WarpCtx& wc, int cols)
 {
-  const int lim_xw = 2 * w + cols - 2, lim_yw = 2 * w + rows - 2;
+  const int off_x = wc.off_x, off_y = wc.off_y;
   const int y0 = ty + 4 * half;
   double h3y[4], h4y[4];
 #pragma unroll
@@ -253,7 +274,7 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
     for (int r = 0; r < 4; r++) {
       const double Fx = __dadd_rn(__dadd_rn(h0x, h3y[r]), h6);    // (h0*x + h3*y) + h6, left to right
       const double Fy = __dadd_rn(__dadd_rn(h1x, h4y[r]), h7);
-      d[r * 8 + k] -= warp_sample<WS>(win, w, Fx, Fy, off_x, off_y, lim_xw, lim_yw);
+      d[r * 8 + k] -= warp_sample<WS>(wc, Fx, Fy);
     }
   }
   if (!HAD) {
@@ -313,10 +334,11 @@ __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const
   const int tiles_x = cols / 4, ntiles = tiles_x * (rows / 4);
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  const WarpCtx wc(s_win, w, cols, rows, off_x, off_y);
   uint32_t acc = 0;
   for (int tile = g + groups * crank; tile < ntiles; tile += groups * csize) {   // cluster: CTAs interleave tiles
     const int tx = (tile % tiles_x) * 4, ty = (tile / tiles_x) * 4;
-    acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, s_win, w, cols, rows, off_x, off_y);
+    acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, wc, cols);
   }
   atomicAdd(&sh.dist[c], acc);
 }
@@ -332,10 +354,11 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
   const int tiles_x = cols / 8, ntiles = tiles_x * (rows / 8);
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  const WarpCtx wc(s_win, w, cols, rows, off_x, off_y);
   uint32_t acc = 0;
   for (int tile = g + groups * crank; tile < ntiles; tile += groups * csize) {   // cluster: CTAs interleave tiles
     const int tx = (tile % tiles_x) * 8, ty = (tile / tiles_x) * 8;
-    acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, s_win, w, cols, rows, off_x, off_y);
+    acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, wc, cols);
   }
   if (!HAD || half == 0) atomicAdd(&sh.dist[c], acc);   // HAD: both lanes hold the tile sums, count once
 }
@@ -355,12 +378,15 @@ __device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const 
 }
 
 // Window row stride classes (in 32-bit words), compile-time so that the 2x2 footprint is one address
-// plus immediates.  WS == 1 (mod 32): (X, Y) -> bank (X + Y) mod 32, so the two lanes of a tile pair
-// (4 rows apart) and the 2x2 footprints of neighbouring candidates spread over the banks.
-// win_w = cols + min(cols, rows) <= 128.
+// plus immediates.  The 32 lanes of a warp are 16 neighbouring candidates x 2 half tiles reading the SAME
+// pixel of their tile: their window positions differ by the candidates' corner offsets, i.e. by small
+// (dx, dy) with |dx|, |dy| of the same size.  WS == 3 (mod 32) maps (X, Y) to bank (X + 3Y) mod 32, which
+// separates (dx, dy) from (dx +- 1, dy -+ 1): measured 4.0 shared-memory wavefronts per request with
+// WS == 1 (mod 32), 2.1 simulated with 3 (profiles/r01_k2_experiments.txt).  win_w = cols + min(cols, rows) <= 128.
+constexpr int WS_A = 35, WS_B = 67, WS_C = 99, WS_D = 131;
 __host__ __device__ constexpr int gt_stride_class(int win_w)
 {
-  return win_w <= 33 ? 33 : win_w <= 65 ? 65 : win_w <= 97 ? 97 : 129;
+  return win_w <= 32 ? WS_A : win_w <= 64 ? WS_B : win_w <= 96 ? WS_C : WS_D;
 }
 constexpr int gt_class_threads(int) { return GT_THREADS; }
 
@@ -808,7 +834,7 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
   // 2 CTAs x 448 threads for the 64x64 class (shared memory allows only two CTAs there)
   static int env_cfg = -2;
   if (env_cfg == -2) { const char* e = getenv("HOP_K2_CFG"); env_cfg = e ? atoi(e) : -1; }
-  const int cfg = env_cfg >= 0 ? env_cfg : (WS == 129 ? 4 : 5);
+  const int cfg = env_cfg >= 0 ? env_cfg : (WS == WS_D ? 4 : 5);
   switch (cfg) {
     case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
@@ -826,10 +852,10 @@ cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return gt_launch_class<33>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case 65:  return gt_launch_class<65>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case 97:  return gt_launch_class<97>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    default:  return gt_launch_class<129>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_A:  return gt_launch_class<WS_A>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_B:  return gt_launch_class<WS_B>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_C:  return gt_launch_class<WS_C>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    default:  return gt_launch_class<WS_D>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
 
@@ -873,10 +899,10 @@ cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_or
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return sweep_launch_class<33>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
-    case 65:  return sweep_launch_class<65>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
-    case 97:  return sweep_launch_class<97>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
-    default:  return sweep_launch_class<129>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    case WS_A:  return sweep_launch_class<WS_A>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    case WS_B:  return sweep_launch_class<WS_B>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    case WS_C:  return sweep_launch_class<WS_C>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    default:  return sweep_launch_class<WS_D>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
   }
 }
 
@@ -1100,10 +1126,10 @@ cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t*
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case 33:  return motion_tail_cfg<33, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case 65:  return motion_tail_cfg<65, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case 97:  return motion_tail_cfg<97, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    default:  return motion_tail_cfg<129, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_A:  return motion_tail_cfg<WS_A, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_B:  return motion_tail_cfg<WS_B, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_C:  return motion_tail_cfg<WS_C, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    default:  return motion_tail_cfg<WS_D, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
   }
 }
 
@@ -1148,10 +1174,10 @@ cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const 
   if (csize < 2) return cudaErrorNotSupported;
   if (launches) (*launches)++;
   switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
-    case 33:  return gt_cluster_class<33>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    case 65:  return gt_cluster_class<65>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    case 97:  return gt_cluster_class<97>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    default:  return gt_cluster_class<129>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_A:  return gt_cluster_class<WS_A>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_B:  return gt_cluster_class<WS_B>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_C:  return gt_cluster_class<WS_C>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    default:  return gt_cluster_class<WS_D>(d_job, d_org, d_ref, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
   }
 }
 
@@ -1164,10 +1190,10 @@ cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org
   if (csize < 2) return cudaErrorNotSupported;
   if (launches) (*launches)++;
   switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
-    case 33:  return motion_cluster_class<33>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    case 65:  return motion_cluster_class<65>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    case 97:  return motion_cluster_class<97>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    default:  return motion_cluster_class<129>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_A:  return motion_cluster_class<WS_A>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_B:  return motion_cluster_class<WS_B>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_C:  return motion_cluster_class<WS_C>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    default:  return motion_cluster_class<WS_D>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
   }
 }
 
