@@ -40,6 +40,15 @@ struct Scratch {
 
 }  // namespace
 
+#ifdef HOP_TRACE
+#include <time.h>
+static unsigned long long g_host_trace[8];
+static inline unsigned long long host_ns() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (unsigned long long)t.tv_sec * 1000000000ull + t.tv_nsec; }
+#define HOST_STAMP(i) (g_host_trace[(i)] = host_ns())
+#else
+#define HOST_STAMP(i) ((void)0)
+#endif
+
 struct HopCtx {
   int          device = 0;
   cudaStream_t stream = nullptr;
@@ -310,7 +319,7 @@ int k1_slices(const HopCtx* ctx, int n)
 }
 int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                HopSearchResult* d_out, int smem_bytes, cudaStream_t s, unsigned* done_flag = nullptr, unsigned seq = 0,
-               int job_stride = 0)
+               int job_stride = 0, const InlinePu* inl = nullptr)
 {
   // merge words: all-ones keys / zero tickets between launches (the kernel restores them itself)
   const size_t kcap = ctx->keys.cap, dcap = ctx->done.cap;
@@ -321,7 +330,7 @@ int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_
   if (ctx->done.cap != dcap) CU(cudaMemsetAsync(ctx->done.p, 0, ctx->done.cap, s));
   int l = 0;
   CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, (unsigned int*)ctx->done.p,
-                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq, job_stride));
+                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq, job_stride, inl));
   ctx->launches += l;
   return HOP_OK;
 }
@@ -660,6 +669,7 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
   if (n == 1 && !ref) {
     // the encoder's call: zero-copy job / block / result, two stream-ordered launches, one wait
     if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
+    HOST_STAMP(0);
     if ((st = pin_ready(ctx))) return st;
     HopMotionJob packed = jobs[0];
     const HopSearchJob& j = jobs[0].search;
@@ -667,27 +677,35 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
     if (j.org_off < 0 || (size_t)j.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
     packed.search.org_off = 0;
     packed.search.org_stride = j.cols;
-    memcpy(ctx->pin_h, &packed, sizeof(packed));
-    int16_t* dst = (int16_t*)(ctx->pin_h + PIN_JOB);
+    // job (and a small block) as kernel parameters; larger blocks through the mapped buffer
+    static thread_local InlinePu ipu;
+    ipu.use = j.cols * j.rows <= INLINE_ORG_SAMPLES ? 2 : 1;
+    ipu.job = packed;
+    int16_t* dst = ipu.use == 2 ? ipu.org : (int16_t*)(ctx->pin_h + PIN_JOB);
     for (int r = 0; r < j.rows; r++) memcpy(dst + (size_t)r * j.cols, org + j.org_off + (size_t)r * j.org_stride, sizeof(int16_t) * j.cols);
     const unsigned seq = ++ctx->pin_seq;
     const int16_t* d_org = (const int16_t*)(ctx->pin_d + PIN_JOB);
+    HOST_STAMP(1);
     st = search_dev(ctx, 1, (const HopSearchJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1, (int)smem, ctx->stream,
-                    nullptr, 0, (int)sizeof(HopMotionJob));
+                    nullptr, 0, (int)sizeof(HopMotionJob), &ipu);
     if (st) return st;
+    HOST_STAMP(2);
     int l = 0;
     cudaError_t ce = ctx->use_clusters
         ? motion_single_launch((const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
                                (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                               bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq)
+                               bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq, &ipu)
         : cudaErrorNotSupported;
     if (ce == cudaErrorNotSupported)
       ce = motion_tail_launch(1, (const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
                               (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                              bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq);
+                              bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq, &ipu);
     CU(ce);
     ctx->launches += l;
-    return unpack_single(ctx, seq, out);
+    HOST_STAMP(3);
+    st = unpack_single(ctx, seq, out);
+    HOST_STAMP(4);
+    return st;
   }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopMotionJob), org, org_samples, ref, ref_samples, sizeof(HopMotionResult) * (size_t)n, &d_ref);
@@ -813,3 +831,17 @@ int hop_probe_alu(HopCtx* ctx, int what, double* gops_out, double* ms_out)
 }
 
 }  // extern "C"
+
+#ifdef HOP_TRACE
+// debug builds only: out[0..7] host stamps (ns, CLOCK_MONOTONIC), out[8..71] k1 table, out[72..135] tail table (%globaltimer ns)
+extern "C" int hop_debug_trace(HopCtx* ctx, unsigned long long* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 8; i++) out[i] = g_host_trace[i];
+  hop::trace_read_k1(out + 8);
+  hop::trace_read_k2(out + 8 + 64);
+  return HOP_OK;
+}
+#endif

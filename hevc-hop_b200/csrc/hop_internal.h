@@ -33,24 +33,37 @@ cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_or
                               RefBounds rb = REF_UNBOUNDED);
 cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,
                                   const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches);
+struct InlinePu;
 // latency path: one PU searched by a thread-block cluster; cudaErrorNotSupported for single-tile shapes
 cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
                              int cols, int rows, cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq);
 cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
                                  const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows,
-                                 cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq);
+                                 cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq,
+                                 const InlinePu* inl = nullptr);
+// Single-call latency path: the job and (for PUs up to 512 samples) the original block travel as kernel
+// parameters -- the constant bank is filled by the launch itself, so the kernels start without a dependent
+// read of host memory over PCIe (measured 2.4-5 us per read, twice per kernel).  use == 0: read jobs[] / org[].
+constexpr int INLINE_ORG_SAMPLES = 512;
+struct InlinePu {
+  int use;                            // 0 = off, 1 = job inline, 2 = job and original block inline
+  int pad;
+  HopMotionJob job;                   // .search is the K1 job; org_off 0, org_stride cols when the block is inline
+  int16_t org[INLINE_ORG_SAMPLES];
+};
 // K1
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
                           int smem_bytes, cudaStream_t stream, int* launches,
-                          unsigned* done_flag = nullptr, unsigned seq = 0, int job_stride = 0);
+                          unsigned* done_flag = nullptr, unsigned seq = 0, int job_stride = 0,
+                          const InlinePu* inl = nullptr);
 // K5 + fused motion search
 cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                         HopFracResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);
 cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
                                cudaStream_t stream, int* launches, RefBounds rb = REF_UNBOUNDED,
-                               unsigned* done_flag = nullptr, unsigned seq = 0);
+                               unsigned* done_flag = nullptr, unsigned seq = 0, const InlinePu* inl = nullptr);
 size_t      search_smem_bytes(const HopSearchJob& job, int slices);
 constexpr int K1_DEFAULT_SMEM = 96 * 1024;   // byte-path budget when the job shapes are not known on the host
 // K3
@@ -63,5 +76,21 @@ cudaError_t ref_extend_launch(int16_t* d_origin, int stride, int pic_w, int pic_
 // probes
 cudaError_t probe_launch(int what, int blocks, int threads, int iters, unsigned* d_sink,
                          cudaStream_t stream, double* lane_ops_per_thread_iter);
+
+
+// ---- latency tracing (debug builds only: tools/build_variant.sh trace -DHOP_TRACE) ---------------------------
+// HOP_STAMP(i) records %globaltimer (ns) of one thread at a phase boundary of the single-call path; every
+// translation unit keeps its own table, read back by trace_read_k1 / trace_read_k2 (tools/latency_trace.py).
+#ifdef HOP_TRACE
+#define HOP_TRACE_SLOTS 64
+#define HOP_STAMP_ANY(tbl, i) do { if (threadIdx.x == 0) { unsigned long long t_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); (tbl)[(i)] = t_; } } while (0)
+#define HOP_STAMP(tbl, i) do { if (blockIdx.x == 0 && blockIdx.y == 0) HOP_STAMP_ANY(tbl, i); } while (0)
+void trace_read_k1(unsigned long long* out);
+void trace_read_k2(unsigned long long* out);
+#else
+#define HOP_STAMP_ANY(tbl, i) do {} while (0)
+#define HOP_STAMP(tbl, i) do {} while (0)
+#endif
 
 }  // namespace hop

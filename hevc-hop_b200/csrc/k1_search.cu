@@ -110,7 +110,7 @@ __device__ __forceinline__ unsigned long long k1_generic(const HopSearchJob& job
     for (int r = 0; r < rows; r += g.step) {
       const int16_t* rr = srch + r * stride;
       const int16_t* oo = org + r * job.org_stride;
-      for (int c = 0; c < cols; c++) sum = __sad((int)__ldg(oo + c), (int)__ldg(rr + c), sum);
+      for (int c = 0; c < cols; c++) sum = __sad((int)oo[c], (int)__ldg(rr + c), sum);   // org may sit in shared memory (inline path)
     }
     sum <<= sub_shift;
     sum >>= dist_shift;
@@ -221,23 +221,36 @@ __device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, 
   return best;
 }
 
+#ifdef HOP_TRACE
+__device__ unsigned long long g_trace_k1[HOP_TRACE_SLOTS];
+void trace_read_k1(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_trace_k1, sizeof(g_trace_k1)); }
+#endif
+
 __global__ void __launch_bounds__(K1_THREADS)
 k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
           const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys,
           unsigned int* __restrict__ done, HopSearchResult* __restrict__ out, int smem_limit,
-          unsigned* done_flag, unsigned seq, int job_stride)
+          unsigned* done_flag, unsigned seq, int job_stride, const __grid_constant__ InlinePu ipu)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ unsigned long long s_red[32];
   __shared__ int s_unclean;
+  __shared__ int16_t s_inl_org[INLINE_ORG_SAMPLES];
+  HOP_STAMP(g_trace_k1, 0);
   const int job_id = blockIdx.x;
   // job_stride: bytes between jobs (HopSearchJob arrays, or the leading member of HopMotionJob arrays)
-  const HopSearchJob job = *reinterpret_cast<const HopSearchJob*>(reinterpret_cast<const char*>(jobs) + (size_t)job_id * job_stride);
+  const HopSearchJob job = ipu.use ? ipu.job.search
+                                   : *reinterpret_cast<const HopSearchJob*>(reinterpret_cast<const char*>(jobs) + (size_t)job_id * job_stride);
   const K1Geom g = k1_geom(job, blockIdx.y, gridDim.y);
   const bool empty = g.nx <= 0 || g.ny <= 0 || g.y_lo >= g.y_hi;    // degenerate window / slice beyond it
   const int16_t* org = org_buf + job.org_off;
   const int16_t* ref_y = ref_buf + job.ref_off;
   const int cols = job.cols, rows = job.rows;
+  if (ipu.use == 2) {                 // original block from the parameter bank (contiguous, stride cols)
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) s_inl_org[i] = ipu.org[i];
+    org = s_inl_org;
+    __syncthreads();
+  }
 
   bool bytes_ok = !empty && job.bit_depth == 8 && (cols % 4) == 0 && cols <= HOP_MAX_PU && rows <= HOP_MAX_PU &&
                   k1_smem_bytes(job, g) <= (size_t)smem_limit;
@@ -259,6 +272,7 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
     for (int i = threadIdx.x; i < ny_s; i += blockDim.x)
       s_bits_y[i] = (int)component_bits(((job.rng_top + g.y_lo + i) << job.cost.cost_scale) - job.cost.pred.ver);
     __syncthreads();
+    HOP_STAMP(g_trace_k1, 1);   // job arrived, bit tables built
     // original block: the sub-sampled rows, packed to bytes
     int bad = 0;
     for (int i = threadIdx.x; i < g.rused * (cols / 4); i += blockDim.x) {
@@ -293,6 +307,7 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
     }
     if (bad) s_unclean = 1;
     __syncthreads();
+    HOP_STAMP(g_trace_k1, 2);   // block and window staged
     // staircase check: NOT_VALID samples form a suffix of every row, starting no later than in the row above
     for (int r = threadIdx.x; r < g.st_rows; r += blockDim.x) {
       const int first = s_first_invalid[r], cnt = s_cnt_invalid[r];
@@ -302,6 +317,7 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
       if (!ok) s_unclean = 1;
     }
     __syncthreads();
+    HOP_STAMP(g_trace_k1, 3);   // staircase checked
     bytes_ok = s_unclean == 0;
     if (bytes_ok) {
       switch (cols / 4) {
@@ -318,7 +334,9 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
     }
   }
   if (!bytes_ok) best = empty ? ~0ull : k1_generic(job, g, org, ref_y);
+  HOP_STAMP(g_trace_k1, 4);     // positions searched
   best = block_min_u64(best, s_red);
+  HOP_STAMP(g_trace_k1, 5);
   if (threadIdx.x == 0) {
     if (best != ~0ull) atomicMin(&keys[job_id], best);
     __threadfence();
@@ -327,6 +345,7 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
       const unsigned long long key = atomicExch(&keys[job_id], ~0ull);
       done[job_id] = 0;
       k1_write_result(job, key, &out[job_id]);
+      HOP_STAMP_ANY(g_trace_k1, 6);   // last slice published the result
       if (done_flag) {               // single-call path: result and flag live in mapped host memory
         __threadfence_system();
         *(volatile unsigned*)done_flag = seq;
@@ -338,9 +357,10 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
                           int smem_bytes, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq,
-                          int job_stride)
+                          int job_stride, const InlinePu* inl)
 {
   static int attr_set = 0;
+  static const InlinePu no_inline = {};
   const int smem_max = 160 * 1024;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k1_search, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -352,7 +372,7 @@ cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_or
   if (smem_bytes > smem_max) smem_bytes = smem_max;
   if (smem_bytes < 1024) smem_bytes = 1024;
   k1_search<<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes, done_flag, seq,
-                                                                      job_stride ? job_stride : (int)sizeof(HopSearchJob));
+                                                                      job_stride ? job_stride : (int)sizeof(HopSearchJob), inl ? *inl : no_inline);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

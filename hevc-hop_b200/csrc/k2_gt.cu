@@ -27,7 +27,9 @@ namespace hop {
 
 namespace cg = cooperative_groups;
 
-__constant__ int8_t c_gt_offsets[GT_CANDS][8];   // x0,y0,x1,y1,x2,y2,x3,y3 in {-1,0,1}, loop order
+// x0,y0,x1,y1,x2,y2,x3,y3 in {-1,0,1}, loop order; global memory: every thread reads its own entry (a per-thread
+// index into constant memory would be serialised by the constant cache)
+__device__ __align__(8) int8_t d_gt_offsets[GT_CANDS][8];
 
 void gt_build_offset_table(int8_t table[GT_CANDS][8], int* count)
 {
@@ -52,25 +54,34 @@ void gt_build_offset_table(int8_t table[GT_CANDS][8], int* count)
 
 cudaError_t gt_upload_offset_table(const int8_t table[GT_CANDS][8])
 {
-  return cudaMemcpyToSymbol(c_gt_offsets, table, sizeof(int8_t) * GT_CANDS * 8);
+  return cudaMemcpyToSymbol(d_gt_offsets, table, sizeof(int8_t) * GT_CANDS * 8);
 }
+
+#ifdef HOP_TRACE
+__device__ unsigned long long g_trace_k2[HOP_TRACE_SLOTS];
+void trace_read_k2(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_trace_k2, sizeof(g_trace_k2)); }
+#endif
 
 struct GtShared {
   // per-pass candidate table (SoA, loop order)
   double   h0[GT_CANDS], h3[GT_CANDS], h6[GT_CANDS];   // Fx = h0*x + h3*y + h6
   double   h1[GT_CANDS], h4[GT_CANDS], h7[GT_CANDS];   // Fy = h1*x + h4*y + h7
-  uint32_t add_cost[GT_CANDS];                         // getCost(Hor,Ver) + getCost(getBitsGT(..))
-  uint32_t dist[GT_CANDS];                             // sum of tile SATDs / SADs
-  int32_t  valid[GT_CANDS];
-  int16_t  corner[GT_CANDS][8];
-  // search state
-  int32_t  centre[8];        // iBestNSSCenterX/Y[4] interleaved x,y
-  int32_t  best_corner[8];   // iBestCornerX/Y[4]
-  uint32_t dist_best;
-  int32_t  best_ss_x, best_ss_y;
-  int32_t  best_index;
-  uint32_t n_cand;
-  unsigned long long red_key[2];
+  // what the argmin reads is double buffered by pass parity: the set-up of the next pass (by the thread that
+  // owns the candidate) may overtake another warp that is still reducing the current one
+  uint32_t add_cost[2][GT_CANDS];                      // getCost(Hor,Ver) + getCost(getBitsGT(..))
+  uint32_t dist[2][GT_CANDS];                          // sum of tile SATDs / SADs
+  int32_t  valid[2][GT_CANDS];
+  int16_t  corner[2][GT_CANDS][8];
+  // search state, one replica per head warp (identical contents): written by lane 0 after the argmin of a
+  // pass, read by the warp's own lanes when they set up the next pass -- registers stay free for the tiles
+  struct State {
+    int4     cc;                                       // iBestNSSCenterX/Y, packed (y << 16) | (x & 0xffff) like corner[]
+    int4     bc;                                       // iBestCornerX/Y (:4776)
+    uint32_t dist_best;
+    int32_t  best_ss_x, best_ss_y, best_index;
+    uint32_t n_cand;
+  } st[2];
+  unsigned long long red_key[2];                       // sweep kernel: cross-warp argmin
   uint32_t red_cnt[2];
 };
 constexpr size_t GT_SHARED_BYTES = (sizeof(GtShared) + 15) / 16 * 16;
@@ -327,10 +338,10 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
 // A thread keeps its candidate (and the six map coefficients) for the whole pass.
 template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int w, int cols, int rows, int off_x, int off_y, int crank, int csize)
+                                           int w, int cols, int rows, int off_x, int off_y, int crank, int csize, int pb)
 {
   const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
-  if (g >= groups || !sh.valid[c]) return;
+  if (g >= groups || !sh.valid[pb][c]) return;
   const int tiles_x = cols / 4, ntiles = tiles_x * (rows / 4);
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
@@ -340,17 +351,17 @@ __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const
     const int tx = (tile % tiles_x) * 4, ty = (tile / tiles_x) * 4;
     acc += eval_tile4<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, s_org, wc, cols);
   }
-  atomicAdd(&sh.dist[c], acc);
+  atomicAdd(&sh.dist[pb][c], acc);
 }
 
 template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const uint32_t* s_win,
-                                           int w, int cols, int rows, int off_x, int off_y, int crank, int csize)
+                                           int w, int cols, int rows, int off_x, int off_y, int crank, int csize, int pb)
 {
   const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
   const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = blockDim.x / (2 * GT_CANDS);
   // lanes of a pair always agree on (c, g), so the shuffles inside eval_half_tile8 see both lanes
-  if (g >= groups || !sh.valid[c]) return;
+  if (g >= groups || !sh.valid[pb][c]) return;
   const int tiles_x = cols / 8, ntiles = tiles_x * (rows / 8);
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
@@ -360,20 +371,20 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
     const int tx = (tile % tiles_x) * 8, ty = (tile / tiles_x) * 8;
     acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, wc, cols);
   }
-  if (!HAD || half == 0) atomicAdd(&sh.dist[c], acc);   // HAD: both lanes hold the tile sums, count once
+  if (!HAD || half == 0) atomicAdd(&sh.dist[pb][c], acc);   // HAD: both lanes hold the tile sums, count once
 }
 
 template <int WS>
 __device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const uint32_t* s_win, int w,
                                           int cols, int rows, int off_x, int off_y, int tile_n, int use_had,
-                                          int crank = 0, int csize = 1)
+                                          int crank = 0, int csize = 1, int pb = 0)
 {
   if (tile_n == 8) {
-    if (use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
-    else         run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
+    if (use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
+    else         run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
   } else {
-    if (use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
-    else         run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize);
+    if (use_had) run_tasks4<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
+    else         run_tasks4<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
   }
 }
 
@@ -434,11 +445,20 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   if (!org_staged)
     for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
       s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
-  if (threadIdx.x == 0) {
-    for (int k = 0; k < 8; k++) sh.best_corner[k] = 0;
-    sh.dist_best = job.threshold;                               // :4769
-    sh.best_ss_x = 0; sh.best_ss_y = 0; sh.best_index = -1; sh.n_cand = 0;
+
+  // Search state is replicated per head warp (threads 0..63 = two warps): both warps reduce all 56 candidate
+  // costs of a pass and take the same decision, so a pass needs two CTA barriers (table ready, tiles done) and
+  // no serial section.  Thread c < 56 also owns candidate c of the per-pass table.
+  const bool head = threadIdx.x < 64;
+  const int lane = threadIdx.x & 31;
+  const int c_own = threadIdx.x;                                // table entry built by this thread (if < 56)
+  GtShared::State& st = sh.st[(threadIdx.x >> 5) & 1];
+  if (head && lane == 0) {
+    st.bc = make_int4(0, 0, 0, 0);
+    st.dist_best = job.threshold;                               // :4769
+    st.best_ss_x = 0; st.best_ss_y = 0; st.best_index = -1; st.n_cand = 0;
   }
+  int pb = 0;                                                   // parity of the double-buffered arrays
 
   const int n_start = 1 + job.num_pred;
   for (int b = 0; b < n_start; b++) {                           // :5106-5110
@@ -467,25 +487,27 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
       s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
     }
     const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);        // :5345
+    HOP_STAMP(g_trace_k2, 8 + b * 16);   // window loads of start b issued
+    // first pass of a start vector: the centres are the initial rectangle (:5183-5203)
+    if (head && lane == 0) st.cc = make_int4(0, cols * G - 1, ((rows * G - 1) << 16) | (cols * G - 1), (rows * G - 1) << 16);
+    if (head) __syncwarp();
 
     int pass = 0;
     for (int j0 = nss_window; j0 > 1 && pass < 6; j0 /= 2, pass++) {   // :5181
       const int s = j0 / 2;
-      __syncthreads();
-      if (threadIdx.x < GT_CANDS) {
-        const int c = threadIdx.x;
+      pb ^= 1;
+      if (c_own < GT_CANDS) {
+        const int c = c_own;
         int cx[4], cy[4];
-        if (pass == 0) {                                        // :5183-5203
-          cx[0] = 0; cy[0] = 0; cx[1] = cols * G - 1; cy[1] = 0;
-          cx[2] = cols * G - 1; cy[2] = rows * G - 1; cx[3] = 0; cy[3] = rows * G - 1;
-        } else {                                                // :5204-5214
-#pragma unroll
-          for (int k = 0; k < 4; k++) { cx[k] = sh.centre[2 * k]; cy[k] = sh.centre[2 * k + 1]; }
-        }
+        const int4 cc = st.cc;
+        const int ccw[4] = {cc.x, cc.y, cc.z, cc.w};
+        const int2 offw = __ldg(reinterpret_cast<const int2*>(d_gt_offsets) + c);
+        const double Wd = __dsub_rn((double)(cols * G), 1.0), Hd = __dsub_rn((double)(rows * G), 1.0);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          cx[k] += s * c_gt_offsets[c][2 * k];
-          cy[k] += s * c_gt_offsets[c][2 * k + 1];
+          const int w2 = k < 2 ? offw.x : offw.y;
+          cx[k] = (int)(int16_t)(ccw[k] & 0xffff) + s * (int)(int8_t)(w2 >> (16 * (k & 1)));
+          cy[k] = (ccw[k] >> 16) + s * (int)(int8_t)(w2 >> (16 * (k & 1) + 8));
         }
         // calcParamProjective, TComPrediction.cpp:807-832.  The affine test "h[2] == 0.0 && h[5] == 0.0"
         // (:5323) is decided exactly in integers: the numerators of h[2], h[5] are products of small
@@ -493,12 +515,11 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
         // gives 0/0 = NaN, which fails the reference's comparison.  For an accepted candidate
         // h[2] = h[5] = +-0, so h[0] = fl((x1-x0)/W) + (+-0) = fl((x1-x0)/W) etc. -- same values, no
         // division chain through den.
-        const double Wd = __dsub_rn((double)(cols * G), 1.0), Hd = __dsub_rn((double)(rows * G), 1.0);
         const int idx3 = cx[0] - cx[1] + cx[2] - cx[3], idy3 = cy[0] - cy[1] + cy[2] - cy[3];
         const int iden = (cx[1] - cx[2]) * (cy[3] - cy[2]) - (cx[3] - cx[2]) * (cy[1] - cy[2]);
         const int ok = (idx3 == 0 && idy3 == 0 && iden != 0) ? 1 : 0;
-        sh.valid[c] = ok;
-        sh.dist[c] = 0;
+        sh.valid[pb][c] = ok;
+        sh.dist[pb][c] = 0;
         if (ok) {
           sh.h0[c] = __ddiv_rn((double)(cx[1] - cx[0]), Wd);
           sh.h3[c] = __ddiv_rn((double)(cx[3] - cx[0]), Hd);
@@ -506,62 +527,67 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
           sh.h1[c] = __ddiv_rn((double)(cy[1] - cy[0]), Wd);
           sh.h4[c] = __ddiv_rn((double)(cy[3] - cy[0]), Hd);
           sh.h7[c] = (double)cy[0];
-          const uint32_t gb = gt_bits(cx[0] / last_step, cy[0] / last_step,
-                                      (cx[1] - cols * G + 1) / last_step, cy[1] / last_step,
-                                      (cx[2] - cols * G + 1) / last_step, (cy[2] - rows * G + 1) / last_step);
-          sh.add_cost[c] = mv_add + bits_cost(job.cost, gb);    // :5345-5358
+          int g0x = cx[0], g0y = cy[0], g1x = cx[1] - cols * G + 1, g1y = cy[1];
+          int g2x = cx[2] - cols * G + 1, g2y = cy[2] - rows * G + 1;
+          if (last_step != 1) {                                 // only PUs beyond 64x64 have a coarser last step
+            g0x /= last_step; g0y /= last_step; g1x /= last_step; g1y /= last_step; g2x /= last_step; g2y /= last_step;
+          }
+          sh.add_cost[pb][c] = mv_add + bits_cost(job.cost, gt_bits(g0x, g0y, g1x, g1y, g2x, g2y));   // :5345-5358
 #pragma unroll
-          for (int k = 0; k < 4; k++) { sh.corner[c][2 * k] = (int16_t)cx[k]; sh.corner[c][2 * k + 1] = (int16_t)cy[k]; }
+          for (int k = 0; k < 4; k++) { sh.corner[pb][c][2 * k] = (int16_t)cx[k]; sh.corner[pb][c][2 * k + 1] = (int16_t)cy[k]; }
         }
       }
       __syncthreads();
-      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize);
+      HOP_STAMP(g_trace_k2, 9 + b * 16 + 2 * pass);    // candidate table of the pass built
+      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb);
       if (CL) cg::this_cluster().sync(); else __syncthreads();
-      if (threadIdx.x < 64) {
+      HOP_STAMP(g_trace_k2, 10 + b * 16 + 2 * pass);   // tiles of the pass evaluated
+      if (head) {
         // ordered argmin with the carried threshold: the serial loop keeps the FIRST strict minimum in
         // loop order (:5361) == the minimum of (cost, loop index) over the pass, accepted iff it beats
-        // the running best
-        const int c = threadIdx.x;
-        const bool ok = c < GT_CANDS && sh.valid[c];
-        uint32_t dsum = 0;
-        if (ok) {
-          if (CL) {
-            cg::cluster_group cl = cg::this_cluster();
-            for (int r = 0; r < csize; r++) dsum += *cl.map_shared_rank(&sh.dist[c], r);   // tile sums of all CTAs
-          } else {
-            dsum = sh.dist[c];
+        // the running best.  Lane l looks at candidates l and l + 32.
+        unsigned long long key = ~0ull;
+        unsigned n_ok = 0;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int c = lane + 32 * hh;
+          if (c < GT_CANDS && sh.valid[pb][c]) {
+            uint32_t dsum = 0;
+            if (CL) {
+              cg::cluster_group cl = cg::this_cluster();
+              for (int r = 0; r < csize; r++) dsum += *cl.map_shared_rank(&sh.dist[pb][c], r);   // tile sums of all CTAs
+            } else {
+              dsum = sh.dist[pb][c];
+            }
+            const unsigned long long k2 = ((unsigned long long)((dsum >> dist_shift) + sh.add_cost[pb][c]) << 8) | (unsigned)c;
+            key = k2 < key ? k2 : key;
+            n_ok++;
           }
         }
-        unsigned long long key = ok ? ((unsigned long long)((dsum >> dist_shift) + sh.add_cost[c]) << 8) | (unsigned)c
-                                    : ~0ull;
-        const unsigned n_ok = __popc(__ballot_sync(0xffffffffu, ok));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
           key = other < key ? other : key;
+          n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
         }
-        if ((threadIdx.x & 31) == 0) { sh.red_key[threadIdx.x >> 5] = key; sh.red_cnt[threadIdx.x >> 5] = n_ok; }
-      }
-      // cluster: nobody may zero its partial sums (next set-up) before every CTA has gathered them
-      if (CL) cg::this_cluster().sync(); else __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned long long key = sh.red_key[0] < sh.red_key[1] ? sh.red_key[0] : sh.red_key[1];
-        sh.n_cand += sh.red_cnt[0] + sh.red_cnt[1];
-        const int best_c = (key != ~0ull && (uint32_t)(key >> 8) < sh.dist_best) ? (int)(key & 0xff) : -1;
-        if (best_c >= 0) {                                      // :5363-5383
-          sh.dist_best = (uint32_t)(key >> 8);
-          for (int k = 0; k < 8; k++) { sh.best_corner[k] = sh.corner[best_c][k]; sh.centre[k] = sh.corner[best_c][k]; }
-          sh.best_ss_x = Hor; sh.best_ss_y = Ver;
-          sh.best_index = (b * 8 + pass) * 64 + best_c;
-        } else if (pass == 0) {
-          // first pass of a start vector resets the best centres to the initial rectangle (:5183-5203)
-          sh.centre[0] = 0; sh.centre[1] = 0; sh.centre[2] = cols * G - 1; sh.centre[3] = 0;
-          sh.centre[4] = cols * G - 1; sh.centre[5] = rows * G - 1; sh.centre[6] = 0; sh.centre[7] = rows * G - 1;
+        __syncwarp();                       // every lane has read st.cc for the table of this pass
+        if (lane == 0) {
+          st.n_cand += n_ok;
+          if (key != ~0ull && (uint32_t)(key >> 8) < st.dist_best) {   // :5363-5383
+            const int best_c = (int)(key & 0xff);
+            st.dist_best = (uint32_t)(key >> 8);
+            const int4 cr = *reinterpret_cast<const int4*>(sh.corner[pb][best_c]);   // 8 x int16
+            st.cc = cr; st.bc = cr;
+            st.best_ss_x = Hor; st.best_ss_y = Ver;
+            st.best_index = (b * 8 + pass) * 64 + best_c;
+          }
         }
+        __syncwarp();
       }
+      // cluster: the partial sums of this pass are zeroed again two passes later (other parity), after the
+      // next cluster barrier -- no CTA can still be gathering them
     }
   }
-  __syncthreads();
   if (threadIdx.x == 0 && crank == 0) {
     HopGtResult r;
     r.gt_flag = 0;
@@ -569,23 +595,26 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
     r.cost = job.threshold;
     r.mv_int.hor = 0; r.mv_int.ver = 0;
     r.best_index = -1;
-    r.n_candidates = sh.n_cand;
-    int any = 0;
-    for (int k = 0; k < 8; k++) any |= sh.best_corner[k];
+    r.n_candidates = st.n_cand;
+    const int4 bc = st.bc;
+    const int bcw[4] = {bc.x, bc.y, bc.z, bc.w};
+    int bcx[4], bcy[4];
+    for (int k = 0; k < 4; k++) { bcx[k] = (int)(int16_t)(bcw[k] & 0xffff); bcy[k] = bcw[k] >> 16; }
+    const int any = bc.x | bc.y | bc.z | bc.w;
     if (any) {                                                  // :5436-5459
-      const int* bc = sh.best_corner;
       r.gt_flag = 1;
-      r.gt[0].hor = (int16_t)(bc[0] / last_step);                  r.gt[0].ver = (int16_t)(bc[1] / last_step);
-      r.gt[1].hor = (int16_t)((bc[2] - cols * G + 1) / last_step); r.gt[1].ver = (int16_t)(bc[3] / last_step);
-      r.gt[2].hor = (int16_t)((bc[4] - cols * G + 1) / last_step); r.gt[2].ver = (int16_t)((bc[5] - rows * G + 1) / last_step);
-      r.gt[3].hor = (int16_t)(bc[6] / last_step);                  r.gt[3].ver = (int16_t)((bc[7] - rows * G + 1) / last_step);
-      r.cost = sh.dist_best;
-      r.mv_int.hor = (int16_t)(sh.best_ss_x >> 2);
-      r.mv_int.ver = (int16_t)(sh.best_ss_y >> 2);
-      r.best_index = sh.best_index;
+      r.gt[0].hor = (int16_t)(bcx[0] / last_step);                  r.gt[0].ver = (int16_t)(bcy[0] / last_step);
+      r.gt[1].hor = (int16_t)((bcx[1] - cols * G + 1) / last_step); r.gt[1].ver = (int16_t)(bcy[1] / last_step);
+      r.gt[2].hor = (int16_t)((bcx[2] - cols * G + 1) / last_step); r.gt[2].ver = (int16_t)((bcy[2] - rows * G + 1) / last_step);
+      r.gt[3].hor = (int16_t)(bcx[3] / last_step);                  r.gt[3].ver = (int16_t)((bcy[3] - rows * G + 1) / last_step);
+      r.cost = st.dist_best;
+      r.mv_int.hor = (int16_t)(st.best_ss_x >> 2);
+      r.mv_int.ver = (int16_t)(st.best_ss_y >> 2);
+      r.best_index = st.best_index;
     }
     *out = r;
   }
+  if (CL) cg::this_cluster().sync();   // no CTA may leave while another still reads its partial sums
 }
 
 template <int WS, int CFG>
@@ -711,21 +740,21 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
             sh.h4[c] = __ddiv_rn((double)(cy[3] - cy[0]), Hd);
             sh.h7[c] = (double)cy[0];
             const uint32_t gb = gt_bits(cx[0], cy[0], cx[1] - cols + 1, cy[1], cx[2] - cols + 1, cy[2] - rows + 1);
-            sh.add_cost[c] = mv_add + bits_cost(job.cost, gb);                                // :5035-5041
+            sh.add_cost[0][c] = mv_add + bits_cost(job.cost, gb);                                // :5035-5041
             s_flat[c] = sc.flat;
           }
         }
       }
-      sh.valid[c] = ok;
-      sh.dist[c] = 0;
+      sh.valid[0][c] = ok;
+      sh.dist[0][c] = 0;
     }
     __syncthreads();
     run_tasks<WS>(sh, s_org, s_win, w, cols, rows, 0, 0, tile_n, job.use_had);
     __syncthreads();
     if (threadIdx.x < 64) {
       const int c = threadIdx.x;
-      const bool ok = c < GT_CANDS && sh.valid[c];
-      unsigned long long key = ok ? ((unsigned long long)((sh.dist[c] >> dist_shift) + sh.add_cost[c]) << 32) | s_flat[c] : ~0ull;
+      const bool ok = c < GT_CANDS && sh.valid[0][c];
+      unsigned long long key = ok ? ((unsigned long long)((sh.dist[0][c] >> dist_shift) + sh.add_cost[0][c]) << 32) | s_flat[c] : ~0ull;
       const unsigned n_ok = __popc(__ballot_sync(0xffffffffu, ok));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -957,14 +986,15 @@ template <int WS, int CFG, bool CL>
 __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob* __restrict__ jobs,
                                                  const int16_t* __restrict__ org_buf, const int16_t* __restrict__ ref_buf,
                                                  const HopSearchResult* __restrict__ k1, HopMotionResult* __restrict__ out,
-                                                 unsigned* done_flag, unsigned seq, RefBounds rb)
+                                                 unsigned* done_flag, unsigned seq, RefBounds rb, const InlinePu& ipu)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  HOP_STAMP(g_trace_k2, 0);
   int crank = 0, csize = 1;
   if (CL) { cg::cluster_group cl = cg::this_cluster(); crank = (int)cl.block_rank(); csize = (int)cl.num_blocks(); }
   const int job_id = blockIdx.x / csize;
   if (job_id >= n_jobs) return;
-  const HopMotionJob mj = jobs[job_id];
+  const HopMotionJob mj = ipu.use ? ipu.job : jobs[job_id];
   const HopSearchJob& sj = mj.search;
   const HopSearchResult sr = k1[job_id];
   HopMotionResult* res = &out[job_id];
@@ -988,12 +1018,17 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
     FracShared& fs = *reinterpret_cast<FracShared*>(smem_raw);               // aliases GtShared, used before it
     int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
     const int16_t* org = org_buf + sj.org_off;
-    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
-      s_org[i] = org[(i / cols) * sj.org_stride + (i % cols)];
+    if (ipu.use == 2) {
+      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) s_org[i] = ipu.org[i];
+    } else {
+      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+        s_org[i] = org[(i / cols) * sj.org_stride + (i % cols)];
+    }
     unsigned char* scratch = reinterpret_cast<unsigned char*>(s_org + ((rows * cols + 3) & ~3));
     const int16_t* ref_pos = ref_buf + sj.ref_off + sr.mv.hor + (long long)sr.mv.ver * sj.ref_stride;
     const HopFracResult fr = frac_search_cta(fs, s_org, scratch, ref_pos, sj.ref_stride, cols, rows, sj.bit_depth,
                                              mj.use_had, sj.cost, sr.mv);
+    HOP_STAMP(g_trace_k2, 2);   // fractional refinement done
     if (threadIdx.x == 0 && crank == 0) { res->frac = fr; if (!mj.use_gt) res->gt.cost = fr.cost; }
     if (mj.use_gt) {
       HopGtJob gj;
@@ -1008,6 +1043,7 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
       gt_search_cta<WS, CL>(gj, org_buf, ref_buf, smem_raw, &res->gt, true, rb);
     }
   }
+  HOP_STAMP(g_trace_k2, 3);     // GT search done
   if (threadIdx.x == 0 && crank == 0 && done_flag) {
     __threadfence_system();
     *(volatile unsigned*)done_flag = seq;
@@ -1018,9 +1054,10 @@ template <int WS, int CFG>
 __global__ void __launch_bounds__(GtCfg<CFG>::T, GtCfg<CFG>::B)
 k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
               const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
-              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb)
+              HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb,
+              const __grid_constant__ InlinePu ipu)
 {
-  motion_tail_body<WS, CFG, false>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq, rb);
+  motion_tail_body<WS, CFG, false>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq, rb, ipu);
 }
 
 // cluster forms (single-call latency path for PUs with several Hadamard tiles): launched with a cluster
@@ -1029,9 +1066,10 @@ template <int WS>
 __global__ void __launch_bounds__(GtCfg<0>::T, 1)
 k_motion_tail_cl(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
                  const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
-                 HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb)
+                 HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb,
+              const __grid_constant__ InlinePu ipu)
 {
-  motion_tail_body<WS, 0, true>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq, rb);
+  motion_tail_body<WS, 0, true>(n_jobs, jobs, org_buf, ref_buf, k1, out, done_flag, seq, rb, ipu);
 }
 
 template <int WS>
@@ -1096,7 +1134,7 @@ static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
 template <int WS, int CFG>
 static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                    const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
-                                   cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb)
+                                   cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb, const InlinePu& ipu)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1115,21 +1153,24 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
   k_motion_tail<WS, CFG><<<n, threads, motion_smem_bytes(WS, max_cols, max_rows), stream>>>(
-      n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb);
+      n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
   return cudaGetLastError();
 }
 
 cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
-                               cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq)
+                               cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq,
+                               const InlinePu* inl)
 {
+  static const InlinePu no_inline = {};
+  const InlinePu& ipu = inl ? *inl : no_inline;
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case WS_A:  return motion_tail_cfg<WS_A, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case WS_B:  return motion_tail_cfg<WS_B, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    case WS_C:  return motion_tail_cfg<WS_C, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
-    default:  return motion_tail_cfg<WS_D, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
+    case WS_A:  return motion_tail_cfg<WS_A, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
+    case WS_B:  return motion_tail_cfg<WS_B, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
+    case WS_C:  return motion_tail_cfg<WS_C, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
+    default:  return motion_tail_cfg<WS_D, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
   }
 }
 
@@ -1151,7 +1192,8 @@ static cudaError_t gt_cluster_class(const HopGtJob* d_job, const int16_t* d_org,
 template <int WS>
 static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
                                         const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows, int csize,
-                                        int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb)
+                                        int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb,
+                                        const InlinePu& ipu)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -1161,7 +1203,7 @@ static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t
     attr_set = true;
   }
   return launch_cluster(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_bytes(WS, cols, rows), stream,
-                        1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb);
+                        1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
 }
 
 // Latency path: ONE PU, searched by a cluster of CTAs when it has at least two Hadamard tiles.
@@ -1183,17 +1225,20 @@ cudaError_t gt_single_launch(const HopGtJob* d_job, const int16_t* d_org, const 
 
 cudaError_t motion_single_launch(const HopMotionJob* d_job, const int16_t* d_org, const int16_t* d_ref,
                                  const HopSearchResult* d_k1, HopMotionResult* d_out, int cols, int rows,
-                                 cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq)
+                                 cudaStream_t stream, int* launches, RefBounds rb, unsigned* done_flag, unsigned seq,
+                                 const InlinePu* inl)
 {
+  static const InlinePu no_inline = {};
+  const InlinePu& ipu = inl ? *inl : no_inline;
   int csize, threads;
   cluster_geometry(cols, rows, &csize, &threads);
   if (csize < 2) return cudaErrorNotSupported;
   if (launches) (*launches)++;
   switch (gt_stride_class(cols + (cols < rows ? cols : rows))) {
-    case WS_A:  return motion_cluster_class<WS_A>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    case WS_B:  return motion_cluster_class<WS_B>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    case WS_C:  return motion_cluster_class<WS_C>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
-    default:  return motion_cluster_class<WS_D>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb);
+    case WS_A:  return motion_cluster_class<WS_A>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb, ipu);
+    case WS_B:  return motion_cluster_class<WS_B>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb, ipu);
+    case WS_C:  return motion_cluster_class<WS_C>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb, ipu);
+    default:  return motion_cluster_class<WS_D>(d_job, d_org, d_ref, d_k1, d_out, cols, rows, csize, threads, stream, done_flag, seq, rb, ipu);
   }
 }
 
