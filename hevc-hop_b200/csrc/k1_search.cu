@@ -237,6 +237,9 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
   __shared__ int s_unclean;
   __shared__ int16_t s_inl_org[INLINE_ORG_SAMPLES];
   HOP_STAMP(g_trace_k1, 0);
+  // lets a programmatic dependent (the tail of the fused single-call search) become resident right away; it
+  // still waits for this whole grid before it reads the result
+  asm volatile("griddepcontrol.launch_dependents;");
   const int job_id = blockIdx.x;
   // job_stride: bytes between jobs (HopSearchJob arrays, or the leading member of HopMotionJob arrays)
   const HopSearchJob job = ipu.use ? ipu.job.search

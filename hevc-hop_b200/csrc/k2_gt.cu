@@ -81,10 +81,22 @@ struct GtShared {
     int32_t  best_ss_x, best_ss_y, best_index;
     uint32_t n_cand;
   } st[2];
+  int2     offs[GT_CANDS];                             // the 56 corner-offset patterns (8 bytes each)
   unsigned long long red_key[2];                       // sweep kernel: cross-warp argmin
   uint32_t red_cnt[2];
 };
 constexpr size_t GT_SHARED_BYTES = (sizeof(GtShared) + 15) / 16 * 16;
+
+// Quotient tables of calcParamProjective: h0 = fl(n / (W-1)) and h3 = fl(n / (H-1)) (W, H on the 2x grid) for every
+// numerator a corner set can produce -- corners stay within +-nss of the initial rectangle, so
+// n in [-2 nss, W - 1 + 2 nss].  Filled once per PU with the same IEEE division the reference executes, so that
+// the per-pass candidate set-up is four table reads instead of four divisions (0.45 us per pass on the latency path).
+__host__ __device__ inline int gt_div_entries(int dim2x, int nss) { return dim2x + 4 * nss + 1; }
+__host__ __device__ inline size_t gt_div_bytes(int cols, int rows)
+{
+  const int nss = ((rows < cols ? rows : cols) >> 1) * 2;
+  return (sizeof(double) * (size_t)(gt_div_entries(2 * cols, nss) + gt_div_entries(2 * rows, nss)) + 15) & ~(size_t)15;
+}
 
 // ---- in-register Walsh-Hadamard tiles ---------------------------------------------------------
 template <int N>
@@ -340,9 +352,12 @@ template <int WS, bool HAD>
 __device__ __forceinline__ void run_tasks4(GtShared& sh, const int* s_org, const uint32_t* s_win,
                                            int w, int cols, int rows, int off_x, int off_y, int crank, int csize, int pb)
 {
-  const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = blockDim.x / GT_CANDS;
-  if (g >= groups || !sh.valid[pb][c]) return;
   const int tiles_x = cols / 4, ntiles = tiles_x * (rows / 4);
+  // tile groups of this CTA: as many as it has lanes for, but no more than its share of the tiles (a cluster CTA
+  // may be launched wider than its tiles need -- the extra warps serve the staging and the fractional stage)
+  const int per_cta = (ntiles + csize - 1) / csize, avail = blockDim.x / GT_CANDS;
+  const int c = threadIdx.x % GT_CANDS, g = threadIdx.x / GT_CANDS, groups = avail < per_cta ? avail : per_cta;
+  if (g >= groups || !sh.valid[pb][c]) return;
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
   const WarpCtx wc(s_win, w, cols, rows, off_x, off_y);
@@ -359,10 +374,11 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
                                            int w, int cols, int rows, int off_x, int off_y, int crank, int csize, int pb)
 {
   const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
-  const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = blockDim.x / (2 * GT_CANDS);
+  const int tiles_x = cols / 8, ntiles = tiles_x * (rows / 8);
+  const int per_cta = (ntiles + csize - 1) / csize, avail = blockDim.x / (2 * GT_CANDS);
+  const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = avail < per_cta ? avail : per_cta;
   // lanes of a pair always agree on (c, g), so the shuffles inside eval_half_tile8 see both lanes
   if (g >= groups || !sh.valid[pb][c]) return;
-  const int tiles_x = cols / 8, ntiles = tiles_x * (rows / 8);
   const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
   const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
   const WarpCtx wc(s_win, w, cols, rows, off_x, off_y);
@@ -433,7 +449,9 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   int last_step = nss_window >> 6;                              // :4763 (IT_MAX_NSS_Iteration 6)
   if (last_step == 0) last_step = 1;
   const int win_w = cols + 2 * w, win_h = rows + 2 * w;
-  int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
+  double* s_div_w = reinterpret_cast<double*>(smem_raw + GT_SHARED_BYTES);
+  double* s_div_h = s_div_w + gt_div_entries(cols * G, nss_window);
+  int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES + gt_div_bytes(cols, rows));
   uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + ((rows * cols + 3) & ~3));
   if (win_w > WS) return;   // host picked the wrong stride class (cannot happen through the ABI)
   const int16_t* org = org_buf + job.org_off;
@@ -445,6 +463,14 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   if (!org_staged)
     for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
       s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
+  {
+    const double Wd = __dsub_rn((double)(cols * G), 1.0), Hd = __dsub_rn((double)(rows * G), 1.0);   // :811-812
+    const int nw = gt_div_entries(cols * G, nss_window), nh = gt_div_entries(rows * G, nss_window);
+    for (int i = threadIdx.x; i < nw + nh; i += blockDim.x) {
+      if (i < nw) s_div_w[i] = __ddiv_rn((double)(i - 2 * nss_window), Wd);
+      else        s_div_h[i - nw] = __ddiv_rn((double)(i - nw - 2 * nss_window), Hd);
+    }
+  }
 
   // Search state is replicated per head warp (threads 0..63 = two warps): both warps reduce all 56 candidate
   // costs of a pass and take the same decision, so a pass needs two CTA barriers (table ready, tiles done) and
@@ -453,6 +479,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   const int lane = threadIdx.x & 31;
   const int c_own = threadIdx.x;                                // table entry built by this thread (if < 56)
   GtShared::State& st = sh.st[(threadIdx.x >> 5) & 1];
+  if (c_own < GT_CANDS) sh.offs[c_own] = __ldg(reinterpret_cast<const int2*>(d_gt_offsets) + c_own);   // read back by the same thread
   if (head && lane == 0) {
     st.bc = make_int4(0, 0, 0, 0);
     st.dist_best = job.threshold;                               // :4769
@@ -501,8 +528,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
         int cx[4], cy[4];
         const int4 cc = st.cc;
         const int ccw[4] = {cc.x, cc.y, cc.z, cc.w};
-        const int2 offw = __ldg(reinterpret_cast<const int2*>(d_gt_offsets) + c);
-        const double Wd = __dsub_rn((double)(cols * G), 1.0), Hd = __dsub_rn((double)(rows * G), 1.0);
+        const int2 offw = sh.offs[c];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const int w2 = k < 2 ? offw.x : offw.y;
@@ -518,14 +544,16 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
         const int idx3 = cx[0] - cx[1] + cx[2] - cx[3], idy3 = cy[0] - cy[1] + cy[2] - cy[3];
         const int iden = (cx[1] - cx[2]) * (cy[3] - cy[2]) - (cx[3] - cx[2]) * (cy[1] - cy[2]);
         const int ok = (idx3 == 0 && idy3 == 0 && iden != 0) ? 1 : 0;
+        if (b == 0 && pass == 1) HOP_STAMP(g_trace_k2, 57);
         sh.valid[pb][c] = ok;
         sh.dist[pb][c] = 0;
         if (ok) {
-          sh.h0[c] = __ddiv_rn((double)(cx[1] - cx[0]), Wd);
-          sh.h3[c] = __ddiv_rn((double)(cx[3] - cx[0]), Hd);
+          const int nb = 2 * nss_window;                        // table index of numerator 0
+          sh.h0[c] = s_div_w[cx[1] - cx[0] + nb];               // fl((x1 - x0) / (W - 1))
+          sh.h3[c] = s_div_h[cx[3] - cx[0] + nb];               // fl((x3 - x0) / (H - 1))
           sh.h6[c] = (double)cx[0];
-          sh.h1[c] = __ddiv_rn((double)(cy[1] - cy[0]), Wd);
-          sh.h4[c] = __ddiv_rn((double)(cy[3] - cy[0]), Hd);
+          sh.h1[c] = s_div_w[cy[1] - cy[0] + nb];
+          sh.h4[c] = s_div_h[cy[3] - cy[0] + nb];
           sh.h7[c] = (double)cy[0];
           int g0x = cx[0], g0y = cy[0], g1x = cx[1] - cols * G + 1, g1y = cy[1];
           int g2x = cx[2] - cols * G + 1, g2y = cy[2] - rows * G + 1;
@@ -536,6 +564,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
 #pragma unroll
           for (int k = 0; k < 4; k++) { sh.corner[pb][c][2 * k] = (int16_t)cx[k]; sh.corner[pb][c][2 * k + 1] = (int16_t)cy[k]; }
         }
+        if (b == 0 && pass == 1) HOP_STAMP(g_trace_k2, 58);
       }
       __syncthreads();
       HOP_STAMP(g_trace_k2, 9 + b * 16 + 2 * pass);    // candidate table of the pass built
@@ -555,7 +584,9 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
             uint32_t dsum = 0;
             if (CL) {
               cg::cluster_group cl = cg::this_cluster();
-              for (int r = 0; r < csize; r++) dsum += *cl.map_shared_rank(&sh.dist[pb][c], r);   // tile sums of all CTAs
+              // tile sums of all CTAs: independent remote loads (one DSMEM latency, not csize of them)
+#pragma unroll
+              for (int r = 0; r < 8; r++) if (r < csize) dsum += *cl.map_shared_rank(&sh.dist[pb][c], r);
             } else {
               dsum = sh.dist[pb][c];
             }
@@ -564,12 +595,13 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
             n_ok++;
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-          key = other < key ? other : key;
-          n_ok += __shfl_xor_sync(0xffffffffu, n_ok, o);
-        }
+        // warp minimum of the 64-bit key with two redux operations: cost first, then the loop index among
+        // the lanes that hold that cost
+        const unsigned kcost = (unsigned)(key >> 8) | (key == ~0ull ? 0xffffffffu : 0u);
+        const unsigned mcost = __reduce_min_sync(0xffffffffu, kcost);
+        const unsigned mc = __reduce_min_sync(0xffffffffu, (key != ~0ull && kcost == mcost) ? (unsigned)(key & 0xff) : 0xffffffffu);
+        n_ok = __reduce_add_sync(0xffffffffu, n_ok);
+        key = mc == 0xffffffffu ? ~0ull : ((unsigned long long)mcost << 8) | mc;
         __syncwarp();                       // every lane has read st.cc for the table of this pass
         if (lane == 0) {
           st.n_cand += n_ok;
@@ -584,6 +616,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
         }
         __syncwarp();
       }
+      if (b == 0 && pass == 0) HOP_STAMP(g_trace_k2, 56);
       // cluster: the partial sums of this pass are zeroed again two passes later (other parity), after the
       // next cluster barrier -- no CTA can still be gathering them
     }
@@ -823,7 +856,7 @@ static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
 {
   const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
   const size_t org = ((size_t)max_cols * max_rows + 3) & ~(size_t)3;
-  return GT_SHARED_BYTES + sizeof(int) * org + sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
+  return GT_SHARED_BYTES + gt_div_bytes(max_cols, max_rows) + sizeof(int) * org + sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
 }
 
 template <int WS, int CFG>
@@ -863,7 +896,8 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
   // 2 CTAs x 448 threads for the 64x64 class (shared memory allows only two CTAs there)
   static int env_cfg = -2;
   if (env_cfg == -2) { const char* e = getenv("HOP_K2_CFG"); env_cfg = e ? atoi(e) : -1; }
-  const int cfg = env_cfg >= 0 ? env_cfg : (WS == WS_D ? 4 : 5);
+  // a single PU (latency path) takes the widest CTA: all of its tiles at once
+  const int cfg = env_cfg >= 0 ? env_cfg : ((WS == WS_D || n == 1) ? 4 : 5);
   switch (cfg) {
     case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
@@ -996,6 +1030,20 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
   if (job_id >= n_jobs) return;
   const HopMotionJob mj = ipu.use ? ipu.job : jobs[job_id];
   const HopSearchJob& sj = mj.search;
+  // the original block does not depend on k1_search: stage it before waiting for that grid (the single-call
+  // path launches this kernel with programmatic stream serialisation, so it is resident while K1 still runs)
+  {
+    int* s_org0 = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES + gt_div_bytes(sj.cols, sj.rows));
+    const int16_t* org0 = org_buf + sj.org_off;
+    if (ipu.use == 2) {
+      for (int i = threadIdx.x; i < sj.rows * sj.cols; i += blockDim.x) s_org0[i] = ipu.org[i];
+    } else {
+      for (int i = threadIdx.x; i < sj.rows * sj.cols; i += blockDim.x)
+        s_org0[i] = org0[(i / sj.cols) * sj.org_stride + (i % sj.cols)];
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
+  HOP_STAMP(g_trace_k2, 1);
   const HopSearchResult sr = k1[job_id];
   HopMotionResult* res = &out[job_id];
   const bool go = sr.found == 1 && !(sr.mv.hor == 0 && sr.mv.ver == 0);      // :4603-4611
@@ -1016,14 +1064,7 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
   if (go) {
     const int cols = sj.cols, rows = sj.rows;
     FracShared& fs = *reinterpret_cast<FracShared*>(smem_raw);               // aliases GtShared, used before it
-    int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES);
-    const int16_t* org = org_buf + sj.org_off;
-    if (ipu.use == 2) {
-      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) s_org[i] = ipu.org[i];
-    } else {
-      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
-        s_org[i] = org[(i / cols) * sj.org_stride + (i % cols)];
-    }
+    int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES + gt_div_bytes(cols, rows));
     unsigned char* scratch = reinterpret_cast<unsigned char*>(s_org + ((rows * cols + 3) & ~3));
     const int16_t* ref_pos = ref_buf + sj.ref_off + sr.mv.hor + (long long)sr.mv.ver * sj.ref_stride;
     const HopFracResult fr = frac_search_cta(fs, s_org, scratch, ref_pos, sj.ref_stride, cols, rows, sj.bit_depth,
@@ -1063,7 +1104,7 @@ k_motion_tail(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* 
 // cluster forms (single-call latency path for PUs with several Hadamard tiles): launched with a cluster
 // dimension of 2, 4 or 8 CTAs per PU
 template <int WS>
-__global__ void __launch_bounds__(GtCfg<0>::T, 1)
+__global__ void __launch_bounds__(GtCfg<4>::T, 1)
 k_motion_tail_cl(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
                  const int16_t* __restrict__ ref_buf, const HopSearchResult* __restrict__ k1,
                  HopMotionResult* __restrict__ out, unsigned* done_flag, unsigned seq, RefBounds rb,
@@ -1073,7 +1114,7 @@ k_motion_tail_cl(int n_jobs, const HopMotionJob* __restrict__ jobs, const int16_
 }
 
 template <int WS>
-__global__ void __launch_bounds__(GtCfg<0>::T, 1)
+__global__ void __launch_bounds__(GtCfg<4>::T, 1)
 k2_gt_search_cl(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
                 const int16_t* __restrict__ ref_buf, HopGtResult* __restrict__ out, unsigned* done_flag, unsigned seq,
                 RefBounds rb)
@@ -1093,33 +1134,56 @@ k2_gt_search_cl(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __
 // cluster size and CTA size for a PU shape on the latency path
 static void cluster_geometry(int cols, int rows, int* csize, int* threads)
 {
+  // Measured on the single-call path (profiles/r01_latency_trace.txt): a cluster costs ~0.9 us per pass (cluster
+  // barrier + remote gathers), one 8x8 tile of all 56 candidates ~0.5 us of an SM's conversion (XU) pipe.  So: one
+  // CTA per 8x8 tile (or per four 4x4 tiles) up to the portable cluster size of 8, and no cluster for a PU that
+  // is a single 8x8 tile's worth of work (8x8, 8x4, 4x8, 16x4, 4x16).
+  constexpr int T = GtCfg<4>::T;
   const int tile = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
   const int ntiles = (cols / tile) * (rows / tile);
-  int cs = ntiles >= 8 ? 8 : ntiles >= 4 ? 4 : ntiles >= 2 ? 2 : 1;
+  const int work = tile == 8 ? ntiles : ntiles / 4;       // in 8x8 tiles
+  const int cs = work >= 8 ? 8 : work >= 4 ? 4 : work >= 2 ? 2 : 1;
   const int per_cta = (ntiles + cs - 1) / cs;
-  const int max_groups = GtCfg<0>::T / per_group;
+  const int max_groups = T / per_group;
   int groups = per_cta < max_groups ? per_cta : max_groups;
   for (int g = groups - 1; g >= 1; g--)
     if ((per_cta + g - 1) / g <= (per_cta + groups - 1) / groups) groups = g;
   int t = per_group * groups;
   if (t < 64) t = 64;
+  if (cs > 1 && t < 448) t = 448;   // every CTA of a cluster runs the whole fractional stage: give it the warps
   *csize = cs; *threads = t;
 }
 
+// csize > 1: thread-block cluster; pdl: programmatic dependent launch -- the grid may become resident while the
+// preceding kernel of the stream still runs and waits for it at griddepcontrol.wait
 template <typename K, typename... Args>
-static cudaError_t launch_cluster(K kernel, int n, int csize, int threads, size_t smem, cudaStream_t stream, Args... args)
+static cudaError_t launch_ex(K kernel, int n, int csize, int threads, size_t smem, cudaStream_t stream, bool pdl, Args... args)
 {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * csize);
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (csize > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = csize; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+template <typename K, typename... Args>
+static cudaError_t launch_cluster(K kernel, int n, int csize, int threads, size_t smem, cudaStream_t stream, Args... args)
+{
+  return launch_ex(kernel, n, csize, threads, smem, stream, false, args...);
 }
 
 static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
@@ -1128,7 +1192,7 @@ static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
   const size_t org = ((size_t)max_cols * max_rows + 3) & ~(size_t)3;
   const size_t win = sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
   const size_t fr = frac_smem_bytes(max_cols, max_rows);
-  return GT_SHARED_BYTES + sizeof(int) * org + (win > fr ? win : fr);
+  return GT_SHARED_BYTES + gt_div_bytes(max_cols, max_rows) + sizeof(int) * org + (win > fr ? win : fr);
 }
 
 template <int WS, int CFG>
@@ -1152,9 +1216,8 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
-  k_motion_tail<WS, CFG><<<n, threads, motion_smem_bytes(WS, max_cols, max_rows), stream>>>(
-      n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
-  return cudaGetLastError();
+  return launch_ex(k_motion_tail<WS, CFG>, n, 1, threads, motion_smem_bytes(WS, max_cols, max_rows), stream, ipu.use != 0,
+                   n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
 }
 
 cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
@@ -1167,9 +1230,12 @@ cudaError_t motion_tail_launch(int n, const HopMotionJob* d_jobs, const int16_t*
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case WS_A:  return motion_tail_cfg<WS_A, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
-    case WS_B:  return motion_tail_cfg<WS_B, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
-    case WS_C:  return motion_tail_cfg<WS_C, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
+    case WS_A:  return n == 1 ? motion_tail_cfg<WS_A, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu)
+                              : motion_tail_cfg<WS_A, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
+    case WS_B:  return n == 1 ? motion_tail_cfg<WS_B, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu)
+                              : motion_tail_cfg<WS_B, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
+    case WS_C:  return n == 1 ? motion_tail_cfg<WS_C, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu)
+                              : motion_tail_cfg<WS_C, 5>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
     default:  return motion_tail_cfg<WS_D, 4>(n, d_jobs, d_org, d_ref, d_k1, d_out, max_cols, max_rows, stream, done_flag, seq, rb, ipu);
   }
 }
@@ -1202,8 +1268,8 @@ static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_cluster(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_bytes(WS, cols, rows), stream,
-                        1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
+  return launch_ex(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_bytes(WS, cols, rows), stream, ipu.use != 0,
+                   1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
 }
 
 // Latency path: ONE PU, searched by a cluster of CTAs when it has at least two Hadamard tiles.

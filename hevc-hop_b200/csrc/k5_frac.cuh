@@ -27,20 +27,22 @@ struct FracShared {
   uint32_t best_cost;
 };
 
-constexpr int FRAC_CHUNK = 3;   // positions handled per shared-memory round (9 positions = 3 rounds)
+// positions handled per shared-memory round: all 9 at once for PUs up to 1024 samples (one round, two barriers),
+// 3 rounds of 3 beyond that (keeps the scratch of a 64x64 PU at 24 KB)
+__host__ __device__ inline int frac_chunk(int cols, int rows) { return cols * rows <= 1024 ? 9 : 3; }
 
 __host__ __device__ inline size_t frac_smem_bytes(int cols, int rows)
 {
   // [source region (rows+8) x (cols+8) int16][3 horizontal intermediates (rows+8) x cols int16]
-  // [row-transformed differences of FRAC_CHUNK positions, rows x cols int16]
+  // [row-transformed differences of frac_chunk() positions, rows x cols int16]
   return (sizeof(int16_t) * ((size_t)(rows + 8) * (cols + 8) + 3 * (size_t)(rows + 8) * cols +
-                             (size_t)FRAC_CHUNK * rows * cols) + 15) & ~(size_t)15;
+                             (size_t)frac_chunk(cols, rows) * rows * cols) + 15) & ~(size_t)15;
 }
 
 // one refinement stage: positions base + step * refine[i] (quarter-pel units), i = 0..8.
 //   s_org : original block, int32, stride cols          s_src : staged source region
 //   s_tmp : 3 horizontal intermediates, plane index = refine x-component + 1
-//   s_rt  : row-transformed differences of FRAC_CHUNK positions
+//   s_rt  : row-transformed differences of frac_chunk() positions
 // Two phases per round so that even an 8x8 PU keeps ~70 threads busy: (A) one thread per tile ROW filters
 // its N pixels vertically, subtracts the original and runs the horizontal N-point butterflies; (B) one
 // thread per tile COLUMN runs the vertical butterflies; the N column sums of a tile meet by shuffles for
@@ -76,6 +78,7 @@ __device__ __forceinline__ void frac_stage(FracShared& fs, const int* __restrict
   __syncthreads();
   const int tiles_x = cols / N;
   const int max_val = (1 << bit_depth) - 1;
+  const int FRAC_CHUNK = frac_chunk(cols, rows);
   for (int i0 = 0; i0 < 9; i0 += FRAC_CHUNK) {
     // phase A: (position, row y, tile column tx) -> N pixels
     for (int t = threadIdx.x; t < FRAC_CHUNK * rows * tiles_x; t += blockDim.x) {

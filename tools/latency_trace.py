@@ -36,8 +36,13 @@ def main():
                    "k1 job+tables": k1[1] - k1[0], "k1 staging": k1[2] - k1[1], "k1 staircase": k1[3] - k1[2],
                    "k1 search": k1[4] - k1[3], "k1 reduce": k1[5] - k1[4], "k1 finalize (last slice)": k1[6] - k1[5],
                    "k1 total": k1[6] - k1[0], "gap k1 -> tail": k2[0] - k1[6],
-                   "tail org+frac": k2[2] - k2[0], "tail gt": k2[3] - k2[2], "tail total": k2[3] - k2[0],
+                   "tail prologue + wait for k1": k2[1] - k2[0], "k1 end -> tail released": k2[1] - k1[6],
+                   "tail frac": k2[2] - k2[1], "tail gt": k2[3] - k2[2], "tail total": k2[3] - k2[0],
                    "gpu span": k2[3] - k1[0]}
+            row["fine: barrier -> argmin done"] = k2[56] - k2[8 + 2]
+            row["fine: argmin done -> table math start"] = k2[57] - k2[56]
+            row["fine: table math + stores"] = k2[58] - k2[57]
+            row["fine: stores -> barrier passed"] = k2[8 + 3] - k2[58]
             for bb in range(3):
                 base = 8 + 16 * bb
                 if k2[base] >= k2[2]:
