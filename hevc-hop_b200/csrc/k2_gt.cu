@@ -390,11 +390,100 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
   if (!HAD || half == 0) atomicAdd(&sh.dist[pb][c], acc);   // HAD: both lanes hold the tile sums, count once
 }
 
+// ---- latency form: one lane per tile ROW ----------------------------------------------------------
+// A single PU (the in-encoder call) cannot fill the machine, so the length of the dependent chain decides: N
+// adjacent lanes share a tile, each warps one row of N pixels (a quarter of the chain of the half-tile form),
+// runs the horizontal butterflies in registers and meets the other rows through log2(N) shuffle stages; the
+// last stage is folded into the magnitude sum as above.  ~20 % more instructions per pixel than the register
+// tiles, which is why the batched (throughput) launches keep those.
+template <int WS, bool HAD, int N>
+__device__ __forceinline__ uint32_t eval_tile_row(double h0, double h3, double h6, double h1, double h4, double h7,
+                                                  int tx, int ty, int j, unsigned group_mask, const int* __restrict__ org,
+                                                  const WarpCtx& wc, int cols)
+{
+  const int off_x = wc.off_x, off_y = wc.off_y;
+  const int y = ty + j;
+  const double yd = small_int_to_double(off_y + y);
+  const double h3y = __dmul_rn(h3, yd), h4y = __dmul_rn(h4, yd);
+  int d[N];
+#pragma unroll
+  for (int k = 0; k < N; k += 4) {
+    const int4 a = *reinterpret_cast<const int4*>(org + y * cols + tx + k);
+    d[k] = a.x; d[k + 1] = a.y; d[k + 2] = a.z; d[k + 3] = a.w;
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const double xd = small_int_to_double(off_x + tx + k);
+    const double Fx = __dadd_rn(__dadd_rn(__dmul_rn(h0, xd), h3y), h6);    // (h0*x + h3*y) + h6, left to right
+    const double Fy = __dadd_rn(__dadd_rn(__dmul_rn(h1, xd), h4y), h7);
+    d[k] -= warp_sample<WS>(wc, Fx, Fy);
+  }
+  unsigned s = 0;
+  if (!HAD) {
+#pragma unroll
+    for (int k = 0; k < N; k++) s = __sad(d[k], 0, s);
+    return s;                                        // per-lane share of the tile SAD
+  }
+#pragma unroll
+  for (int len = 1; len < N; len <<= 1)              // horizontal N-point
+#pragma unroll
+    for (int i = 0; i < N; i += len << 1)
+#pragma unroll
+      for (int q = i; q < i + len; q++) { const int a = d[q], b = d[q + len]; d[q] = a + b; d[q + len] = a - b; }
+#pragma unroll
+  for (int m = 1; m < N / 2; m <<= 1)                // vertical stages across the lanes, all but the last
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const int recv = __shfl_xor_sync(group_mask, d[k], m);
+      d[k] = (j & m) ? recv - d[k] : d[k] + recv;
+    }
+#pragma unroll
+  for (int k = 0; k < N; k++) {                      // last stage: |a+b| + |a-b| == 2*max(|a|,|b|), seen from both lanes
+    const int recv = __shfl_xor_sync(group_mask, d[k], N / 2);
+    s += (unsigned)max(abs(d[k]), abs(recv));
+  }
+#pragma unroll
+  for (int m = 1; m < N; m <<= 1) s += __shfl_xor_sync(group_mask, s, m);   // sum over the N lanes == sum |T|
+  return N == 8 ? (s + 2) >> 2 : (s + 1) >> 1;       // xCalcHADs8x8 :1572 / xCalcHADs4x4 :1476
+}
+
+template <int WS, bool HAD, int N>
+__device__ __forceinline__ void run_tasks_rows(GtShared& sh, const int* s_org, const uint32_t* s_win,
+                                               int w, int cols, int rows, int off_x, int off_y, int crank, int csize, int pb)
+{
+  const int tiles_x = cols / N, ntiles = tiles_x * (rows / N);
+  const int per_cta = (ntiles + csize - 1) / csize, avail = blockDim.x / (N * GT_CANDS);
+  const int j = threadIdx.x & (N - 1), slot = threadIdx.x / N;
+  const int c = slot % GT_CANDS, g = slot / GT_CANDS, groups = avail < per_cta ? avail : per_cta;
+  // the N lanes of a tile agree on (c, g): they leave, loop and shuffle together
+  if (g >= groups || !sh.valid[pb][c]) return;
+  const unsigned group_mask = ((1u << N) - 1u) << (threadIdx.x & 31 & ~(N - 1));
+  const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
+  const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  const WarpCtx wc(s_win, w, cols, rows, off_x, off_y);
+  uint32_t acc = 0;
+  for (int tile = g + groups * crank; tile < ntiles; tile += groups * csize) {
+    const int tx = (tile % tiles_x) * N, ty = (tile / tiles_x) * N;
+    acc += eval_tile_row<WS, HAD, N>(h0, h3, h6, h1, h4, h7, tx, ty, j, group_mask, s_org, wc, cols);
+  }
+  if (!HAD || j == 0) atomicAdd(&sh.dist[pb][c], acc);   // HAD: every lane holds the tile sums, count once
+}
+
 template <int WS>
 __device__ __forceinline__ void run_tasks(GtShared& sh, const int* s_org, const uint32_t* s_win, int w,
                                           int cols, int rows, int off_x, int off_y, int tile_n, int use_had,
-                                          int crank = 0, int csize = 1, int pb = 0)
+                                          int crank = 0, int csize = 1, int pb = 0, bool fine = false)
 {
+  if (fine) {
+    if (tile_n == 8) {
+      if (use_had) run_tasks_rows<WS, true, 8>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
+      else         run_tasks_rows<WS, false, 8>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
+    } else {
+      if (use_had) run_tasks_rows<WS, true, 4>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
+      else         run_tasks_rows<WS, false, 4>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
+    }
+    return;
+  }
   if (tile_n == 8) {
     if (use_had) run_tasks8<WS, true>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
     else         run_tasks8<WS, false>(sh, s_org, s_win, w, cols, rows, off_x, off_y, crank, csize, pb);
@@ -475,6 +564,11 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   // Search state is replicated per head warp (threads 0..63 = two warps): both warps reduce all 56 candidate
   // costs of a pass and take the same decision, so a pass needs two CTA barriers (table ready, tiles done) and
   // no serial section.  Thread c < 56 also owns candidate c of the per-pass table.
+  // single PU in the grid (the in-encoder call): row-per-lane tiles when that takes a single trip, i.e. the CTA
+  // has 8 lanes for every (candidate, 8x8 tile) it owns -- measured 1.9 us per pass against 3.0 us for the
+  // half-tile form; with two trips, or with 4x4 tiles (1.25 us either way), the register tiles stay
+  const int my_tiles = ((cols / tile_n) * (rows / tile_n) + csize - 1) / csize;
+  const bool fine = (int)gridDim.x == csize && tile_n == 8 && my_tiles * 8 * GT_CANDS <= (int)blockDim.x;
   const bool head = threadIdx.x < 64;
   const int lane = threadIdx.x & 31;
   const int c_own = threadIdx.x;                                // table entry built by this thread (if < 56)
@@ -568,7 +662,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
       }
       __syncthreads();
       HOP_STAMP(g_trace_k2, 9 + b * 16 + 2 * pass);    // candidate table of the pass built
-      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb);
+      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb, fine);
       if (CL) cg::this_cluster().sync(); else __syncthreads();
       HOP_STAMP(g_trace_k2, 10 + b * 16 + 2 * pass);   // tiles of the pass evaluated
       if (head) {
@@ -882,6 +976,7 @@ static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
+  if (n == 1) threads = GtCfg<CFG>::T;   // single PU: all lanes, for the row-per-lane tiles (gt_search_cta: fine)
   k2_gt_search<WS, CFG><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq, rb);
   return cudaGetLastError();
 }
@@ -1216,6 +1311,7 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
+  if (n == 1) threads = GtCfg<CFG>::T;   // single PU: all lanes, for the row-per-lane tiles and the fractional stage
   return launch_ex(k_motion_tail<WS, CFG>, n, 1, threads, motion_smem_bytes(WS, max_cols, max_rows), stream, ipu.use != 0,
                    n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
 }
