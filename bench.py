@@ -182,7 +182,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": c, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -513,13 +513,31 @@ def run_ours(args):
         "encode": enc,
         "sweep": swp,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        emit(line)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # stdout carries exactly one JSON line: whatever libraries print while the bench runs (torch prints an
+    # "NCCL version" banner at the first collective) is sent to stderr at the file-descriptor level
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

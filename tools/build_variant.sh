@@ -9,5 +9,5 @@ for f in $root/hevc-hop_b200/csrc/*.cu; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --fmad=false "$@" -c $f -o $out/$name/$(basename $f .cu).o &
 done
 wait
-nvcc -shared -o $out/libhopgpu_$name.so $out/$name/*.o -cudart static
+nvcc -shared -arch=sm_100a -o $out/libhopgpu_$name.so $out/$name/*.o -cudart static
 echo $out/libhopgpu_$name.so
