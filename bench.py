@@ -527,7 +527,7 @@ def emit(line):
     if _REAL_STDOUT is not None:
         os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
     else:
-        emit(line)
+        print(json.dumps(line))
 
 
 def main():
