@@ -207,8 +207,8 @@ def _ptr(a):
 class HopContext:
     """One encoder context (= one GPU).  Thin object wrapper over the hop_ctx_* / hop_* C functions."""
 
-    def __init__(self, device=0):
-        self.lib = load_library()
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load_library(lib_path)   # lib_path: another build of the same ABI (tests: the refops twin)
         h = _P()
         self._check(self.lib.hop_ctx_create(int(device), C.byref(h)))
         self.h = h

@@ -324,3 +324,35 @@ def test_randomised_content_and_parameters(ctx):
         fj["cost"] = gj["cost"]
         got, want = ctx.frac_search(fj, org, ref), _oracle.frac_search(fj, org, ref)
         assert got.tobytes() == want.tobytes(), it
+
+
+def test_three_lerp_blend_equals_reference_operation_sequence_at_full_size(ctx):
+    """DESIGN.md "warp rounding": K2 blends with three lerps; libhopgpu_refops.so is the same library with the
+    reference's literal binary64 operation sequence (-DHOP_WARP_REFERENCE_OPS).  The oracle pins both at sizes
+    it can finish in seconds; here the two GPU builds are compared at bench size (thousands of PUs up to 64x64,
+    both bit depths, diamond search and exhaustive sweep) -- every result field must be identical."""
+    import __graft_entry__ as graft
+    from hevc_hop_b200.workload import GtBatch
+    if not os.path.exists(graft.LIB_REFOPS):
+        pytest.skip("libhopgpu_refops.so not built")
+    twin = hop.HopContext(0, lib_path=graft.LIB_REFOPS)
+    rng = np.random.default_rng(77)
+    pixels = 0
+    try:
+        for (c, r, n) in [(8, 8, 2048), (16, 16, 1024), (32, 32, 512), (64, 64, 384), (16, 12, 512), (8, 4, 1024), (64, 32, 256)]:
+            for bd in (8, 10):
+                b = GtBatch(c, r, n, seed=900 + c + r + bd, bit_depth=bd)
+                gj = b.gt_jobs.copy()
+                gj["threshold"] = rng.choice([0xFFFFFFFE, 100000, 5000], size=n)
+                gj["use_had"] = rng.integers(0, 2, size=n)
+                got, want = ctx.pattern_search_gt(gj, b.org, b.ref), twin.pattern_search_gt(gj, b.org, b.ref)
+                assert got.tobytes() == want.tobytes(), (c, r, bd)
+                pixels += int(got["n_candidates"].sum()) * c * r
+        for (c, r, n) in [(16, 16, 24), (8, 8, 48)]:
+            b = PuBatch(c, r, n, seed=31, bit_depth=10, sr=32, n_start=1)
+            got, want = ctx.gt_sweep(b.gt_jobs, b.org, b.ref), twin.gt_sweep(b.gt_jobs, b.org, b.ref)
+            assert got.tobytes() == want.tobytes(), ("sweep", c, r)
+            pixels += int(got["n_candidates"].sum()) * c * r
+    finally:
+        twin.close()
+    assert pixels > 1.5e9   # warped pixels compared (1.85e9 for the diamond cases alone)
