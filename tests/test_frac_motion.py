@@ -111,8 +111,13 @@ def test_gpu_motion_search_on_the_mirror_single_call(ctx):
     ctx.ref_upload(host)
     stride = pic_w + 2 * m
     # multi-tile shapes take the thread-block-cluster form of the latency path (2, 4 or 8 CTAs per PU)
-    for (c, r) in [(16, 16), (8, 4), (32, 32), (64, 64), (16, 12), (32, 8), (16, 8), (8, 8), (64, 32), (24, 32)]:
-        b = PuBatch(c, r, 1, seed=c, sr=16, n_start=2)
+    # every PU shape of the encoder: single CTA, row-per-lane tiles, clusters of 2/4/8, inline and mapped blocks
+    every = [(8, 8), (16, 16), (32, 32), (64, 64), (8, 4), (4, 8), (16, 8), (8, 16), (16, 4), (4, 16), (16, 12), (12, 16),
+             (32, 16), (16, 32), (32, 8), (8, 32), (32, 24), (24, 32), (64, 32), (32, 64), (64, 16), (16, 64), (64, 48), (48, 64)]
+    for (c, r), seed in [(sh, sd) for sh in every for sd in (0, 1)]:
+        if not hop.load_library().hop_shape_supported(c, r):
+            continue
+        b = PuBatch(c, r, 1, seed=c + 100 * seed, sr=16, n_start=2 + seed)
         mj = b.motion_jobs()
         s = mj["search"]
         s["ref_stride"] = stride; s["ref_off"] = 64 * stride + 64
