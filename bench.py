@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pus", type=int, default=4096, help="PUs per shape per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="PUs per shape in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="PUs per shape in the CPU baseline sample (~16 s on one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encode-size", type=int, default=1024, help="edge of the square lenslet image encoded per GPU; 0 = skip")
     ap.add_argument("--sweep-pus", type=int, default=256, help="PUs (16x16, Main10) of the sharded exhaustive sweep; 0 = skip")

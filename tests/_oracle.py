@@ -51,6 +51,15 @@ class _Checker:
         hop = self.hop
         jobs = np.ascontiguousarray(jobs, dtype=hop.GT_JOB_DT)
         out = np.zeros(len(jobs), dtype=hop.GT_RES_DT)
+        if self.prefix == "ref_" and len(jobs):
+            # the reference's prologue interpolates 16 planes around the window (8-tap filters: a few rows and
+            # columns beyond the 2W x 2H samples the search reads) although only plane [0][0] is used afterwards;
+            # on compact per-PU windows those reads leave the buffer at its two ends, so give it guard bands
+            guard = 8 * int(jobs["ref_stride"].max()) + 64
+            ref = np.concatenate([np.zeros(guard, np.int16), np.ascontiguousarray(ref, dtype=np.int16).reshape(-1),
+                                  np.zeros(guard, np.int16)])
+            jobs = jobs.copy()
+            jobs["ref_off"] += guard
         self._gt(len(jobs), _np(jobs), _np(org), _np(ref), _np(out))
         return out
 
