@@ -178,9 +178,14 @@ REF_DECODER = os.path.join(ORACLE_DIR, "_ref", "TAppDecoderRef")
 
 
 def encode_reference(width, height, **kw):
-    """Encode a synthetic lenslet frame with the unmodified CPU reference (checker / baseline only)."""
+    """Encode a synthetic lenslet frame with the unmodified CPU reference (checker / baseline only).
+
+    The unmodified reference dies with SIGSEGV now and then (tools/flake_probe.py: 1-2 of 45 runs of the 136x104
+    case even with one retry; it reads beyond its buffers, e.g. the interpolation prologue of xPatternSearchGT and
+    AMVP start vectors that leave the plane, so the outcome depends on the heap layout).  Its OUTPUT is stable
+    (44 of 44 identical), so the checker is simply started again; the GPU-backed encoder gets no retries."""
     from hevc_hop_b200 import encoder
-    return encoder.encode(REF_ENCODER, width, height, retries=1, **kw)
+    return encoder.encode(REF_ENCODER, width, height, retries=5, **kw)
 
 
 def ref_path():
