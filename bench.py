@@ -211,12 +211,15 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
     import _oracle
     if world == 1 and not args.no_cpu_baseline and os.path.exists(_oracle.REF_ENCODER):
         # bounded CPU sample: the unmodified reference on a 256x256 image, the patched encoder on the same image
-        ref = _oracle.encode_reference(256, 256, seed=7)
-        hop = encoder.encode(encoder.HOP_ENCODER, 256, 256, seed=7, device=local)
-        enc["cpu_reference_256x256"] = {"s_per_image": ref["seconds"], "s_per_ctu": ref["seconds"] / 16, "cores": 1,
-                                        "gpu_s_per_image_same_input": hop["seconds"],
-                                        "bitstream_identical": hashlib.md5(ref["bitstream"]).hexdigest() ==
-                                        hashlib.md5(hop["bitstream"]).hexdigest()}
+        try:
+            ref = _oracle.encode_reference(256, 256, seed=7)
+            hop = encoder.encode(encoder.HOP_ENCODER, 256, 256, seed=7, device=local)
+            enc["cpu_reference_256x256"] = {"s_per_image": ref["seconds"], "s_per_ctu": ref["seconds"] / 16, "cores": 1,
+                                            "gpu_s_per_image_same_input": hop["seconds"],
+                                            "bitstream_identical": hashlib.md5(ref["bitstream"]).hexdigest() ==
+                                            hashlib.md5(hop["bitstream"]).hexdigest()}
+        except RuntimeError as e:     # the unmodified reference segfaults sporadically (tests/_oracle.py)
+            enc["cpu_reference_256x256"] = {"error": str(e)[:200]}
     return enc
 
 
