@@ -145,14 +145,17 @@ int hop_ctx_create(int device, HopCtx** out)
                 e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
   if (device < 0 || device >= n) return fail(HOP_ERR_ARG, "device %d out of range (%d devices)", device, n);
   CU(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    return fail(HOP_ERR_CUDA, "device %d is sm_%d%d; libhopgpu carries sm_100a code only", device, prop.major, prop.minor);
+  // three attributes instead of cudaGetDeviceProperties (which queries everything and costs tens of ms at start-up)
+  int cc_major = 0, cc_minor = 0, sm_count = 0;
+  CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  CU(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major != 10)
+    return fail(HOP_ERR_CUDA, "device %d is sm_%d%d; libhopgpu carries sm_100a code only", device, cc_major, cc_minor);
   HopCtx* ctx = new (std::nothrow) HopCtx();
   if (!ctx) return fail(HOP_ERR_NOMEM, "out of host memory");
   ctx->device = device;
-  ctx->sm_count = prop.multiProcessorCount;
+  ctx->sm_count = sm_count;
   { const char* e = getenv("HOP_CLUSTERS"); ctx->use_clusters = !(e && e[0] == '0'); }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete ctx; return fail(HOP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
