@@ -128,12 +128,12 @@ __device__ __forceinline__ unsigned vsad4_acc(unsigned a, unsigned b, unsigned c
   return d;
 }
 
-constexpr int K1_Q = 4;   // y positions per thread (they share reference rows)
+constexpr int K1_Q = 4;   // y positions per thread (they share reference rows); 1 on the single-PU latency path
 
 // ---- byte path ----------------------------------------------------------------------------------
 // WORDS = cols / 4 (compile time so that the per-row word loop unrolls)
-template <int WORDS>
-__device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, const K1Geom& g,
+template <int WORDS, int K1_Q>
+__device__ __forceinline__ unsigned long long k1_bytes_q(const HopSearchJob& job, const K1Geom& g,
                                                        const unsigned char* __restrict__ s_win,
                                                        const unsigned* __restrict__ s_org,
                                                        const int* __restrict__ s_first_invalid,
@@ -219,6 +219,21 @@ __device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, 
     }
   }
   return best;
+}
+
+// A batch keeps K1_Q = 4 positions per thread (each staged reference row serves four block rows).  A single PU
+// (the in-encoder call) has only a few position rows per slice and leaves most of the CTA idle with that: one
+// position row per thread makes the per-thread chain 2-4x shorter and uses 2-4x more lanes.
+template <int WORDS>
+__device__ __forceinline__ unsigned long long k1_bytes(const HopSearchJob& job, const K1Geom& g,
+                                                       const unsigned char* __restrict__ s_win,
+                                                       const unsigned* __restrict__ s_org,
+                                                       const int* __restrict__ s_first_invalid,
+                                                       const int* __restrict__ s_bits_x,
+                                                       const int* __restrict__ s_bits_y)
+{
+  if (gridDim.x == 1) return k1_bytes_q<WORDS, 1>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y);
+  return k1_bytes_q<WORDS, K1_Q>(job, g, s_win, s_org, s_first_invalid, s_bits_x, s_bits_y);
 }
 
 #ifdef HOP_TRACE
