@@ -515,6 +515,45 @@ template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
 template <> struct GtCfg<4> { static constexpr int T = 448, B = 2; };
 template <> struct GtCfg<5> { static constexpr int T = 224, B = 4; };
 
+// Start vector b of the diamond search in integer pels (TEncSearch.cpp:5106-5153); false = the reference skips it.
+__device__ __forceinline__ bool gt_start_vector(const HopGtJob& job, int b, int* Hx, int* Hy)
+{
+  if (b == 0) {
+    if (job.ss_cand.hor == 0 && job.ss_cand.ver == 0) return false;   // :5116
+    *Hx = job.ss_cand.hor; *Hy = job.ss_cand.ver;
+  } else {
+    const HopMv e = job.amvp[b - 1];
+    if (e.hor == 0 && e.ver == 0) return false;                       // :5144
+    *Hx = (int16_t)(e.hor >> 2); *Hy = (int16_t)(e.ver >> 2);         // :5148-5149
+  }
+  return true;
+}
+
+// Sample (wx, wy) of the window of start vector (Hx, Hy): [Hx - w, Hx + w + cols) x [Hy - w, Hy + w + rows) relative
+// to the PU, clamped to [0, 2^bd - 1] (filterCopy first+last, TComInterpolationFilter.cpp:113-154), as the high
+// word of its binary64 value (converted once, exact).  AMVP start vectors are raw neighbour vectors: their
+// window may leave the reference buffer (the reference then reads whatever lies beyond its plane); the read is
+// kept inside the buffer.
+__device__ __forceinline__ long long gt_window_offset(long long ref_off, int ref_stride, RefBounds rb, int Hx, int Hy, int w, int wx, int wy)
+{
+  long long o = ref_off + (long long)(Hy - w + wy) * ref_stride + (Hx - w + wx);
+  return o < rb.lo ? rb.lo : (o > rb.hi ? rb.hi : o);
+}
+__device__ __forceinline__ uint32_t gt_window_word(int v, int max_val)
+{
+  v = min(max(v, 0), max_val);
+  return (uint32_t)__double2hiint((double)v);
+}
+template <int WS>
+__device__ __forceinline__ void gt_stage_window(const HopGtJob& job, const int16_t* __restrict__ ref_buf, RefBounds rb,
+                                                int Hx, int Hy, int w, int win_w, int win_h, int max_val, uint32_t* win)
+{
+  for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
+    const int wy = i / win_w, wx = i - wy * win_w;
+    win[wy * WS + wx] = gt_window_word(ref_buf[gt_window_offset(job.ref_off, job.ref_stride, rb, Hx, Hy, w, wx, wy)], max_val);
+  }
+}
+
 // The whole xPatternSearchGT of one PU, executed by one CTA.  `out` is written by thread 0.
 // smem_raw: [GtShared][org rows*cols int32][window (rows+2w) x WS uint32]; when `org_staged` the int32
 // original block is already in place (the fused motion kernel stages it once for all stages).
@@ -526,7 +565,8 @@ template <> struct GtCfg<5> { static constexpr int T = 224, B = 4; };
 template <int WS, bool CL = false>
 __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t* __restrict__ org_buf,
                                               const int16_t* __restrict__ ref_buf, unsigned char* smem_raw,
-                                              HopGtResult* __restrict__ out, bool org_staged, RefBounds rb)
+                                              HopGtResult* __restrict__ out, bool org_staged, RefBounds rb,
+                                              uint32_t* win_slots = nullptr, int slot_words = 0, unsigned pre_mask = 0)
 {
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
   int crank = 0, csize = 1;
@@ -560,6 +600,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
       else        s_div_h[i - nw] = __ddiv_rn((double)(i - nw - 2 * nss_window), Hd);
     }
   }
+  __syncthreads();   // quotient tables (and the original block) visible before the first candidate set-up
 
   // Search state is replicated per head warp (threads 0..63 = two warps): both warps reduce all 56 candidate
   // costs of a pass and take the same decision, so a pass needs two CTA barriers (table ready, tiles done) and
@@ -584,28 +625,14 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   const int n_start = 1 + job.num_pred;
   for (int b = 0; b < n_start; b++) {                           // :5106-5110
     int Hx, Hy;                                                 // integer-pel start vector
-    if (b == 0) {
-      if (job.ss_cand.hor == 0 && job.ss_cand.ver == 0) continue;   // :5116
-      Hx = job.ss_cand.hor; Hy = job.ss_cand.ver;
-    } else {
-      const HopMv e = job.amvp[b - 1];
-      if (e.hor == 0 && e.ver == 0) continue;                   // :5144
-      Hx = (int16_t)(e.hor >> 2); Hy = (int16_t)(e.ver >> 2);   // :5148-5149
-    }
+    if (!gt_start_vector(job, b, &Hx, &Hy)) continue;
     const int Hor = (int16_t)(Hx << 2), Ver = (int16_t)(Hy << 2);   // Short, quarter-pel
-    __syncthreads();   // previous pass done with s_win
-    // window staging: samples [Hx - w, Hx + w + cols) x [Hy - w, Hy + w + rows) relative to the PU,
-    // clamped to [0, 2^bd - 1] (filterCopy first+last, TComInterpolationFilter.cpp:113-154), stored as
-    // the high word of their binary64 value (converted once, exact)
-    for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
-      const int wy = i / win_w, wx = i - wy * win_w;
-      // AMVP start vectors are raw neighbour vectors: their window may leave the reference buffer (the
-      // reference then reads whatever lies beyond its plane); keep the read inside the buffer
-      long long o = job.ref_off + (long long)(Hy - w + wy) * job.ref_stride + (Hx - w + wx);
-      o = o < rb.lo ? rb.lo : (o > rb.hi ? rb.hi : o);
-      int v = ref_buf[o];
-      v = min(max(v, 0), max_val);
-      s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
+    // latency path: one window slot per start vector, staged ahead by the caller (pre_mask); otherwise one slot,
+    // restaged per start
+    uint32_t* const win_b = win_slots ? win_slots + (size_t)b * slot_words : s_win;
+    if (!((pre_mask >> b) & 1u)) {
+      if (!win_slots) __syncthreads();   // previous start done with the slot
+      gt_stage_window<WS>(job, ref_buf, rb, Hx, Hy, w, win_w, win_h, max_val, win_b);
     }
     const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);        // :5345
     HOP_STAMP(g_trace_k2, 8 + b * 16);   // window loads of start b issued
@@ -662,7 +689,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
       }
       __syncthreads();
       HOP_STAMP(g_trace_k2, 9 + b * 16 + 2 * pass);    // candidate table of the pass built
-      run_tasks<WS>(sh, s_org, s_win, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb, fine);
+      run_tasks<WS>(sh, s_org, win_b, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb, fine);
       if (CL) cg::this_cluster().sync(); else __syncthreads();
       HOP_STAMP(g_trace_k2, 10 + b * 16 + 2 * pass);   // tiles of the pass evaluated
       if (head) {
@@ -1125,17 +1152,48 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
   if (job_id >= n_jobs) return;
   const HopMotionJob mj = ipu.use ? ipu.job : jobs[job_id];
   const HopSearchJob& sj = mj.search;
-  // the original block does not depend on k1_search: stage it before waiting for that grid (the single-call
-  // path launches this kernel with programmatic stream serialisation, so it is resident while K1 still runs)
+  const int cols = sj.cols, rows = sj.rows;
+  const int w = (rows < cols ? rows : cols) >> 1, win_w = cols + 2 * w, win_h = rows + 2 * w;
+  const int max_val = (1 << sj.bit_depth) - 1;
+  FracShared& fs = *reinterpret_cast<FracShared*>(smem_raw);               // aliases GtShared, used before it
+  int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES + gt_div_bytes(cols, rows));
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(s_org + ((rows * cols + 3) & ~3));
+  // Single PU with room in shared memory (the launcher asks for it): the fractional stage and the window of every
+  // start vector get their own space, so that all global-memory reads of the call happen in two rounds -- the
+  // AMVP windows before K1 has finished, the K1-dependent ones (fractional source, window of the SS vector)
+  // together right after -- instead of one exposed latency per stage.
+  unsigned dyn_smem;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_smem));
+  const int slot_words = WS * win_h;
+  const size_t fr_bytes = (frac_smem_bytes(cols, rows) + 15) & ~(size_t)15;
+  const size_t multi_bytes = (size_t)(scratch - smem_raw) + fr_bytes + sizeof(uint32_t) * (size_t)slot_words * (1 + HOP_MAX_PRED);
+  const bool multi = (int)gridDim.x == csize && mj.use_gt && win_w <= WS && multi_bytes <= dyn_smem;
+  uint32_t* win_slots = multi ? reinterpret_cast<uint32_t*>(scratch + fr_bytes) : nullptr;
+  HopGtJob gj;
+  gj.org_off = sj.org_off; gj.ref_off = sj.ref_off; gj.org_stride = sj.org_stride; gj.ref_stride = sj.ref_stride;
+  gj.cols = cols; gj.rows = rows;
+  gj.num_pred = mj.num_pred;
+  for (int k = 0; k < HOP_MAX_PRED; k++) gj.amvp[k] = mj.amvp[k];
+  gj.use_had = mj.use_had; gj.bit_depth = sj.bit_depth;
+  gj.cost = sj.cost; gj.cost.cost_scale = 0;   // :4619
+  unsigned pre_mask = 0;
+  // nothing below depends on k1_search: it runs before the wait for that grid (the single-call path launches this
+  // kernel with programmatic stream serialisation, so it is resident while K1 still works)
   {
-    int* s_org0 = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES + gt_div_bytes(sj.cols, sj.rows));
     const int16_t* org0 = org_buf + sj.org_off;
     if (ipu.use == 2) {
-      for (int i = threadIdx.x; i < sj.rows * sj.cols; i += blockDim.x) s_org0[i] = ipu.org[i];
+      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) s_org[i] = ipu.org[i];
     } else {
-      for (int i = threadIdx.x; i < sj.rows * sj.cols; i += blockDim.x)
-        s_org0[i] = org0[(i / sj.cols) * sj.org_stride + (i % sj.cols)];
+      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+        s_org[i] = org0[(i / cols) * sj.org_stride + (i % cols)];
     }
+    if (multi)
+      for (int b = 1; b <= gj.num_pred; b++) {
+        int Hx, Hy;
+        if (!gt_start_vector(gj, b, &Hx, &Hy)) continue;
+        gt_stage_window<WS>(gj, ref_buf, rb, Hx, Hy, w, win_w, win_h, max_val, win_slots + (size_t)b * slot_words);
+        pre_mask |= 1u << b;
+      }
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
   HOP_STAMP(g_trace_k2, 1);
@@ -1157,26 +1215,30 @@ __device__ __forceinline__ void motion_tail_body(int n_jobs, const HopMotionJob*
     }
   }
   if (go) {
-    const int cols = sj.cols, rows = sj.rows;
-    FracShared& fs = *reinterpret_cast<FracShared*>(smem_raw);               // aliases GtShared, used before it
-    int* s_org = reinterpret_cast<int*>(smem_raw + GT_SHARED_BYTES + gt_div_bytes(cols, rows));
-    unsigned char* scratch = reinterpret_cast<unsigned char*>(s_org + ((rows * cols + 3) & ~3));
     const int16_t* ref_pos = ref_buf + sj.ref_off + sr.mv.hor + (long long)sr.mv.ver * sj.ref_stride;
+    gj.ss_cand = sr.mv;                            // pcCU->getSSBestCand()[0]
+    if (multi) {
+      // fractional source region and the window of the SS vector: both loads of an iteration are issued before
+      // either value is used
+      int16_t* s_src = reinterpret_cast<int16_t*>(scratch);
+      const int src_w = cols + 8, n_src = (rows + 8) * src_w, n_win = win_w * win_h;
+      for (int i = threadIdx.x; i < (n_src > n_win ? n_src : n_win); i += blockDim.x) {
+        int a = 0, v = 0;
+        const int wy = i / win_w, wx = i - wy * win_w;
+        if (i < n_src) { const int y = i / src_w, x = i - y * src_w; a = ref_pos[(long long)(y - 4) * sj.ref_stride + (x - 4)]; }
+        if (i < n_win) v = ref_buf[gt_window_offset(gj.ref_off, gj.ref_stride, rb, sr.mv.hor, sr.mv.ver, w, wx, wy)];
+        if (i < n_src) s_src[i] = (int16_t)a;
+        if (i < n_win) win_slots[wy * WS + wx] = gt_window_word(v, max_val);
+      }
+      pre_mask |= 1u;
+    }
     const HopFracResult fr = frac_search_cta(fs, s_org, scratch, ref_pos, sj.ref_stride, cols, rows, sj.bit_depth,
-                                             mj.use_had, sj.cost, sr.mv);
+                                             mj.use_had, sj.cost, sr.mv, multi);
     HOP_STAMP(g_trace_k2, 2);   // fractional refinement done
     if (threadIdx.x == 0 && crank == 0) { res->frac = fr; if (!mj.use_gt) res->gt.cost = fr.cost; }
     if (mj.use_gt) {
-      HopGtJob gj;
-      gj.org_off = sj.org_off; gj.ref_off = sj.ref_off; gj.org_stride = sj.org_stride; gj.ref_stride = sj.ref_stride;
-      gj.cols = cols; gj.rows = rows;
-      gj.ss_cand = sr.mv;                          // pcCU->getSSBestCand()[0]
-      gj.num_pred = mj.num_pred;
-      for (int k = 0; k < HOP_MAX_PRED; k++) gj.amvp[k] = mj.amvp[k];
       gj.threshold = fr.cost;                      // ruiCost coming out of the frac stage (:4769)
-      gj.use_had = mj.use_had; gj.bit_depth = sj.bit_depth;
-      gj.cost = sj.cost; gj.cost.cost_scale = 0;   // :4619
-      gt_search_cta<WS, CL>(gj, org_buf, ref_buf, smem_raw, &res->gt, true, rb);
+      gt_search_cta<WS, CL>(gj, org_buf, ref_buf, smem_raw, &res->gt, true, rb, win_slots, slot_words, pre_mask);
     }
   }
   HOP_STAMP(g_trace_k2, 3);     // GT search done
@@ -1290,6 +1352,19 @@ static size_t motion_smem_bytes(int ws, int max_cols, int max_rows)
   return GT_SHARED_BYTES + gt_div_bytes(max_cols, max_rows) + sizeof(int) * org + (win > fr ? win : fr);
 }
 
+// single-PU launch: room for the fractional scratch AND one window per start vector (motion_tail_body: multi), when
+// that stays below MOTION_SMEM_CAP; otherwise the shared layout of the batched launches
+constexpr size_t MOTION_SMEM_CAP = 200 * 1024;
+static size_t motion_smem_single(int ws, int cols, int rows)
+{
+  const int w = (cols < rows ? cols : rows) >> 1;
+  const size_t org = ((size_t)cols * rows + 3) & ~(size_t)3;
+  const size_t fr = (frac_smem_bytes(cols, rows) + 15) & ~(size_t)15;
+  const size_t multi = GT_SHARED_BYTES + gt_div_bytes(cols, rows) + sizeof(int) * org + fr +
+                       sizeof(uint32_t) * (size_t)ws * (rows + 2 * w) * (1 + HOP_MAX_PRED);
+  return multi <= MOTION_SMEM_CAP ? multi : motion_smem_bytes(ws, cols, rows);
+}
+
 template <int WS, int CFG>
 static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                    const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
@@ -1298,7 +1373,7 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_motion_tail<WS, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)motion_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+                                         (int)MOTION_SMEM_CAP);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -1312,7 +1387,8 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
   if (n == 1) threads = GtCfg<CFG>::T;   // single PU: all lanes, for the row-per-lane tiles and the fractional stage
-  return launch_ex(k_motion_tail<WS, CFG>, n, 1, threads, motion_smem_bytes(WS, max_cols, max_rows), stream, ipu.use != 0,
+  return launch_ex(k_motion_tail<WS, CFG>, n, 1, threads,
+                   n == 1 ? motion_smem_single(WS, max_cols, max_rows) : motion_smem_bytes(WS, max_cols, max_rows), stream, ipu.use != 0,
                    n, d_jobs, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
 }
 
@@ -1360,11 +1436,11 @@ static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_motion_tail_cl<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)motion_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+                                         (int)MOTION_SMEM_CAP);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_ex(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_bytes(WS, cols, rows), stream, ipu.use != 0,
+  return launch_ex(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_single(WS, cols, rows), stream, ipu.use != 0,
                    1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);
 }
 

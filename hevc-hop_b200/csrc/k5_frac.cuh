@@ -160,17 +160,19 @@ __device__ __forceinline__ void frac_stage(FracShared& fs, const int* __restrict
 __device__ __forceinline__ HopFracResult frac_search_cta(FracShared& fs, const int* __restrict__ s_org,
                                                          unsigned char* scratch, const int16_t* __restrict__ ref_pos,
                                                          int ref_stride, int cols, int rows, int bit_depth, int use_had,
-                                                         HopCostState cs, HopMv mv_int)
+                                                         HopCostState cs, HopMv mv_int, bool src_staged = false)
 {
   int16_t* s_src = reinterpret_cast<int16_t*>(scratch);
   int16_t* s_tmp = s_src + (rows + 8) * (cols + 8);
   int16_t* s_rt = s_tmp + 3 * (rows + 8) * cols;
   const int src_w = cols + 8;
-  // source region: x in [-4, cols+4), y in [-4, rows+4) around the integer position (:6579)
-  for (int i = threadIdx.x; i < (rows + 8) * src_w; i += blockDim.x) {
-    const int y = i / src_w, x = i - y * src_w;
-    s_src[i] = ref_pos[(long long)(y - 4) * ref_stride + (x - 4)];
-  }
+  // source region: x in [-4, cols+4), y in [-4, rows+4) around the integer position (:6579); the fused
+  // single-PU kernel stages it together with the first HOP window (one global-memory latency for both)
+  if (!src_staged)
+    for (int i = threadIdx.x; i < (rows + 8) * src_w; i += blockDim.x) {
+      const int y = i / src_w, x = i - y * src_w;
+      s_src[i] = ref_pos[(long long)(y - 4) * ref_stride + (x - 4)];
+    }
   __syncthreads();
   const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
   const int dist_shift = bit_depth - 8;
