@@ -5,17 +5,20 @@
 // (TLibCommon/TComPrediction.cpp:807-832, 904-1030), xGetHADs / xCalcHADs4x4/8x8 and the SAD family
 // (TLibCommon/TComRdCost.cpp:513-1010, 1366-1708) and the bit-cost helpers.
 //
-// Parallel restatement (DESIGN.md §K2):
-//   * one CTA per PU job; start vectors and diamond passes are walked sequentially inside the kernel
-//     (they are data dependent), the 56 affine corner sets of a pass are evaluated in parallel;
-//   * the 620 corner sets of a pass reduce to a fixed table of 56 offset patterns (in reference loop
-//     order) because the pass centres always form a parallelogram; every candidate is still put
-//     through the reference's own double-precision affine test;
-//   * a task = (candidate, HAD tile): one thread warps an 8x8 (or 4x4) tile into registers with the
-//     reference's IEEE binary64 operation sequence (no FMA contraction, __d*_rn intrinsics), takes the
-//     difference to the original block, runs the 2-D Walsh-Hadamard butterflies in registers and adds
-//     the rounded tile SATD to the candidate's accumulator in shared memory;
-//   * ordered argmin: candidates are scanned in loop order with strict '<' against the running best,
+// Parallel restatement (DESIGN.md §3 K2):
+//   * one CTA per PU (a cluster of CTAs for a multi-tile PU on the single-call path); start vectors and diamond
+//     passes are walked sequentially inside the kernel (they are data dependent), the 56 affine corner sets of a
+//     pass are evaluated in parallel;
+//   * the 620 corner sets of a pass reduce to a fixed table of 56 offset patterns (in reference loop order)
+//     because the pass centres always form a parallelogram; every candidate is still put through the
+//     reference's own affine test, decided exactly in integers;
+//   * a task = (candidate, Hadamard tile): two lanes warp one 8x8 tile (one lane a 4x4 tile; eight lanes, a row
+//     each, on the single-call path) -- sample POSITIONS with the reference's binary64 operation sequence
+//     (no FMA contraction, __d*_rn intrinsics), the bilinear VALUE by three lerps whose rounded result provably
+//     equals the reference's (DESIGN.md "warp rounding") -- take the difference to the original block, run the
+//     2-D Walsh-Hadamard butterflies in registers / shuffles and add the rounded tile SATD to the candidate's
+//     accumulator in shared memory;
+//   * ordered argmin: the minimum of (cost, loop index) over the pass, accepted iff it beats the running best,
 //     which carries across passes and start vectors exactly as uiDistBest does.
 #include "hop_common.cuh"
 #include <cstdlib>
