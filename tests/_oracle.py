@@ -91,7 +91,9 @@ def oracle():
     if "orc" not in _cache:
         path = os.path.join(ORACLE_DIR, "_build", "libhoporacle.so")
         src = os.path.join(ORACLE_DIR, "hop_oracle.c")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        if os.environ.get("HOP_ORACLE_LIB"):          # e.g. the sanitizer build of `make -C oracle asan`
+            path = os.path.abspath(os.environ["HOP_ORACLE_LIB"])
+        elif not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
             build_oracle()
         lib = C.CDLL(path)
         chk = _Checker(lib, "orc_")
