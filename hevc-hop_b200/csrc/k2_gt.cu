@@ -587,7 +587,6 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + ((rows * cols + 3) & ~3));
   if (win_w > WS) return;   // host picked the wrong stride class (cannot happen through the ABI)
   const int16_t* org = org_buf + job.org_off;
-  const int16_t* ref_y = ref_buf + job.ref_off;
   const int max_val = (1 << job.bit_depth) - 1;
   const int dist_shift = job.bit_depth - 8;
   const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
@@ -844,7 +843,6 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
   uint32_t* s_win = reinterpret_cast<uint32_t*>(s_org + ((rows * cols + 3) & ~3));
   if (win_w > WS) return;
   const int16_t* org = org_buf + job.org_off;
-  const int16_t* ref_y = ref_buf + job.ref_off;
   const int max_val = (1 << job.bit_depth) - 1;
   const int dist_shift = job.bit_depth - 8;
   const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
