@@ -11,7 +11,7 @@ struct RefBounds { long long lo, hi; };
 constexpr RefBounds REF_UNBOUNDED = {-(1ll << 62), (1ll << 62)};
 
 constexpr int GT_CANDS   = 56;    // affine corner sets per diamond pass
-constexpr int GT_THREADS = 336;   // K2 CTA size upper bound: 56 candidates x 2 lanes x 3 tile groups
+constexpr int GT_THREADS = 448;   // sweep CTA size upper bound: 56 candidates x 2 lanes x 4 tile groups (72 registers, 2 CTAs per SM)
 constexpr int K1_THREADS = 256;
 constexpr int K1_MAX_SLICES = 32; // CTAs cooperating on one PU's search window
 
