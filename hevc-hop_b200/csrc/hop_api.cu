@@ -747,7 +747,9 @@ int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int1
   CU(sweep_init_launch(n, (unsigned long long*)d_keys, d_counts, s, &l));
   if (cand_end > cand_begin) {
     const int batches = (cand_end - cand_begin + GT_CANDS - 1) / GT_CANDS;
-    int chunks = (2 * ctx->sm_count + n - 1) / n;      // spread one PU's candidate batches over the machine
+    // spread one PU's candidate batches over the machine: at least ~6 waves of the 2 CTAs resident per SM, so that
+    // the last, partly filled wave costs a few percent instead of up to half of the launch
+    int chunks = (12 * ctx->sm_count + n - 1) / n;
     if (chunks > batches) chunks = batches;
     if (chunks < 1) chunks = 1;
     CU(sweep_keys_launch(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks,
