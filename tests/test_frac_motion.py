@@ -135,3 +135,45 @@ def test_gpu_motion_search_on_the_mirror_single_call(ctx):
             gj["ref_stride"] = stride; gj["ref_off"] = 64 * stride + 64
             gj["ss_cand"] = want["search"]["mv"]; gj["threshold"] = want["frac"]["cost"]; gj["amvp"] = mj["amvp"]
             assert ctx.pattern_search_gt(gj, b.org, None).tobytes() == want["gt"].tobytes(), (c, r)
+
+
+@pytest.mark.gpu
+def test_gpu_single_call_random_start_vectors(ctx):
+    """Single-PU fused calls with random AMVP lists: 0-3 predictors, zero vectors (skipped by the reference), vectors
+    that leave the valid region, the windows-staged-ahead layout and its fall-back, with and without Hadamard."""
+    rng = np.random.default_rng(11)
+    pic_w, pic_h, m = 192, 160, 80
+    ctx.ref_create(pic_w, pic_h, m)
+    host = np.full((pic_h + 2 * m, pic_w + 2 * m), -1, dtype=np.int16)
+    img = rng.integers(0, 256, size=(pic_h, pic_w)).astype(np.int16)
+    host[m:m + 96, m:m + pic_w] = img[:96]                       # causal region: rows above, and the row band left of the PU
+    host[m + 96:m + pic_h, m:m + 96] = img[96:, :96]
+    _oracle.extend_border_oracle(host, pic_w, pic_h, m)
+    ctx.ref_upload(host)
+    stride = pic_w + 2 * m
+    shapes = [(8, 4), (4, 8), (8, 8), (16, 8), (8, 16), (16, 16), (16, 12), (32, 16), (32, 32), (32, 64), (64, 32), (64, 64)]
+    for it in range(72):
+        c, r = shapes[it % len(shapes)]
+        b = PuBatch(c, r, 1, seed=500 + it, sr=16, n_start=1)
+        mj = b.motion_jobs()
+        s = mj["search"]
+        s["ref_stride"] = stride; s["ref_off"] = 96 * stride + 96   # PU at (96, 96) of the picture
+        s["rng_left"], s["rng_right"], s["rng_top"], s["rng_bottom"] = -70, 40, -70, -4
+        mj["search"] = s
+        mj["num_pred"] = int(rng.integers(0, 4))
+        for k in range(3):
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                hv = (0, 0)                                       # skipped start (:5144)
+            elif kind == 1:
+                hv = (int(rng.integers(-90, -10)) * 4, int(rng.integers(-90, -10)) * 4)
+            elif kind == 2:
+                hv = (int(rng.integers(-300, 150)), int(rng.integers(-300, 150)))   # raw quarter-pel, anywhere inside the plane (also into NOT_VALID samples)
+            else:
+                hv = (int(rng.integers(-8, 8)), int(rng.integers(-8, 8)))           # rounds to a (near) zero integer vector
+            mj["amvp"]["hor"][:, k] = hv[0]; mj["amvp"]["ver"][:, k] = hv[1]
+        mj["use_had"] = int(it % 3 != 0)
+        got = ctx.motion_search(mj, b.org, None)
+        m2 = mj.copy(); s2 = m2["search"]; s2["ref_off"] += m * stride + m; m2["search"] = s2
+        want = _oracle.motion_search(m2, b.org, host.reshape(-1))
+        assert got.tobytes() == want.tobytes(), (it, c, r, int(mj["num_pred"][0]))
