@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--encode-size", type=int, default=1024, help="edge of the square lenslet image encoded per GPU; 0 = skip")
     ap.add_argument("--sweep-pus", type=int, default=256, help="PUs (16x16, Main10) of the sharded exhaustive sweep; 0 = skip")
-    ap.add_argument("--k1-pus", type=int, default=256, help="PUs per shape for the secondary K1 (SS full search) measurement; 0 = skip")
+    ap.add_argument("--k1-pus", type=int, default=592, help="PUs per shape for the secondary K1 (SS full search) measurement (592 = two waves of the 2 CTAs resident per SM); 0 = skip")
     return ap.parse_args()
 
 
