@@ -350,7 +350,7 @@ def run_ours(args):
     def step_resident():
         for d in dbat:
             b = d["b"]
-            ctx.pattern_search_gt_dev(b.n, d["jobs"].data_ptr(), d["org"].data_ptr(), d["ref"].data_ptr(),
+            ctx.pattern_search_gt_dev(b.n, d["jobs"].data_ptr(), d["org"].data_ptr(), d["ref"].data_ptr(), b.ref.size,
                                       d["out"].data_ptr(), b.cols, b.rows, stream)
 
     # host calls of one end-to-end step: one hop_pattern_search_gt_batch_async call per shape, except that a
@@ -412,7 +412,7 @@ def run_ours(args):
         for i, d in enumerate(dbat):
             b = d["b"]
             ev[s][i].record(tstream)
-            ctx.pattern_search_gt_dev(b.n, d["jobs"].data_ptr(), d["org"].data_ptr(), d["ref"].data_ptr(),
+            ctx.pattern_search_gt_dev(b.n, d["jobs"].data_ptr(), d["org"].data_ptr(), d["ref"].data_ptr(), b.ref.size,
                                       d["out"].data_ptr(), b.cols, b.rows, stream)
         ev[s][len(dbat)].record(tstream)
     e1.record(tstream)

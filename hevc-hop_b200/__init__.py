@@ -92,6 +92,11 @@ class HopMotionResult(C.Structure):
     _fields_ = [("search", HopSearchResult), ("refined", C.c_int32), ("frac", HopFracResult), ("gt", HopGtResult)]
 
 
+class HopCtxStats(C.Structure):
+    _fields_ = [("single_calls", C.c_uint64), ("cache_hits", C.c_uint64), ("cache_misses", C.c_uint64),
+                ("prefetched", C.c_uint64), ("prefetch_dropped", C.c_uint64), ("candidates", C.c_uint64)]
+
+
 class HopDistJob(C.Structure):
     _fields_ = [
         ("org_off", C.c_int64), ("cur_off", C.c_int64),
@@ -163,13 +168,15 @@ ABI = [
     ("hop_dist_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_frac_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_motion_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    ("hop_motion_search_prefetch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
     ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
-    ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, C.c_int, C.c_int, _P]),
     ("hop_dist_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
-    ("hop_gt_sweep_keys_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    ("hop_gt_sweep_keys_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     ("hop_gt_sweep_finalize_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_gt_sweep_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_ctx_launch_count", C.c_uint64, [_P]),
+    ("hop_ctx_stats", C.c_int, [_P, _P]),
     ("hop_probe_alu", C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 
@@ -292,6 +299,16 @@ class HopContext:
             self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
         return out
 
+    def motion_prefetch(self, jobs, org):
+        """Enqueue speculative single-PU motion searches against the SS mirror (hop_motion_search_prefetch)."""
+        jobs = np.ascontiguousarray(jobs, dtype=MOTION_JOB_DT)
+        self._check(self.lib.hop_motion_search_prefetch(self.h, len(jobs), _ptr(jobs), _ptr(org), org.size))
+
+    def stats(self):
+        st = HopCtxStats()
+        self._check(self.lib.hop_ctx_stats(self.h, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in HopCtxStats._fields_}
+
     def dist(self, jobs, org, cur):
         jobs = np.ascontiguousarray(jobs, dtype=DIST_JOB_DT)
         out = np.zeros(len(jobs), dtype=np.uint32)
@@ -303,8 +320,9 @@ class HopContext:
     def pattern_search_dev(self, n, d_jobs, d_org, d_ref, d_out, stream=None):
         self._check(self.lib.hop_pattern_search_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out, stream))
 
-    def pattern_search_gt_dev(self, n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream=None):
-        self._check(self.lib.hop_pattern_search_gt_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out,
+    def pattern_search_gt_dev(self, n, d_jobs, d_org, d_ref, ref_samples, d_out, max_cols, max_rows, stream=None):
+        """ref_samples: int16 samples addressable behind d_ref (bounds the window reads)."""
+        self._check(self.lib.hop_pattern_search_gt_batch_dev(self.h, n, d_jobs, d_org, d_ref, ref_samples, d_out,
                                                              max_cols, max_rows, stream))
 
     def dist_dev(self, n, d_jobs, d_org, d_cur, d_out, stream=None):
@@ -318,9 +336,9 @@ class HopContext:
             self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
         return out
 
-    def gt_sweep_keys_dev(self, n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, d_keys, d_counts=None,
-                          stream=None):
-        self._check(self.lib.hop_gt_sweep_keys_dev(self.h, n, d_jobs, d_org, d_ref, max_cols, max_rows,
+    def gt_sweep_keys_dev(self, n, d_jobs, d_org, d_ref, ref_samples, max_cols, max_rows, cand_begin, cand_end, d_keys,
+                          d_counts=None, stream=None):
+        self._check(self.lib.hop_gt_sweep_keys_dev(self.h, n, d_jobs, d_org, d_ref, ref_samples, max_cols, max_rows,
                                                    cand_begin, cand_end, d_keys, d_counts, stream))
 
     def gt_sweep_finalize_dev(self, n, d_jobs, d_keys, d_counts, d_out, stream=None):

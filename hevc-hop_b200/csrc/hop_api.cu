@@ -6,7 +6,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <mutex>
 #include <new>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define HOP_CPU_RELAX() _mm_pause()
+#else
+#define HOP_CPU_RELAX() ((void)0)
+#endif
 
 #include "hop_internal.h"
 
@@ -49,16 +57,42 @@ static inline unsigned long long host_ns() { timespec t; clock_gettime(CLOCK_MON
 #define HOST_STAMP(i) ((void)0)
 #endif
 
+// Single-PU (in-encoder) searches run through SLOTS.  A slot owns a piece of mapped pinned host memory
+// [job | original block | result | completion flag] (the GPU reads the block from it and writes result + flag back,
+// zero-copy), the K1 merge words of its launch and, except slot 0, a side stream.  Slot 0 serves the synchronous
+// call on the context stream; slots 1.. hold SPECULATIVE searches (hop_motion_search_prefetch): the complete
+// request (job, block, version of the SS mirror) is the cache key, so a later hop_motion_search_batch(n = 1) that
+// asks for exactly that search picks the finished result up instead of launching.
+constexpr int PU_SLOTS = 1 + HOP_PREFETCH_SLOTS;
+struct PuSlot {
+  unsigned char* h = nullptr;       // mapped pinned host memory
+  unsigned char* d = nullptr;       // its device alias
+  unsigned       seq = 0;           // sequence number of the slot's last launch == flag value once it has finished
+  bool           cached = false;    // holds a speculative search that nobody has consumed yet
+  uint64_t       ref_version = 0;   // version of the SS mirror the search ran against
+  uint64_t       synced_version = ~0ull;   // last mirror version the side stream has been ordered behind
+  HopMotionJob   key;               // normalised job (org_off 0, org_stride cols, unused AMVP entries zero)
+  cudaStream_t   stream = nullptr;
+  unsigned long long* d_key = nullptr;     // K1 merge word, ticket counter and integer result of this slot's launch
+  unsigned int*       d_done = nullptr;
+  HopSearchResult*    d_k1 = nullptr;
+};
+
 struct HopCtx {
   int          device = 0;
   cudaStream_t stream = nullptr;
   int          sm_count = 0;
   uint64_t     launches = 0;
   Scratch      jobs, org, ref, out, keys, done, sweep_keys, k1res, sink;
-  // single-call (in-encoder) path: one pinned host buffer [job | original block | result] and its device twin
-  unsigned char* pin_h = nullptr;   // mapped pinned host memory (zero-copy): the GPU reads job + block from it
-  unsigned char* pin_d = nullptr;   // ... through this device alias, and writes result + completion flag back
-  unsigned       pin_seq = 0;
+  PuSlot       slots_pu[PU_SLOTS];
+  unsigned char* pin_base_h = nullptr;     // one allocation for all slots
+  unsigned char* slot_words = nullptr;     // device: PU_SLOTS x 64 B of merge words / K1 results
+  int          next_pu_slot = 1;
+  uint64_t     ref_version = 0;            // bumped by every change of the SS mirror
+  cudaEvent_t  ref_event = nullptr;        // recorded on `stream` after the latest mirror change ...
+  uint64_t     ref_event_version = ~0ull;  // ... of this version
+  HopCtxStats  stats = {};
+  double       spin_timeout_s = 20.0;      // HOP_TIMEOUT_MS: a kernel that never publishes its flag is an error, not a hang
   bool           use_clusters = true;   // HOP_CLUSTERS=0 turns the cluster form of the latency path off
   // asynchronous batches: a copy stream and a ring of scratch sets
   cudaStream_t copy_stream = nullptr;
@@ -99,11 +133,14 @@ int shape_ok(int cols, int rows)
   return ok(cols) && ok(rows) && !(cols == 4 && rows == 4);
 }
 
+// __device__ tables are per device; contexts may be created from several host threads
+std::mutex g_table_mutex;
 bool g_table_ready[64] = {false};
 bool g_sweep_ready[64] = {false};
 
 int sweep_table_ready(HopCtx* ctx)
 {
+  std::lock_guard<std::mutex> lock(g_table_mutex);
   if (ctx->device < 64 && g_sweep_ready[ctx->device]) return HOP_OK;
   SweepCand* table = new (std::nothrow) SweepCand[SWEEP_CANDS];
   if (!table) return fail(HOP_ERR_NOMEM, "out of host memory");
@@ -157,16 +194,18 @@ int hop_ctx_create(int device, HopCtx** out)
   ctx->device = device;
   ctx->sm_count = sm_count;
   { const char* e = getenv("HOP_CLUSTERS"); ctx->use_clusters = !(e && e[0] == '0'); }
+  { const char* e = getenv("HOP_TIMEOUT_MS"); if (e && atof(e) > 0) ctx->spin_timeout_s = atof(e) * 1e-3; }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete ctx; return fail(HOP_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-  if (device < 64 && !g_table_ready[device]) {
+  std::lock_guard<std::mutex> lock(g_table_mutex);
+  if (device >= 64 || !g_table_ready[device]) {
     int8_t table[GT_CANDS][8];
     int count = 0;
     gt_build_offset_table(table, &count);
     if (count != GT_CANDS) { delete ctx; return fail(HOP_ERR_STATE, "GT offset table has %d entries, expected %d", count, GT_CANDS); }
     e = gt_upload_offset_table(table);
     if (e != cudaSuccess) { delete ctx; return fail(HOP_ERR_CUDA, "offset table upload: %s", cudaGetErrorString(e)); }
-    g_table_ready[device] = true;
+    if (device < 64) g_table_ready[device] = true;
   }
   *out = ctx;
   return HOP_OK;
@@ -179,7 +218,11 @@ void hop_ctx_destroy(HopCtx* ctx)
   cudaStreamSynchronize(ctx->stream);
   Scratch* all[] = {&ctx->jobs, &ctx->org, &ctx->ref, &ctx->out, &ctx->keys, &ctx->done, &ctx->sweep_keys, &ctx->k1res, &ctx->sink};
   for (Scratch* s : all) if (s->p) cudaFree(s->p);
-  if (ctx->pin_h) cudaFreeHost(ctx->pin_h);
+  for (int i = 1; i < PU_SLOTS; i++)
+    if (ctx->slots_pu[i].stream) { cudaStreamSynchronize(ctx->slots_pu[i].stream); cudaStreamDestroy(ctx->slots_pu[i].stream); }
+  if (ctx->ref_event) cudaEventDestroy(ctx->ref_event);
+  if (ctx->pin_base_h) cudaFreeHost(ctx->pin_base_h);
+  if (ctx->slot_words) cudaFree(ctx->slot_words);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (auto& sl : ctx->slots) {
     Scratch* ss[] = {&sl.jobs, &sl.org, &sl.ref, &sl.out};
@@ -198,12 +241,20 @@ int hop_ctx_sync(HopCtx* ctx)
   if (st) return st;
   if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 1; i < PU_SLOTS; i++) if (ctx->slots_pu[i].stream) CU(cudaStreamSynchronize(ctx->slots_pu[i].stream));
   for (auto& sl : ctx->slots) sl.busy = false;
   return HOP_OK;
 }
 
 void* hop_ctx_stream(HopCtx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t hop_ctx_launch_count(HopCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hop_ctx_stats(HopCtx* ctx, HopCtxStats* out)
+{
+  if (!ctx || !out) return fail(HOP_ERR_ARG, "NULL argument");
+  *out = ctx->stats;
+  return HOP_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // SS reference mirror (K4)
@@ -219,6 +270,7 @@ int hop_ref_create(HopCtx* ctx, int pic_w, int pic_h, int margin)
   cudaError_t e = cudaMalloc((void**)&ctx->plane, samples * sizeof(int16_t));
   if (e != cudaSuccess) return fail(HOP_ERR_NOMEM, "cudaMalloc(plane %zu samples): %s", samples, cudaGetErrorString(e));
   ctx->plane_valid = false;
+  ctx->ref_version++;
   return HOP_OK;
 }
 
@@ -232,6 +284,7 @@ int hop_ref_reset(HopCtx* ctx, int value)
   CU(ref_fill_launch(ctx->plane, samples, value, ctx->stream, &l));
   ctx->launches += l;
   ctx->plane_valid = true;
+  ctx->ref_version++;
   return HOP_OK;
 }
 
@@ -245,6 +298,7 @@ int hop_ref_upload(HopCtx* ctx, const int16_t* plane, size_t plane_samples)
   CU(cudaMemcpyAsync(ctx->plane, plane, samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));   // the host plane may change right after the call
   ctx->plane_valid = true;
+  ctx->ref_version++;
   return HOP_OK;
 }
 
@@ -262,6 +316,7 @@ int hop_ref_update(HopCtx* ctx, int x, int y, int w, int h, const int16_t* src, 
   int l = 0;
   CU(ref_extend_launch(origin, ctx->stride, ctx->pic_w, ctx->pic_h, ctx->margin, x, y, w, h, ctx->stream, &l));
   ctx->launches += l;
+  ctx->ref_version++;      // speculative searches against the previous state can no longer be handed out
   return HOP_OK;
 }
 
@@ -304,6 +359,17 @@ RefBounds bounds_for(const HopCtx* ctx, bool mirror, size_t ref_samples)
   return rb;
 }
 
+// bounds of a caller-supplied device reference buffer: the mirror's own geometry when d_ref is the mirror origin,
+// else [0, ref_samples) -- AMVP start vectors are raw neighbour vectors, their windows may leave the buffer and the
+// kernels keep every read inside these bounds
+int dev_bounds(const HopCtx* ctx, const int16_t* d_ref, size_t ref_samples, RefBounds* rb)
+{
+  if (ctx->plane && d_ref == ctx->plane + (size_t)ctx->margin * ctx->stride + ctx->margin) { *rb = bounds_for(ctx, true, 0); return HOP_OK; }
+  if (ref_samples == 0) return fail(HOP_ERR_ARG, "ref_samples == 0: the size of the device reference buffer is needed to bound the window reads");
+  *rb = bounds_for(ctx, false, ref_samples);
+  return HOP_OK;
+}
+
 int gt_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
            int max_cols, int max_rows, cudaStream_t s, RefBounds rb)
 {
@@ -322,9 +388,17 @@ int k1_slices(const HopCtx* ctx, int n)
 }
 int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                HopSearchResult* d_out, int smem_bytes, cudaStream_t s, unsigned* done_flag = nullptr, unsigned seq = 0,
-               int job_stride = 0, const InlinePu* inl = nullptr)
+               int job_stride = 0, const InlinePu* inl = nullptr, const PuSlot* slot = nullptr)
 {
-  // merge words: all-ones keys / zero tickets between launches (the kernel restores them itself)
+  if (slot) {        // single-PU launch of a slot: its own merge words, so that slots may run concurrently
+    int l = 0;
+    CU(search_launch(n, d_jobs, d_org, d_ref, d_out, slot->d_key, slot->d_done, k1_slices(ctx, n), smem_bytes, s, &l,
+                     done_flag, seq, job_stride, inl));
+    ctx->launches += l;
+    return HOP_OK;
+  }
+  // merge words: all-ones keys / zero tickets between launches (the kernel restores them itself).  They belong to
+  // the context: batched searches of one context must be issued on one stream at a time.
   const size_t kcap = ctx->keys.cap, dcap = ctx->done.cap;
   int st = ensure(ctx, ctx->keys, sizeof(unsigned long long) * (size_t)n);
   if (st) return st;
@@ -351,7 +425,7 @@ int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,
 }
 
 int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org,
-                                    const int16_t* d_ref, HopGtResult* d_out, int max_cols, int max_rows,
+                                    const int16_t* d_ref, size_t ref_samples, HopGtResult* d_out, int max_cols, int max_rows,
                                     void* stream)
 {
   int st = bind(ctx);
@@ -360,9 +434,11 @@ int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, 
   if (max_cols < 4 || max_cols > HOP_MAX_PU || max_rows < 4 || max_rows > HOP_MAX_PU)
     return fail(HOP_ERR_ARG, "shape bound %dx%d out of range", max_cols, max_rows);
   if (n == 0) return HOP_OK;
+  RefBounds rb;
+  if ((st = dev_bounds(ctx, d_ref, ref_samples, &rb))) return st;
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   int l = 0;
-  CU(gt_launch(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, s, &l));
+  CU(gt_launch(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, s, &l, rb));
   ctx->launches += l;
   return HOP_OK;
 }
@@ -387,60 +463,191 @@ int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs, const int16
 namespace {
 
 extern "C++" {
-// In-encoder single call on the SS mirror (the latency path).  One mapped pinned host buffer holds
+// In-encoder single call on the SS mirror (the latency path).  A slot's mapped pinned host buffer holds
 // [job | W x H original block | result | completion flag]; the kernel reads the job and the block straight
 // from host memory (a few KB over PCIe), writes the result and then the flag back, and the host spins on
-// the flag: one kernel launch per search, no copy calls, no stream synchronisation.
-constexpr size_t PIN_JOB = 128;                                   // job slot (the largest job struct is 112 B)
+// the flag: no copy calls, no stream synchronisation.
+constexpr size_t PIN_JOB = 128;                                   // job slot (HopMotionJob, the largest job struct, is 104 B)
 constexpr size_t PIN_ORG = HOP_MAX_PU * HOP_MAX_PU * sizeof(int16_t);
-constexpr size_t PIN_OUT = 128;                                   // result slot (HopMotionResult is 76 B)
+constexpr size_t PIN_OUT = 128;                                   // result slot (HopMotionResult is 72 B)
 constexpr size_t PIN_FLAG = 64;
 constexpr size_t PIN_BYTES = PIN_JOB + PIN_ORG + PIN_OUT + PIN_FLAG;
+constexpr size_t SLOT_WORDS = 64;                                 // device bytes per slot: key 8 | ticket 4 | pad 4 | K1 result 16
+static_assert(sizeof(HopMotionJob) <= PIN_JOB && sizeof(HopMotionResult) <= PIN_OUT, "slot layout");
 
-int pin_ready(HopCtx* ctx)
+int slots_ready(HopCtx* ctx)
 {
-  if (ctx->pin_h) return HOP_OK;
-  CU(cudaHostAlloc((void**)&ctx->pin_h, PIN_BYTES, cudaHostAllocMapped));
-  memset(ctx->pin_h, 0, PIN_BYTES);
-  CU(cudaHostGetDevicePointer((void**)&ctx->pin_d, ctx->pin_h, 0));
+  if (ctx->pin_base_h) return HOP_OK;
+  unsigned char* h = nullptr;
+  unsigned char* d = nullptr;
+  CU(cudaHostAlloc((void**)&h, PIN_BYTES * PU_SLOTS, cudaHostAllocMapped));
+  memset(h, 0, PIN_BYTES * PU_SLOTS);
+  CU(cudaHostGetDevicePointer((void**)&d, h, 0));
+  CU(cudaMalloc((void**)&ctx->slot_words, SLOT_WORDS * PU_SLOTS));
+  CU(cudaMemsetAsync(ctx->slot_words, 0, SLOT_WORDS * PU_SLOTS, ctx->stream));
+  for (int i = 0; i < PU_SLOTS; i++) {
+    PuSlot& sl = ctx->slots_pu[i];
+    sl.h = h + PIN_BYTES * i;
+    sl.d = d + PIN_BYTES * i;
+    unsigned char* w = ctx->slot_words + SLOT_WORDS * i;
+    sl.d_key = (unsigned long long*)w;
+    sl.d_done = (unsigned int*)(w + 8);
+    sl.d_k1 = (HopSearchResult*)(w + 16);
+    CU(cudaMemsetAsync(sl.d_key, 0xFF, sizeof(unsigned long long), ctx->stream));   // all-ones between launches
+    if (i == 0) sl.stream = ctx->stream;
+    else CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  }
+  CU(cudaEventCreateWithFlags(&ctx->ref_event, cudaEventDisableTiming));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->pin_base_h = h;
   return HOP_OK;
 }
 
 template <typename JOB>
-int pack_single(HopCtx* ctx, const JOB& job, const int16_t* org, size_t org_samples)
+int pack_single(HopCtx* ctx, PuSlot& sl, const JOB& job, const int16_t* org, size_t org_samples)
 {
-  int st = pin_ready(ctx);
-  if (st) return st;
   const size_t need = (size_t)(job.rows - 1) * job.org_stride + job.cols;
   if (job.org_off < 0 || (size_t)job.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
   JOB packed = job;
   packed.org_off = 0;                          // the block becomes contiguous behind the job
   packed.org_stride = job.cols;
-  memcpy(ctx->pin_h, &packed, sizeof(JOB));
-  int16_t* dst = (int16_t*)(ctx->pin_h + PIN_JOB);
+  memcpy(sl.h, &packed, sizeof(JOB));
+  int16_t* dst = (int16_t*)(sl.h + PIN_JOB);
   const int16_t* src = org + job.org_off;
   for (int r = 0; r < job.rows; r++) memcpy(dst + (size_t)r * job.cols, src + (size_t)r * job.org_stride, sizeof(int16_t) * job.cols);
+  (void)ctx;
   return HOP_OK;
 }
 
-inline unsigned* pin_flag_dev(HopCtx* ctx) { return (unsigned*)(ctx->pin_d + PIN_JOB + PIN_ORG + PIN_OUT); }
+inline unsigned* slot_flag_dev(const PuSlot& sl) { return (unsigned*)(sl.d + PIN_JOB + PIN_ORG + PIN_OUT); }
+inline const int16_t* slot_org_dev(const PuSlot& sl) { return (const int16_t*)(sl.d + PIN_JOB); }
+inline unsigned char* slot_out_dev(const PuSlot& sl) { return sl.d + PIN_JOB + PIN_ORG; }
 
-template <typename RES>
-int unpack_single(HopCtx* ctx, unsigned seq, RES* out)
+inline double mono_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+
+// Wait for the slot's launch number sl.seq to publish its completion flag.  A kernel that dies, or that finishes
+// without publishing, or that does not finish within the time-out is an error status -- never an endless spin.
+int wait_slot_flag(HopCtx* ctx, PuSlot& sl)
 {
-  volatile unsigned* flag = (volatile unsigned*)(ctx->pin_h + PIN_JOB + PIN_ORG + PIN_OUT);
+  volatile unsigned* flag = (volatile unsigned*)(sl.h + PIN_JOB + PIN_ORG + PIN_OUT);
+  const unsigned seq = sl.seq;
   unsigned long long spins = 0;
+  double t0 = 0.0;
   while (*flag != seq) {
-    if ((++spins & 0xFFFFF) == 0) {            // every ~1M polls: did the kernel die?
-      cudaError_t e = cudaStreamQuery(ctx->stream);
+    HOP_CPU_RELAX();
+    if ((++spins & 0xFFFF) == 0) {             // every 64K polls: did the kernel die, are we out of time?
+      cudaError_t e = cudaStreamQuery(sl.stream);
       if (e != cudaSuccess && e != cudaErrorNotReady)
         return fail(HOP_ERR_CUDA, "kernel failed: %s", cudaGetErrorString(e));
       if (e == cudaSuccess && *flag != seq) return fail(HOP_ERR_CUDA, "kernel finished without publishing its result");
+      const double now = mono_s();
+      if (t0 == 0.0) t0 = now;
+      else if (now - t0 > ctx->spin_timeout_s)
+        return fail(HOP_ERR_CUDA, "no result within %.1f s (HOP_TIMEOUT_MS): kernel hung or launch lost", ctx->spin_timeout_s);
     }
   }
   __sync_synchronize();
-  memcpy(out, ctx->pin_h + PIN_JOB + PIN_ORG, sizeof(RES));
   return HOP_OK;
+}
+
+template <typename RES>
+int unpack_single(HopCtx* ctx, PuSlot& sl, RES* out)
+{
+  int st = wait_slot_flag(ctx, sl);
+  if (st) return st;
+  memcpy(out, sl.h + PIN_JOB + PIN_ORG, sizeof(RES));
+  return HOP_OK;
+}
+
+// ---- the fused single-PU motion search of a slot ----------------------------------------------------------------
+// normalised request: what the kernels see (contiguous block) with the unused AMVP entries cleared
+HopMotionJob motion_key(const HopMotionJob& job)
+{
+  HopMotionJob k = job;
+  k.search.org_off = 0;
+  k.search.org_stride = job.search.cols;
+  for (int i = 0; i < HOP_MAX_PRED; i++)
+    if (i >= job.num_pred) { k.amvp[i].hor = 0; k.amvp[i].ver = 0; }
+  return k;
+}
+
+int motion_job_ok(const HopMotionJob& mj, int i)
+{
+  const HopSearchJob& j = mj.search;
+  if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 12 || mj.num_pred < 0 || mj.num_pred > HOP_MAX_PRED)
+    return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / num_pred %d", i, j.cols, j.rows, j.bit_depth, mj.num_pred);
+  return HOP_OK;
+}
+
+// K1 -> (frac -> GT) for ONE PU against the SS mirror, enqueued on the slot's stream; the result lands in the
+// slot's pinned buffer and its flag takes the value sl.seq.
+int launch_motion_slot(HopCtx* ctx, PuSlot& sl, const HopMotionJob& job, const int16_t* org, size_t org_samples)
+{
+  const HopSearchJob& j = job.search;
+  const size_t need = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+  if (j.org_off < 0 || (size_t)j.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
+  HOST_STAMP(0);
+  // job (and a small block) as kernel parameters; larger blocks through the mapped buffer
+  static thread_local InlinePu ipu;
+  ipu.use = j.cols * j.rows <= INLINE_ORG_SAMPLES ? 2 : 1;
+  ipu.job = motion_key(job);
+  sl.key = ipu.job;
+  int16_t* pin_org = (int16_t*)(sl.h + PIN_JOB);     // always filled: it is the block part of the cache key
+  for (int r = 0; r < j.rows; r++) memcpy(pin_org + (size_t)r * j.cols, org + j.org_off + (size_t)r * j.org_stride, sizeof(int16_t) * j.cols);
+  if (ipu.use == 2) memcpy(ipu.org, pin_org, sizeof(int16_t) * (size_t)j.cols * j.rows);
+  const int slices = k1_slices(ctx, 1);
+  size_t smem = search_smem_bytes(j, slices);
+  if (smem > (size_t)(160 * 1024)) smem = 160 * 1024;
+  const unsigned seq = ++sl.seq;
+  sl.ref_version = ctx->ref_version;
+  HOST_STAMP(1);
+  int st = search_dev(ctx, 1, (const HopSearchJob*)sl.d, slot_org_dev(sl), hop_ref_origin_dev(ctx), sl.d_k1, (int)smem, sl.stream,
+                      nullptr, 0, (int)sizeof(HopMotionJob), &ipu, &sl);
+  if (st) return st;
+  HOST_STAMP(2);
+  int l = 0;
+  cudaError_t ce = ctx->use_clusters
+      ? motion_single_launch((const HopMotionJob*)sl.d, slot_org_dev(sl), hop_ref_origin_dev(ctx), sl.d_k1,
+                             (HopMotionResult*)slot_out_dev(sl), j.cols, j.rows, sl.stream, &l,
+                             bounds_for(ctx, true, 0), slot_flag_dev(sl), seq, &ipu)
+      : cudaErrorNotSupported;
+  if (ce == cudaErrorNotSupported)
+    ce = motion_tail_launch(1, (const HopMotionJob*)sl.d, slot_org_dev(sl), hop_ref_origin_dev(ctx), sl.d_k1,
+                            (HopMotionResult*)slot_out_dev(sl), j.cols, j.rows, sl.stream, &l,
+                            bounds_for(ctx, true, 0), slot_flag_dev(sl), seq, &ipu);
+  CU(ce);
+  ctx->launches += l;
+  HOST_STAMP(3);
+  return HOP_OK;
+}
+
+// side streams read the mirror: order them behind the latest change of it (made on the context stream)
+int order_behind_mirror(HopCtx* ctx, PuSlot& sl)
+{
+  if (sl.stream == ctx->stream || sl.synced_version == ctx->ref_version) return HOP_OK;
+  if (ctx->ref_event_version != ctx->ref_version) {
+    CU(cudaEventRecord(ctx->ref_event, ctx->stream));
+    ctx->ref_event_version = ctx->ref_version;
+  }
+  CU(cudaStreamWaitEvent(sl.stream, ctx->ref_event, 0));
+  sl.synced_version = ctx->ref_version;
+  return HOP_OK;
+}
+
+// slot holding a finished-or-running speculative search for exactly this request, or -1
+int find_cached(HopCtx* ctx, const HopMotionJob& key, const int16_t* org, size_t org_off, int org_stride)
+{
+  for (int i = 1; i < PU_SLOTS; i++) {
+    const PuSlot& sl = ctx->slots_pu[i];
+    if (!sl.cached || sl.ref_version != ctx->ref_version || memcmp(&sl.key, &key, sizeof(HopMotionJob)) != 0) continue;
+    const int16_t* blk = (const int16_t*)(sl.h + PIN_JOB);
+    const int cols = key.search.cols, rows = key.search.rows;
+    bool same = true;
+    for (int r = 0; r < rows && same; r++)
+      same = memcmp(blk + (size_t)r * cols, org + org_off + (size_t)r * org_stride, sizeof(int16_t) * cols) == 0;
+    if (same) return i;
+  }
+  return -1;
 }
 }  // extern "C++"
 
@@ -482,17 +689,20 @@ int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs, const
   if (n == 1 && !ref && jobs[0].cols <= HOP_MAX_PU && jobs[0].rows <= HOP_MAX_PU) {
     // the encoder's call: one PU against the SS mirror
     if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
-    if ((st = pack_single(ctx, jobs[0], org, org_samples))) return st;
+    if ((st = slots_ready(ctx))) return st;
+    PuSlot& sl = ctx->slots_pu[0];
+    if ((st = pack_single(ctx, sl, jobs[0], org, org_samples))) return st;
     HopSearchJob packed;
-    memcpy(&packed, ctx->pin_h, sizeof(packed));
+    memcpy(&packed, sl.h, sizeof(packed));
     const int slices = k1_slices(ctx, 1);
     size_t smem = search_smem_bytes(packed, slices);
-    const unsigned seq = ++ctx->pin_seq;
-    st = search_dev(ctx, 1, (const HopSearchJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                    (HopSearchResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream,
-                    pin_flag_dev(ctx), seq);
+    const unsigned seq = ++sl.seq;
+    st = search_dev(ctx, 1, (const HopSearchJob*)sl.d, slot_org_dev(sl), hop_ref_origin_dev(ctx),
+                    (HopSearchResult*)slot_out_dev(sl), (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream,
+                    slot_flag_dev(sl), seq, 0, nullptr, &sl);
     if (st) return st;
-    return unpack_single(ctx, seq, out);
+    ctx->stats.single_calls++;
+    return unpack_single(ctx, sl, out);
   }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopSearchJob), org, org_samples, ref, ref_samples,
@@ -529,21 +739,26 @@ int hop_pattern_search_gt_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const 
   }
   if (n == 1 && !ref) {
     if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
-    if ((st = pack_single(ctx, jobs[0], org, org_samples))) return st;
-    const unsigned seq = ++ctx->pin_seq;
+    if ((st = slots_ready(ctx))) return st;
+    PuSlot& sl = ctx->slots_pu[0];
+    if ((st = pack_single(ctx, sl, jobs[0], org, org_samples))) return st;
+    const unsigned seq = ++sl.seq;
     int l = 0;
     cudaError_t ce = ctx->use_clusters
-        ? gt_single_launch((const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                           (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                           bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq)
+        ? gt_single_launch((const HopGtJob*)sl.d, slot_org_dev(sl), hop_ref_origin_dev(ctx),
+                           (HopGtResult*)slot_out_dev(sl), max_cols, max_rows, ctx->stream, &l,
+                           bounds_for(ctx, true, 0), slot_flag_dev(sl), seq)
         : cudaErrorNotSupported;
     if (ce == cudaErrorNotSupported)
-      ce = gt_launch(1, (const HopGtJob*)ctx->pin_d, (const int16_t*)(ctx->pin_d + PIN_JOB), hop_ref_origin_dev(ctx),
-                     (HopGtResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                     bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq);
+      ce = gt_launch(1, (const HopGtJob*)sl.d, slot_org_dev(sl), hop_ref_origin_dev(ctx),
+                     (HopGtResult*)slot_out_dev(sl), max_cols, max_rows, ctx->stream, &l,
+                     bounds_for(ctx, true, 0), slot_flag_dev(sl), seq);
     CU(ce);
     ctx->launches += l;
-    return unpack_single(ctx, seq, out);
+    ctx->stats.single_calls++;
+    if ((st = unpack_single(ctx, sl, out))) return st;
+    ctx->stats.candidates += out->n_candidates;
+    return HOP_OK;
   }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopGtJob), org, org_samples, ref, ref_samples,
@@ -655,61 +870,44 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
   if (n < 0 || (n > 0 && (!jobs || !org || !out))) return fail(HOP_ERR_ARG, "NULL argument");
   if (n == 0) return HOP_OK;
   int max_cols = 4, max_rows = 4;
+  for (int i = 0; i < n; i++) {
+    if ((st = motion_job_ok(jobs[i], i))) return st;
+    const HopSearchJob& j = jobs[i].search;
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+  }
+  if (n == 1 && !ref) {
+    // the encoder's call: zero-copy job / block / result, two stream-ordered launches, one wait -- or no launch at
+    // all when a speculative search for exactly this request is already running or done
+    if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
+    if ((st = slots_ready(ctx))) return st;
+    const HopSearchJob& j = jobs[0].search;
+    const size_t need = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+    if (j.org_off < 0 || (size_t)j.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
+    const int hit = find_cached(ctx, motion_key(jobs[0]), org, (size_t)j.org_off, j.org_stride);
+    PuSlot& sl = ctx->slots_pu[hit > 0 ? hit : 0];
+    if (hit > 0) {
+      sl.cached = false;
+      ctx->stats.cache_hits++;
+    } else {
+      ctx->stats.cache_misses++;
+      if ((st = launch_motion_slot(ctx, sl, jobs[0], org, org_samples))) return st;
+    }
+    ctx->stats.single_calls++;
+    st = unpack_single(ctx, sl, out);
+    HOST_STAMP(4);
+    if (st == HOP_OK) ctx->stats.candidates += out->gt.n_candidates;
+    return st;
+  }
   size_t smem = 0;
   const int slices = k1_slices(ctx, n);
   for (int i = 0; i < n; i++) {
-    const HopSearchJob& j = jobs[i].search;
-    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 12 || jobs[i].num_pred < 0 || jobs[i].num_pred > HOP_MAX_PRED)
-      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / num_pred %d", i, j.cols, j.rows, j.bit_depth, jobs[i].num_pred);
-    if (j.cols > max_cols) max_cols = j.cols;
-    if (j.rows > max_rows) max_rows = j.rows;
-    const size_t b = search_smem_bytes(j, slices);
+    const size_t b = search_smem_bytes(jobs[i].search, slices);
     if (b > smem) smem = b;
   }
   if (smem > (size_t)(160 * 1024)) smem = 160 * 1024;
   if ((st = ensure(ctx, ctx->k1res, sizeof(HopSearchResult) * (size_t)n))) return st;
   HopSearchResult* d_k1 = (HopSearchResult*)ctx->k1res.p;
-  if (n == 1 && !ref) {
-    // the encoder's call: zero-copy job / block / result, two stream-ordered launches, one wait
-    if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "ref == NULL but the context has no valid SS reference mirror");
-    HOST_STAMP(0);
-    if ((st = pin_ready(ctx))) return st;
-    HopMotionJob packed = jobs[0];
-    const HopSearchJob& j = jobs[0].search;
-    const size_t need = (size_t)(j.rows - 1) * j.org_stride + j.cols;
-    if (j.org_off < 0 || (size_t)j.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
-    packed.search.org_off = 0;
-    packed.search.org_stride = j.cols;
-    // job (and a small block) as kernel parameters; larger blocks through the mapped buffer
-    static thread_local InlinePu ipu;
-    ipu.use = j.cols * j.rows <= INLINE_ORG_SAMPLES ? 2 : 1;
-    ipu.job = packed;
-    int16_t* dst = ipu.use == 2 ? ipu.org : (int16_t*)(ctx->pin_h + PIN_JOB);
-    for (int r = 0; r < j.rows; r++) memcpy(dst + (size_t)r * j.cols, org + j.org_off + (size_t)r * j.org_stride, sizeof(int16_t) * j.cols);
-    const unsigned seq = ++ctx->pin_seq;
-    const int16_t* d_org = (const int16_t*)(ctx->pin_d + PIN_JOB);
-    HOST_STAMP(1);
-    st = search_dev(ctx, 1, (const HopSearchJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1, (int)smem, ctx->stream,
-                    nullptr, 0, (int)sizeof(HopMotionJob), &ipu);
-    if (st) return st;
-    HOST_STAMP(2);
-    int l = 0;
-    cudaError_t ce = ctx->use_clusters
-        ? motion_single_launch((const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
-                               (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                               bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq, &ipu)
-        : cudaErrorNotSupported;
-    if (ce == cudaErrorNotSupported)
-      ce = motion_tail_launch(1, (const HopMotionJob*)ctx->pin_d, d_org, hop_ref_origin_dev(ctx), d_k1,
-                              (HopMotionResult*)(ctx->pin_d + PIN_JOB + PIN_ORG), max_cols, max_rows, ctx->stream, &l,
-                              bounds_for(ctx, true, 0), pin_flag_dev(ctx), seq, &ipu);
-    CU(ce);
-    ctx->launches += l;
-    HOST_STAMP(3);
-    st = unpack_single(ctx, seq, out);
-    HOST_STAMP(4);
-    return st;
-  }
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopMotionJob), org, org_samples, ref, ref_samples, sizeof(HopMotionResult) * (size_t)n, &d_ref);
   if (st) return st;
@@ -726,11 +924,46 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
   return HOP_OK;
 }
 
+// Speculative searches: enqueue the fused single-PU motion search of every job on a side stream and return at
+// once.  The caller goes on with host work; when it later asks hop_motion_search_batch(n = 1, ref = NULL) for
+// EXACTLY one of these requests (same job fields, same block samples, SS mirror unchanged since) it gets that
+// launch's result -- bit for bit what the synchronous call computes, because it is the same kernels on the same
+// inputs.  Any other request is simply a miss.  Results nobody asks for are dropped when their slot is reused.
+int hop_motion_search_prefetch(HopCtx* ctx, int n, const HopMotionJob* jobs, const int16_t* org, size_t org_samples)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  if (!ctx->plane || !ctx->plane_valid) return fail(HOP_ERR_STATE, "prefetch needs a valid SS reference mirror");
+  if ((st = slots_ready(ctx))) return st;
+  for (int i = 0; i < n; i++) {
+    if ((st = motion_job_ok(jobs[i], i))) return st;
+    const HopSearchJob& j = jobs[i].search;
+    const size_t need = (size_t)(j.rows - 1) * j.org_stride + j.cols;
+    if (j.org_off < 0 || (size_t)j.org_off + need > org_samples) return fail(HOP_ERR_ARG, "original block outside the org buffer");
+    if (find_cached(ctx, motion_key(jobs[i]), org, (size_t)j.org_off, j.org_stride) > 0) continue;   // already on its way
+    PuSlot& sl = ctx->slots_pu[ctx->next_pu_slot];
+    ctx->next_pu_slot = ctx->next_pu_slot + 1 < PU_SLOTS ? ctx->next_pu_slot + 1 : 1;
+    if (sl.cached) {
+      // oldest speculative search, never asked for: its kernels must be through with the slot's buffers
+      if ((st = wait_slot_flag(ctx, sl))) return st;
+      sl.cached = false;
+      ctx->stats.prefetch_dropped++;
+    }
+    if ((st = order_behind_mirror(ctx, sl))) return st;
+    if ((st = launch_motion_slot(ctx, sl, jobs[i], org, org_samples))) return st;
+    sl.cached = true;
+    ctx->stats.prefetched++;
+  }
+  return HOP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // exhaustive sweep
 // ---------------------------------------------------------------------------------------------
 int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                          int max_cols, int max_rows, int cand_begin, int cand_end,
+                          size_t ref_samples, int max_cols, int max_rows, int cand_begin, int cand_end,
                           uint64_t* d_keys, uint32_t* d_counts, void* stream)
 {
   int st = bind(ctx);
@@ -742,6 +975,8 @@ int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int1
     return fail(HOP_ERR_ARG, "candidate slice [%d,%d) outside [0,%d]", cand_begin, cand_end, SWEEP_CANDS);
   if (n == 0) return HOP_OK;
   if ((st = sweep_table_ready(ctx))) return st;
+  RefBounds rb;
+  if ((st = dev_bounds(ctx, d_ref, ref_samples, &rb))) return st;
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   int l = 0;
   CU(sweep_init_launch(n, (unsigned long long*)d_keys, d_counts, s, &l));
@@ -753,7 +988,7 @@ int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int1
     if (chunks > batches) chunks = batches;
     if (chunks < 1) chunks = 1;
     CU(sweep_keys_launch(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks,
-                         (unsigned long long*)d_keys, d_counts, s, &l));
+                         (unsigned long long*)d_keys, d_counts, s, &l, rb));
   }
   ctx->launches += l;
   return HOP_OK;
@@ -795,7 +1030,7 @@ int hop_gt_sweep_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* 
   if ((st = ensure(ctx, ctx->sweep_keys, (sizeof(unsigned long long) + sizeof(unsigned int)) * (size_t)n + 16))) return st;
   uint64_t* d_keys = (uint64_t*)ctx->sweep_keys.p;
   uint32_t* d_counts = (uint32_t*)(d_keys + n);
-  st = hop_gt_sweep_keys_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, max_cols, max_rows,
+  st = hop_gt_sweep_keys_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, ref_samples, max_cols, max_rows,
                              0, SWEEP_CANDS, d_keys, d_counts, ctx->stream);
   if (st) return st;
   st = hop_gt_sweep_finalize_dev(ctx, n, (const HopGtJob*)ctx->jobs.p, d_keys, d_counts, (HopGtResult*)ctx->out.p, ctx->stream);

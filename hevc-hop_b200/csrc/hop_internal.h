@@ -2,9 +2,29 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/hop_gpu.h"
 
 namespace hop {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel, and one process may hold
+// contexts on several GPUs (hop_ctx_create(device)): one bit per device ordinal, one object per kernel instantiation.
+// Setting the attribute twice is harmless, so a race between two host threads only repeats the call.
+struct SmemOptIn {
+  std::atomic<unsigned long long> done{0};
+  template <typename K>
+  cudaError_t ensure(K kernel, int bytes)
+  {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
 
 // addressable sample offsets of the reference buffer handed to a kernel (relative to its base pointer)
 struct RefBounds { long long lo, hi; };

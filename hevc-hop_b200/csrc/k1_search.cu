@@ -377,13 +377,12 @@ cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_or
                           int smem_bytes, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq,
                           int job_stride, const InlinePu* inl)
 {
-  static int attr_set = 0;
+  static SmemOptIn opt_in;
   static const InlinePu no_inline = {};
   const int smem_max = 160 * 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k1_search, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  {
+    cudaError_t e = opt_in.ensure(k1_search, smem_max);
     if (e != cudaSuccess) return e;
-    attr_set = 1;
   }
   if (slices < 1) slices = 1;
   if (slices > K1_MAX_SLICES) slices = K1_MAX_SLICES;

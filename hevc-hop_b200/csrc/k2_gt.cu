@@ -986,12 +986,10 @@ static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d
                                  HopGtResult* d_out, int max_cols, int max_rows, cudaStream_t stream,
                                  unsigned* done_flag, unsigned seq, RefBounds rb)
 {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k2_gt_search<WS, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = opt_in.ensure(k2_gt_search<WS, CFG>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   // CTA = 56 candidates x `groups` tile groups x (2 lanes per 8x8 tile | 1 lane per 4x4 tile)
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
@@ -1050,12 +1048,10 @@ static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16
                                       int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
                                       unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, RefBounds rb)
 {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k2_gt_sweep<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = opt_in.ensure(k2_gt_sweep<WS>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
@@ -1124,12 +1120,11 @@ k5_frac_search(int n_jobs, const HopFracJob* __restrict__ jobs, const int16_t* _
 cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                         HopFracResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches)
 {
-  static bool attr_set = false;
+  static SmemOptIn opt_in;
   const size_t worst = 64 + sizeof(int) * HOP_MAX_PU * HOP_MAX_PU + frac_smem_bytes(HOP_MAX_PU, HOP_MAX_PU);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k5_frac_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)worst);
+  {
+    cudaError_t e = opt_in.ensure(k5_frac_search, (int)worst);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const size_t smem = 64 + sizeof(int) * (((size_t)max_cols * max_rows + 3) & ~(size_t)3) + frac_smem_bytes(max_cols, max_rows);
   k5_frac_search<<<n, 128, smem, stream>>>(n, d_jobs, d_org, d_ref, d_out);
@@ -1371,12 +1366,10 @@ static cudaError_t motion_tail_cfg(int n, const HopMotionJob* d_jobs, const int1
                                    const HopSearchResult* d_k1, HopMotionResult* d_out, int max_cols, int max_rows,
                                    cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb, const InlinePu& ipu)
 {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_motion_tail<WS, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)MOTION_SMEM_CAP);
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = opt_in.ensure(k_motion_tail<WS, CFG>, (int)MOTION_SMEM_CAP);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
@@ -1417,12 +1410,10 @@ template <int WS>
 static cudaError_t gt_cluster_class(const HopGtJob* d_job, const int16_t* d_org, const int16_t* d_ref, HopGtResult* d_out,
                                     int cols, int rows, int csize, int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb)
 {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k2_gt_search_cl<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = opt_in.ensure(k2_gt_search_cl<WS>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   return launch_cluster(k2_gt_search_cl<WS>, 1, csize, threads, gt_smem_bytes(WS, cols, rows), stream,
                         1, d_job, d_org, d_ref, d_out, done_flag, seq, rb);
@@ -1434,12 +1425,10 @@ static cudaError_t motion_cluster_class(const HopMotionJob* d_job, const int16_t
                                         int threads, cudaStream_t stream, unsigned* done_flag, unsigned seq, RefBounds rb,
                                         const InlinePu& ipu)
 {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_motion_tail_cl<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)MOTION_SMEM_CAP);
+  static SmemOptIn opt_in;
+  {
+    cudaError_t e = opt_in.ensure(k_motion_tail_cl<WS>, (int)MOTION_SMEM_CAP);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   return launch_ex(k_motion_tail_cl<WS>, 1, csize, threads, motion_smem_single(WS, cols, rows), stream, ipu.use != 0,
                    1, d_job, d_org, d_ref, d_k1, d_out, done_flag, seq, rb, ipu);

@@ -16,22 +16,32 @@ from .lenslet import lenslet_luma, write_yuv420
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOP_ENCODER = os.path.join(ROOT, "integration", "_build", "TAppEncoderHop")
 CFG = os.path.join(ROOT, "integration", "hop_intra.cfg")
+CFG_LOWDELAY_P = os.path.join(ROOT, "integration", "hop_lowdelay_p.cfg")   # ISS frame + PSS frames (temporal + SS reference)
 
 
-def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=None, keep=False, retries=0):
-    """Encode one synthetic lenslet frame; returns dict(bitstream=bytes, seconds=float, rec=bytes, log=str)."""
+def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=None, keep=False, retries=0,
+           crop_of=None, cfg=None, env_extra=None, frames=1, extra_args=()):
+    """Encode one synthetic lenslet frame; returns dict(bitstream=bytes, seconds=float, rec=bytes, log=str).
+
+    crop_of=(W, H): the frame is the top-left width x height region of the W x H image with this seed;
+    cfg: another encoder configuration file than integration/hop_intra.cfg; env_extra: extra environment;
+    frames > 1: frame k is the lenslet image with seed + k (low-delay P cfg: ISS frame followed by PSS frames)."""
     if not os.path.exists(binary):
         raise FileNotFoundError(binary + " not built (python __graft_entry__.py in the build container)")
     tmp = workdir or tempfile.mkdtemp(prefix="hopenc_")
     yuv = os.path.join(tmp, "in.yuv")
-    write_yuv420(yuv, lenslet_luma(width, height, seed=seed, bit_depth=bit_depth), bit_depth=bit_depth)
-    cmd = [binary, "-c", CFG, "-i", yuv, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", "1",
+    for k in range(frames):
+        write_yuv420(yuv, lenslet_luma(width, height, seed=seed + k, bit_depth=bit_depth, crop_of=crop_of), bit_depth=bit_depth,
+                     append=k > 0)
+    cmd = [binary, "-c", cfg or CFG, "-i", yuv, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", str(frames),
            "-b", "str.bin", "-o", "rec.yuv", "--MIsize=15", "--QP=%d" % qp]
     if bit_depth != 8:
         cmd += ["--InputBitDepth=%d" % bit_depth, "--InternalBitDepth=%d" % bit_depth]
     if width % 8 or height % 8:
         cmd += ["--ConformanceMode=1"]
+    cmd += list(extra_args)
     env = dict(os.environ, HOP_DEVICE=str(device))
+    env.update(env_extra or {})
     t0 = time.perf_counter()
     p = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     dt = time.perf_counter() - t0

@@ -51,7 +51,7 @@ def sweep_on_device(ctx, torch, dist, n, d_jobs, d_org, d_ref, max_cols, max_row
     begin, end = shard_range(HOP_SWEEP_CANDS, rank, world)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     counts = torch.zeros(n, dtype=torch.int32, device=dev)
-    ctx.gt_sweep_keys_dev(n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), max_cols, max_rows, begin, end,
+    ctx.gt_sweep_keys_dev(n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_ref.numel() // 2, max_cols, max_rows, begin, end,
                           keys.data_ptr(), counts.data_ptr(), stream)
     if world > 1:
         # all-ones (nothing scored) is -1 as int64: lift it above every real key before the MIN

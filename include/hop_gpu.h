@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HOP_ABI_VERSION 1
+#define HOP_ABI_VERSION 2
 
 typedef enum HopStatus {
   HOP_OK            = 0,
@@ -237,14 +237,26 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs,
                             const int16_t* org, size_t org_samples,
                             const int16_t* ref, size_t ref_samples,
                             HopMotionResult* out);
+/* Speculative form for the encoder (the first PU of every partition mode of a CU searches the same
+ * SS-reference state, TEncCu.cpp:456-633): enqueue the fused motion search of each job against the SS mirror on a
+ * side stream and return immediately.  A later hop_motion_search_batch(n = 1, ref = NULL) whose request is
+ * IDENTICAL (every job field, every sample of the original block, SS mirror not modified in between) returns that
+ * launch's result instead of launching again; any other request takes the normal path, so correctness never
+ * depends on what was predicted.  Up to HOP_PREFETCH_SLOTS requests are kept; older unclaimed ones are dropped. */
+#define HOP_PREFETCH_SLOTS 15
+int hop_motion_search_prefetch(HopCtx* ctx, int n, const HopMotionJob* jobs,
+                               const int16_t* org, size_t org_samples);
 
 /* ---- device entry points (everything already resident in HBM, asynchronous on `stream`) ---- */
 int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,
                                  const int16_t* d_org, const int16_t* d_ref,
                                  HopSearchResult* d_out, void* stream);
-/* max_cols/max_rows: upper bound of the PU shapes in d_jobs (sizes the shared-memory window and CTA) */
+/* max_cols/max_rows: upper bound of the PU shapes in d_jobs (sizes the shared-memory window and CTA).
+ * ref_samples: addressable int16 samples behind d_ref -- start vectors are raw AMVP vectors whose 2W x 2H window may
+ * leave the buffer (the reference then reads whatever lies beyond its plane); the kernels keep every read inside
+ * [d_ref, d_ref + ref_samples).  Ignored (mirror geometry used) when d_ref == hop_ref_origin_dev(ctx). */
 int hop_pattern_search_gt_batch_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs,
-                                    const int16_t* d_org, const int16_t* d_ref,
+                                    const int16_t* d_org, const int16_t* d_ref, size_t ref_samples,
                                     HopGtResult* d_out, int max_cols, int max_rows, void* stream);
 int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs,
                        const int16_t* d_org, const int16_t* d_cur,
@@ -260,7 +272,7 @@ int hop_dist_batch_dev(HopCtx* ctx, int n, const HopDistJob* d_jobs,
  * ------------------------------------------------------------------------------------------- */
 #define HOP_SWEEP_CANDS 7200
 int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
-                          int max_cols, int max_rows, int cand_begin, int cand_end,
+                          size_t ref_samples, int max_cols, int max_rows, int cand_begin, int cand_end,
                           uint64_t* d_keys, uint32_t* d_counts /* may be NULL */, void* stream);
 int hop_gt_sweep_finalize_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const uint64_t* d_keys,
                               const uint32_t* d_counts /* may be NULL */, HopGtResult* d_out, void* stream);
@@ -270,6 +282,17 @@ int hop_gt_sweep_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* 
 
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 uint64_t hop_ctx_launch_count(HopCtx* ctx);
+
+/* Counters of the single-PU (in-encoder) path since the context was created. */
+typedef struct HopCtxStats {
+  uint64_t single_calls;      /* n = 1 calls against the SS mirror (search, GT or fused motion search)           */
+  uint64_t cache_hits;        /* ... of the fused kind answered by a speculative search                            */
+  uint64_t cache_misses;      /* ... that launched their own kernels                                               */
+  uint64_t prefetched;        /* speculative searches enqueued by hop_motion_search_prefetch                       */
+  uint64_t prefetch_dropped;  /* ... whose result was never asked for and whose slot was reused                    */
+  uint64_t candidates;        /* HOP candidates warped + scored for the single-PU calls that returned (n_candidates) */
+} HopCtxStats;
+int hop_ctx_stats(HopCtx* ctx, HopCtxStats* out);
 
 /* ALU peak probes for the roofline: run a dependent-free instruction loop on every
  * SM and return achieved Gop/s (lane-operations) for the named pipe.

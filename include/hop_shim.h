@@ -20,21 +20,21 @@ namespace hopshim {
 
 /* HOP_STATS=1: wall time spent inside the library per entry point, printed when the encoder exits */
 struct Stats {
-  double   sec[4];
-  unsigned long long calls[4];
+  double   sec[5];
+  unsigned long long calls[5];
   double   shape_sec[2][17][17];               // [K1|K2][cols/4][rows/4]
   unsigned long long shape_calls[2][17][17];
   bool     on;
   Stats() : on(getenv("HOP_STATS") != NULL)
   {
-    for (int i = 0; i < 4; i++) { sec[i] = 0; calls[i] = 0; }
+    for (int i = 0; i < 5; i++) { sec[i] = 0; calls[i] = 0; }
     for (int k = 0; k < 2; k++) for (int a = 0; a < 17; a++) for (int b = 0; b < 17; b++) { shape_sec[k][a][b] = 0; shape_calls[k][a][b] = 0; }
   }
   ~Stats()
   {
     if (!on) return;
-    static const char* name[4] = {"xPatternSearch", "xPatternSearchGT", "refUpdate", "refReset"};
-    for (int i = 0; i < 4; i++)
+    static const char* name[5] = {"xPatternSearch", "xPatternSearchGT", "refUpdate", "refReset+create", "prefetch"};
+    for (int i = 0; i < 5; i++)
       fprintf(stderr, "hopshim: %-18s %9llu calls %9.3f s (%.1f us/call)\n", name[i], calls[i], sec[i],
               calls[i] ? 1e6 * sec[i] / calls[i] : 0.0);
     for (int k = 0; k < 2; k++) for (int a = 0; a < 17; a++) for (int b = 0; b < 17; b++)
@@ -64,7 +64,8 @@ struct State {
   const Pel* buf_lo;       // first / one-past-last host sample of that plane incl. margins
   const Pel* buf_hi;
   int        stride;
-  State() : ctx(NULL), origin(NULL), buf_lo(NULL), buf_hi(NULL), stride(0) {}
+  bool       recording;    // inside prefetchBegin()/prefetchEnd(): searches are enqueued speculatively, not awaited
+  State() : ctx(NULL), origin(NULL), buf_lo(NULL), buf_hi(NULL), stride(0), recording(false) {}
 };
 
 inline State& state() { static State s; return s; }
@@ -77,24 +78,66 @@ inline void check(int status, const char* what)
   }
 }
 
+/* HOP_FUSED=0 keeps the three stages as separate calls (fractional refinement on the host) */
+inline bool fused() { static int f = -1; if (f < 0) { const char* e = getenv("HOP_FUSED"); f = (e && e[0] == '0') ? 0 : 1; } return f != 0; }
+
 inline HopCtx* ctx()
 {
   State& s = state();
   if (!s.ctx) {
     const char* dev = getenv("HOP_DEVICE");
+    Timer tm(3);
     check(hop_ctx_create(dev ? atoi(dev) : 0, &s.ctx), "hop_ctx_create");
   }
   return s.ctx;
 }
 
-/* After TComSlice::setRefPicList wired the SS reference of an ISS slice (TEncGOP.cpp:794): the plane was
- * reset to NOT_VALID and border-extended on the host; mirror it as it is. */
+/* TEncTop::create (TEncTop.cpp:89-110): one context per encoder instance = per GPU (HOP_DEVICE selects it). */
+inline void create() { ctx(); }
+
+/* TEncTop::destroy (TEncTop.cpp:204-213): release the context; HOP_STATS=1 prints what the single-PU path did. */
+inline void destroy()
+{
+  State& s = state();
+  if (!s.ctx) return;
+  if (stats().on) {
+    HopCtxStats cs;
+    if (hop_ctx_stats(s.ctx, &cs) == HOP_OK) {
+      const double gpu_s = stats().sec[0] + stats().sec[1] + stats().sec[4];
+      fprintf(stderr, "hopshim: single-PU calls %llu  cache hits %llu  misses %llu  prefetched %llu  dropped %llu\n",
+              (unsigned long long)cs.single_calls, (unsigned long long)cs.cache_hits, (unsigned long long)cs.cache_misses,
+              (unsigned long long)cs.prefetched, (unsigned long long)cs.prefetch_dropped);
+      fprintf(stderr, "hopshim: HOP candidates scored for the encoder %llu in %.3f s of search calls = %.3g candidates/s in-encoder\n",
+              (unsigned long long)cs.candidates, gpu_s, gpu_s > 0 ? (double)cs.candidates / gpu_s : 0.0);
+    }
+  }
+  hop_ctx_destroy(s.ctx);
+  s = State();
+}
+
+/* The SS reference is not (re)wired for this slice: nothing may be searched on a stale mirror. */
+inline void refInvalidate() { State& s = state(); s.origin = NULL; s.buf_lo = NULL; s.buf_hi = NULL; }
+
+/* Speculation window (TEncCu::xCompressCU, before the inter modes of a CU are tried, TEncCu.cpp:456-633): the
+ * caller runs the reference's own xCheckRDCostInter for the partition modes it is going to try; inside the window
+ * xMotionSearchSS does not wait -- it enqueues the search of the mode's FIRST PU (whose inputs depend on nothing
+ * inside the CU) and reports "no valid vector", which makes predInterSearch return at once (TEncSearch.cpp:3964).
+ * The real pass afterwards builds the same requests and finds the results waiting. */
+inline bool prefetchEnabled() { static int f = -1; if (f < 0) { const char* e = getenv("HOP_PREFETCH"); f = (e && e[0] == '0') ? 0 : 1; } return f != 0 && fused(); }
+inline bool prefetchAmp()     { static int f = -1; if (f < 0) { const char* e = getenv("HOP_PREFETCH_AMP"); f = (e && e[0] == '0') ? 0 : 1; } return f != 0; }
+inline void prefetchBegin() { state().recording = true; }
+inline void prefetchEnd()   { state().recording = false; }
+
+/* After TComSlice::setRefPicList wired the SS reference of an ISS or PSS slice (TEncGOP.cpp:794,
+ * TComSlice.cpp:241-254, 366-377, 496-502): the plane was reset to NOT_VALID and border-extended on the host;
+ * mirror it as it is. */
 inline void refReset(TComPicYuv* pic)
 {
+  HopCtx* c = ctx();
   Timer tm(3);
   State& s = state();
   const int m = pic->getLumaMargin(), w = pic->getWidth(), h = pic->getHeight();
-  check(hop_ref_create(ctx(), w, h, m), "hop_ref_create");
+  check(hop_ref_create(c, w, h, m), "hop_ref_create");
   const size_t samples = (size_t)pic->getStride() * (h + 2 * m);
   check(hop_ref_upload(s.ctx, pic->getBufY(), samples), "hop_ref_upload");
   s.origin = pic->getLumaAddr();
@@ -112,9 +155,6 @@ inline void refUpdate(TComPicYuv* pic, int x, int y, int w, int h)
   check(hop_ref_update(s.ctx, x, y, w, h, pic->getLumaAddr() + (size_t)y * pic->getStride() + x, pic->getStride()),
         "hop_ref_update");
 }
-
-/* HOP_FUSED=0 keeps the three stages as separate calls (fractional refinement on the host) */
-inline bool fused() { static int f = -1; if (f < 0) { const char* e = getenv("HOP_FUSED"); f = (e && e[0] == '0') ? 0 : 1; } return f != 0; }
 
 inline bool owns(const Pel* p) { const State& s = state(); return s.ctx && p >= s.buf_lo && p < s.buf_hi; }
 
@@ -208,7 +248,6 @@ inline bool xMotionSearchSS(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* pi
                             TComMv& rcMv, UInt& ruiCost, TComMv& rcMvHalf, TComMv& rcMvQter,
                             TComMv& rcGT0, TComMv& rcGT1, TComMv& rcGT2, TComMv& rcGT3, Bool& gtFlag, TComMv* ssBestCand)
 {
-  Timer tm(1, pcPatternKey->getROIYWidth(), pcPatternKey->getROIYHeight());
   State& s = state();
   HopMotionJob mj;
   HopSearchJob& j = mj.search;
@@ -235,9 +274,16 @@ inline bool xMotionSearchSS(TComDataCU* pcCU, TComPattern* pcPatternKey, Pel* pi
   }
   HopMotionResult r;
   const size_t org_samples = (size_t)(j.rows - 1) * j.org_stride + j.cols;
-  check(hop_motion_search_batch(s.ctx, 1, &mj, pcPatternKey->getROIY(), org_samples, NULL, 0, &r), "hop_motion_search_batch");
   gtFlag = false;
   rcGT0.set(0, 0); rcGT1.set(0, 0); rcGT2.set(0, 0); rcGT3.set(0, 0);
+  if (s.recording) {                                                          /* speculation window: enqueue, do not wait */
+    Timer tp(4);
+    check(hop_motion_search_prefetch(s.ctx, 1, &mj, pcPatternKey->getROIY(), org_samples), "hop_motion_search_prefetch");
+    ruiCost = MAX_UINT;
+    return false;
+  }
+  Timer tm(1, pcPatternKey->getROIYWidth(), pcPatternKey->getROIYHeight());
+  check(hop_motion_search_batch(s.ctx, 1, &mj, pcPatternKey->getROIY(), org_samples, NULL, 0, &r), "hop_motion_search_batch");
   if (!r.search.found) { ruiCost = MAX_UINT; return false; }               /* :6356-6360 */
   rcMv.set(r.search.mv.hor, r.search.mv.ver);                              /* :6363 */
   ssBestCand[0].set(r.search.mv.hor, r.search.mv.ver);

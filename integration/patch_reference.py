@@ -8,8 +8,10 @@ directory (never into the repo): the patch is the one INTEGRATION.md documents -
 
   TLibCommon/TComRdCost.h      + three read-only accessors of the motion-cost state
   TLibEncoder/TEncSearch.cpp   bodies of xPatternSearch / xPatternSearchGT forward to hop_shim.h
-  TLibEncoder/TEncCu.cpp       xCopyYuv2SSRef notifies the device mirror after the CU copy
+  TLibEncoder/TEncCu.cpp       xCopyYuv2SSRef notifies the device mirror after the CU copy; xCompressCU opens a
+                               speculation window in front of a CU's inter modes (first PU of every mode)
   TLibEncoder/TEncGOP.cpp      the mirror is (re)loaded when the SS reference is wired to the slice
+  TLibEncoder/TEncTop.cpp      context created / destroyed with the encoder
 
 Every edit is anchored on an exact line of the reference; the script fails loudly if an anchor moved.
 """
@@ -96,6 +98,26 @@ def main():
     t = patch(t,
               "    rpcPic->getPicYuvRec()->setBorderExtension(false);\n    rpcPic->getPicYuvRec()->extendPicBorder();\n",
               "    hopshim::refUpdate( rpcPic->getPicYuvRec(), uiLPelX, uiTPelY, g_uiMaxCUWidth>>uiDepth, g_uiMaxCUHeight>>uiDepth );   // libhopgpu\n")
+    # speculation window: the reference's own xCheckRDCostInter is run once per partition mode
+    # with the shim in "enqueue, do not wait" mode -- it derives the AMVP list and search window of the mode's
+    # first PU exactly as the real pass will, hands the request to the GPU and returns through the reference's
+    # own "no valid SS vector" exit; initEstData() then restores the CU as it does between any two modes.
+    # ISS slices only: a PSS slice would run its temporal-reference search for real inside the window.
+    t = patch(t,
+              "      // do inter modes, SKIP and 2Nx2N\n      if( rpcBestCU->getSlice()->getSliceType() != I_SLICE )\n      {\n",
+              "        // libhopgpu: enqueue the motion search of the first PU of every partition mode this CU is going to try\n"
+              "        if ( hopshim::prefetchEnabled() && rpcBestCU->getSlice()->isIntraSS() )\n"
+              "        {\n"
+              "          static const PartSize aeHopModes[7] = { SIZE_2Nx2N, SIZE_Nx2N, SIZE_2NxN, SIZE_2NxnU, SIZE_2NxnD, SIZE_nLx2N, SIZE_nRx2N };\n"
+              "          const Int iHopModes = ( hopshim::prefetchAmp() && pcPic->getSlice(0)->getSPS()->getAMPAcc(uiDepth) && rpcBestCU->getWidth(0) != 64 ) ? 7 : 3;\n"
+              "          hopshim::prefetchBegin();\n"
+              "          for ( Int iHopMode = 0; iHopMode < iHopModes; iHopMode++ )\n"
+              "          {\n"
+              "            xCheckRDCostInter( rpcBestCU, rpcTempCU, aeHopModes[iHopMode] );\n"
+              "          }\n"
+              "          hopshim::prefetchEnd();\n"
+              "          rpcTempCU->initEstData( uiDepth, iQP, bIsLosslessMode );\n"
+              "        }\n")
     wr("TLibEncoder/TEncCu.cpp", t)
 
     # --- TEncGOP.cpp ------------------------------------------------------------------------------
@@ -103,8 +125,17 @@ def main():
     t = patch(t, '#include "TEncGOP.h"\n', '#include "hop_shim.h"   // libhopgpu\n')
     t = patch(t,
               "    pcSlice->setRefPicList ( rcListPic, m_pcEncTop->getSSRefEncoder() );\n",
-              "    if ( pcSlice->isIntraSS() ) hopshim::refReset( m_pcEncTop->getSSRefEncoder()->getPicYuvRec() );   // libhopgpu\n")
+              "    // libhopgpu: the SS reference was reset and re-extended for an ISS / PSS slice: (re)load its device mirror\n"
+              "    if ( pcSlice->isIntraSS() || pcSlice->isInterPSS() ) hopshim::refReset( m_pcEncTop->getSSRefEncoder()->getPicYuvRec() );\n"
+              "    else hopshim::refInvalidate();\n")
     wr("TLibEncoder/TEncGOP.cpp", t)
+
+    # --- TEncTop.cpp ------------------------------------------------------------------------------
+    t = rd("TLibEncoder/TEncTop.cpp")
+    t = patch(t, '#include "TEncTop.h"\n', '#include "hop_shim.h"   // libhopgpu\n')
+    t = patch(t, "Void TEncTop::create ()\n{\n", "  hopshim::create();    // libhopgpu: one context per encoder instance\n")
+    t = patch(t, "Void TEncTop::destroy ()\n{\n", "  hopshim::destroy();   // libhopgpu\n")
+    wr("TLibEncoder/TEncTop.cpp", t)
     print("patched sources written to", out)
 
 

@@ -33,3 +33,68 @@ def test_unfused_call_path_is_identical_too(monkeypatch):
     monkeypatch.setenv("HOP_FUSED", "0")
     hop = encoder.encode(encoder.HOP_ENCODER, 128, 64, seed=3)
     assert hop["bitstream"] == ref["bitstream"] and hop["rec"] == ref["rec"] and hop["trace"] == ref["trace"]
+
+
+# ---- golden bitstreams of the CPU reference at the sizes BASELINE.json quotes --------------------------------
+# tests/golden/encode_golden.json is written by tests/golden/make_encode_golden.py in the build container (the
+# unmodified reference with the reference's OWN cfg files; 13 CPU-minutes for the 1024x1024 frame); here the GPU-backed
+# encoder re-encodes the same frames with the repo's cfg files.  GPU runs get no retries.
+import json  # noqa: E402
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encode_golden.json")
+_golden = json.load(open(_GOLDEN)) if os.path.exists(_GOLDEN) else {}
+
+
+def _encode_case(rec, **kw):
+    args = dict(seed=rec["seed"], qp=rec["qp"], bit_depth=rec.get("bit_depth", 8), frames=rec.get("frames", 1))
+    if rec.get("crop_of"):
+        args["crop_of"] = tuple(rec["crop_of"])
+    if rec.get("lowdelay_p"):
+        args["cfg"] = encoder.CFG_LOWDELAY_P
+    args.update(kw)
+    return encoder.encode(encoder.HOP_ENCODER, rec["width"], rec["height"], **args)
+
+
+@pytest.mark.skipif(not os.path.exists(encoder.HOP_ENCODER), reason="TAppEncoderHop not built")
+@pytest.mark.parametrize("name", sorted(_golden))
+def test_golden_bitstreams(name):
+    """configs[0] (1024x1024 QP 32), a region of the configs[1] image at QP 22/27/32/37, Main10, and ISS + PSS frames:
+    str.bin and rec.yuv byte-identical to the CPU reference's."""
+    rec = _golden[name]
+    hop = _encode_case(rec)
+    assert len(hop["bitstream"]) == rec["bitstream_bytes"]
+    assert hashlib.md5(hop["bitstream"]).hexdigest() == rec["bitstream_md5"]
+    assert hashlib.md5(hop["rec"]).hexdigest() == rec["rec_md5"]
+
+
+@pytest.mark.skipif(not have, reason="encoder binaries not built (need /root/reference at build time)")
+def test_pss_slices_search_the_reset_mirror():
+    """Low-delay P: the SS reference is reset to NOT_VALID for EVERY ISS / PSS slice (TComSlice.cpp:241-254); the
+    mirror has to follow, or PSS searches would run on the previous picture's reconstruction."""
+    ref = _oracle.encode_reference(128, 64, seed=4, frames=2, cfg=encoder.CFG_LOWDELAY_P)
+    hop = encoder.encode(encoder.HOP_ENCODER, 128, 64, seed=4, frames=2, cfg=encoder.CFG_LOWDELAY_P, env_extra={"HOP_STATS": "1"})
+    assert hop["bitstream"] == ref["bitstream"] and hop["rec"] == ref["rec"] and hop["trace"] == ref["trace"]
+    assert "refReset+create" in hop["log"]
+
+
+def _stat(log, key):
+    import re
+    m = re.search(key + r"\s+(\d+)", log)
+    return int(m.group(1)) if m else None
+
+
+@pytest.mark.skipif(not os.path.exists(encoder.HOP_ENCODER), reason="TAppEncoderHop not built")
+def test_speculative_first_pu_searches_are_used_and_change_nothing():
+    """the first PU of every partition mode of a CU is searched ahead of time.  With and without the
+    speculation window the encoder writes the same bytes; with it, most first-PU requests are answered from the cache."""
+    on = encoder.encode(encoder.HOP_ENCODER, 192, 128, seed=9, env_extra={"HOP_STATS": "1"})
+    off = encoder.encode(encoder.HOP_ENCODER, 192, 128, seed=9, env_extra={"HOP_STATS": "1", "HOP_PREFETCH": "0"})
+    noamp = encoder.encode(encoder.HOP_ENCODER, 192, 128, seed=9, env_extra={"HOP_STATS": "1", "HOP_PREFETCH_AMP": "0"})
+    for other in (off, noamp):
+        assert on["bitstream"] == other["bitstream"] and on["rec"] == other["rec"] and on["trace"] == other["trace"]
+    calls, hits, misses = _stat(on["log"], "single-PU calls"), _stat(on["log"], "cache hits"), _stat(on["log"], "misses")
+    assert calls == hits + misses and _stat(off["log"], "cache hits") == 0 and _stat(off["log"], "single-PU calls") == calls
+    assert hits > 0.4 * calls, (calls, hits, misses)          # 18 k of 30.6 k calls are first PUs on a 512x512 image
+    assert _stat(noamp["log"], "cache hits") <= hits
+    cand = _stat(on["log"], "HOP candidates scored for the encoder")
+    assert cand == _stat(off["log"], "HOP candidates scored for the encoder") and cand > 0

@@ -177,3 +177,121 @@ def test_gpu_single_call_random_start_vectors(ctx):
         m2 = mj.copy(); s2 = m2["search"]; s2["ref_off"] += m * stride + m; m2["search"] = s2
         want = _oracle.motion_search(m2, b.org, host.reshape(-1))
         assert got.tobytes() == want.tobytes(), (it, c, r, int(mj["num_pred"][0]))
+
+
+def _cu_mirror(ctx, seed, pic_w=192, pic_h=160, m=80, px=96, py=96):
+    """A picture whose causal area (rows above (px, py) and the band to its left) is coded; returns host plane + stride."""
+    rng = np.random.default_rng(seed)
+    ctx.ref_create(pic_w, pic_h, m)
+    host = np.full((pic_h + 2 * m, pic_w + 2 * m), -1, dtype=np.int16)
+    img = rng.integers(0, 256, size=(pic_h, pic_w)).astype(np.int16)
+    host[m:m + py, m:m + pic_w] = img[:py]
+    host[m + py:m + pic_h, m:m + px] = img[py:, :px]
+    _oracle.extend_border_oracle(host, pic_w, pic_h, m)
+    ctx.ref_upload(host)
+    return host, pic_w + 2 * m, m, img
+
+
+def _cu_jobs(stride, seed, px=96, py=96):
+    """The first-PU requests of one 32x32 CU's partition modes (2Nx2N, Nx2N, 2NxN, four AMP shapes) + two of an 8x8 CU."""
+    out = []
+    for k, (c, r) in enumerate([(32, 32), (16, 32), (32, 16), (32, 8), (32, 24), (8, 32), (24, 32), (8, 8), (4, 8), (8, 4)]):
+        b = PuBatch(c, r, 1, seed=seed * 50 + k, sr=16, n_start=3)
+        mj = b.motion_jobs()
+        s = mj["search"]
+        s["ref_stride"] = stride; s["ref_off"] = py * stride + px
+        s["rng_left"], s["rng_right"], s["rng_top"], s["rng_bottom"] = -70, 40, -70, -4
+        mj["search"] = s
+        mj["amvp"]["hor"][:, 0] = -40 * 4 + k; mj["amvp"]["ver"][:, 0] = -50 * 4
+        mj["amvp"]["hor"][:, 1] = -12 * 4; mj["amvp"]["ver"][:, 1] = -30 * 4 - k
+        out.append((mj, b.org.copy()))
+    return out
+
+
+def _want(mj, org, host, stride, m):
+    m2 = mj.copy(); s2 = m2["search"]; s2["ref_off"] += m * stride + m; m2["search"] = s2
+    return _oracle.motion_search(m2, org, host.reshape(-1))
+
+
+@pytest.mark.gpu
+def test_gpu_speculative_searches_hit_only_identical_requests(ctx):
+    """hop_motion_search_prefetch + hop_motion_search_batch(n = 1, ref = NULL): a request is answered from a
+    speculative launch only when job, block and SS-mirror state are identical; everything else launches afresh;
+    every answer equals the oracle."""
+    host, stride, m, img = _cu_mirror(ctx, seed=21)
+    for rep in range(6):
+        jobs = _cu_jobs(stride, seed=rep)
+        st0 = ctx.stats()
+        for mj, org in jobs:                                   # the speculation window of a CU
+            ctx.motion_prefetch(mj, org)
+        order = list(range(len(jobs)))
+        if rep % 2:
+            order.reverse()                                    # consumed in any order
+        for i in order:
+            mj, org = jobs[i]
+            assert ctx.motion_search(mj, org, None).tobytes() == _want(mj, org, host, stride, m).tobytes(), (rep, i)
+        st1 = ctx.stats()
+        assert st1["cache_hits"] - st0["cache_hits"] == len(jobs) and st1["cache_misses"] == st0["cache_misses"]
+        assert st1["prefetched"] - st0["prefetched"] == len(jobs)
+    # near misses: one job field, one block sample
+    jobs = _cu_jobs(stride, seed=40)
+    for mj, org in jobs:
+        ctx.motion_prefetch(mj, org)
+    st0 = ctx.stats()
+    mj, org = jobs[0]
+    mj2 = mj.copy(); c2 = mj2["search"]["cost"]; c2["pred"]["hor"] += 4; s2 = mj2["search"]; s2["cost"] = c2; mj2["search"] = s2
+    assert ctx.motion_search(mj2, org, None).tobytes() == _want(mj2, org, host, stride, m).tobytes()
+    org2 = org.copy(); org2[5] ^= 1
+    mj, _ = jobs[1]
+    assert ctx.motion_search(mj, org2, None).tobytes() == _want(mj, org2, host, stride, m).tobytes()
+    st1 = ctx.stats()
+    assert st1["cache_misses"] - st0["cache_misses"] == 2 and st1["cache_hits"] == st0["cache_hits"]
+    # the mirror changes (a CU is committed): everything enqueued before is stale
+    blk = img[96:104, 96:104].copy()
+    ctx.ref_update(96, 96, blk)
+    host[m + 96:m + 104, m + 96:m + 104] = blk
+    _oracle.extend_border_oracle(host, 192, 160, m)
+    st0 = ctx.stats()
+    for i in (2, 3, 7):
+        mj, org = jobs[i]
+        assert ctx.motion_search(mj, org, None).tobytes() == _want(mj, org, host, stride, m).tobytes(), i
+    st1 = ctx.stats()
+    assert st1["cache_misses"] - st0["cache_misses"] == 3 and st1["cache_hits"] == st0["cache_hits"]
+    # more requests than slots: the oldest are dropped, the answers stay right
+    many = _cu_jobs(stride, seed=41) + _cu_jobs(stride, seed=42)
+    for mj, org in many:
+        ctx.motion_prefetch(mj, org)
+    for mj, org in many:
+        assert ctx.motion_search(mj, org, None).tobytes() == _want(mj, org, host, stride, m).tobytes()
+    assert ctx.stats()["prefetch_dropped"] > 0
+    # a duplicate request inside one window is enqueued once
+    st0 = ctx.stats()
+    mj, org = many[0]
+    ctx.motion_prefetch(mj, org); ctx.motion_prefetch(mj, org)
+    assert ctx.stats()["prefetched"] - st0["prefetched"] == 1
+    assert ctx.motion_search(mj, org, None).tobytes() == _want(mj, org, host, stride, m).tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_two_contexts_on_two_devices_in_one_process():
+    """One process, one context per GPU (the ABI allows it): kernels that opt in to more than 48 KB of dynamic shared
+    memory must be configured on EVERY device they run on (per-device function attributes)."""
+    lib = hop.load_library()
+    if lib.hop_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctxs = [hop.HopContext(d) for d in (0, 1)]
+    try:
+        for c, r in [(64, 64), (32, 32), (8, 8)]:
+            b = PuBatch(c, r, 3, seed=c + r, sr=128 if c == 64 else 32, n_start=3)
+            want_k1 = _oracle.oracle().pattern_search(b.search_jobs, b.org, b.ref)
+            want_k2 = _oracle.oracle().pattern_search_gt(b.gt_jobs, b.org, b.ref)
+            mj = b.motion_jobs()
+            want_m = _oracle.motion_search(mj, b.org, b.ref)
+            for cx in ctxs:
+                assert cx.pattern_search(b.search_jobs, b.org, b.ref).tobytes() == want_k1.tobytes()
+                assert cx.pattern_search_gt(b.gt_jobs, b.org, b.ref).tobytes() == want_k2.tobytes()
+                assert cx.motion_search(mj, b.org, b.ref).tobytes() == want_m.tobytes()
+                assert cx.gt_sweep(b.gt_jobs[:1], b.org, b.ref).tobytes() == _oracle.gt_sweep(b.gt_jobs[:1], b.org, b.ref).tobytes()
+    finally:
+        for cx in ctxs:
+            cx.close()

@@ -26,7 +26,7 @@ def gt_assert_equal(a, b, extras=True):
 
 
 def test_library_loaded_and_device_is_blackwell(ctx):
-    assert ctx.lib.hop_abi_version() == 1
+    assert ctx.lib.hop_abi_version() == 2
     assert ctx.lib.hop_device_count() >= 1
 
 
@@ -38,6 +38,25 @@ def test_k1_matches_oracle(ctx, shape):
     got = ctx.pattern_search(b.search_jobs, b.org, b.ref)
     want = orc.pattern_search(b.search_jobs, b.org, b.ref)
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (16, 16), (32, 32), (64, 64), (64, 16), (16, 12), (4, 8)])
+@pytest.mark.parametrize("n", [1, 3, 300])
+def test_k1_matches_oracle_full_range(ctx, shape, n):
+    """SearchRange 128 (cfg/3DHencoder_intra_main.cfg:31), the window bench.py's K1 leg is quoted on: 257 x 125
+    positions per PU.  n = 1 and 3 cut one PU's window into 32 row slices (the in-encoder geometry), n = 300 gives one
+    slice per PU with the 160 KB shared-memory cap deciding between byte path and generic path."""
+    c, r = shape
+    if n == 300 and c * r >= 2048:
+        n = 150                                  # oracle time on the box's host cores; still one slice per PU
+    orc = _oracle.oracle()
+    b = PuBatch(c, r, n, seed=c * 7 + r + n, sr=128)
+    j = b.search_jobs[0]
+    assert (j["rng_right"] - j["rng_left"] + 1, j["rng_bottom"] - j["rng_top"] + 1) == (257, 125)
+    got = ctx.pattern_search(b.search_jobs, b.org, b.ref)
+    want = orc.pattern_search(b.search_jobs, b.org, b.ref)
+    assert got.tobytes() == want.tobytes()
+    assert want["found"].all()
 
 
 @pytest.mark.parametrize("shape", ALL_SHAPES)
@@ -237,7 +256,7 @@ def test_device_entry_points_with_torch_buffers(ctx):
     torch.cuda.synchronize()                     # uploads done before the context's stream reads them
     stream = ctx.stream
     ctx.pattern_search_dev(b.n, d_sj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_so.data_ptr(), stream)
-    ctx.pattern_search_gt_dev(b.n, d_gj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_go.data_ptr(), 16, 16, stream)
+    ctx.pattern_search_gt_dev(b.n, d_gj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), b.ref.size, d_go.data_ptr(), 16, 16, stream)
     torch.cuda.synchronize()
     so = d_so.cpu().numpy().view(hop.SEARCH_RES_DT)
     go = d_go.cpu().numpy().view(hop.GT_RES_DT)

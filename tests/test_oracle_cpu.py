@@ -206,7 +206,7 @@ def test_abi_exports_every_declared_symbol():
     bound = {name for name, _, _ in hop.ABI}
     assert declared == bound, (declared ^ bound)
     lib = hop.load_library()       # raises if libhopgpu.so is missing or a symbol is not exported
-    assert lib.hop_abi_version() == 1
+    assert lib.hop_abi_version() == 2
     assert lib.hop_shape_supported(16, 12) == 1 and lib.hop_shape_supported(4, 4) == 0 and lib.hop_shape_supported(20, 8) == 0
 
 

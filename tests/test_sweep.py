@@ -130,7 +130,7 @@ def test_gpu_sharded_keys_min_equals_full_sweep(ctx, world):
         begin, end = sweep.shard_range(hop.HOP_SWEEP_CANDS, rank, world)
         keys = torch.empty(b.n, dtype=torch.int64, device=dev)
         cnt = torch.zeros(b.n, dtype=torch.int32, device=dev)
-        ctx.gt_sweep_keys_dev(b.n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), 16, 16, begin, end,
+        ctx.gt_sweep_keys_dev(b.n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), b.ref.size, 16, 16, begin, end,
                               keys.data_ptr(), cnt.data_ptr(), ctx.stream)
         ctx.sync()
         keys = torch.where(keys < 0, torch.full_like(keys, int(sweep.NONE_KEY)), keys)
