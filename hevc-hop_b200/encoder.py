@@ -20,7 +20,7 @@ CFG_LOWDELAY_P = os.path.join(ROOT, "integration", "hop_lowdelay_p.cfg")   # ISS
 
 
 def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=None, keep=False, retries=0,
-           crop_of=None, cfg=None, env_extra=None, frames=1, extra_args=()):
+           crop_of=None, cfg=None, env_extra=None, frames=1, extra_args=(), launcher=None):
     """Encode one synthetic lenslet frame; returns dict(bitstream=bytes, seconds=float, rec=bytes, log=str).
 
     crop_of=(W, H): the frame is the top-left width x height region of the W x H image with this seed;
@@ -40,6 +40,8 @@ def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=
     if width % 8 or height % 8:
         cmd += ["--ConformanceMode=1"]
     cmd += list(extra_args)
+    if launcher:                      # e.g. ["taskset", "-c", "3"]
+        cmd = list(launcher) + cmd
     env = dict(os.environ, HOP_DEVICE=str(device))
     env.update(env_extra or {})
     t0 = time.perf_counter()

@@ -15,26 +15,27 @@
 #include <cstdlib>
 #include <ctime>
 #include "hop_gpu.h"
+#include "hop_border.h"
 
 namespace hopshim {
 
 /* HOP_STATS=1: wall time spent inside the library per entry point, printed when the encoder exits */
 struct Stats {
-  double   sec[5];
-  unsigned long long calls[5];
+  double   sec[6];
+  unsigned long long calls[6];
   double   shape_sec[2][17][17];               // [K1|K2][cols/4][rows/4]
   unsigned long long shape_calls[2][17][17];
   bool     on;
   Stats() : on(getenv("HOP_STATS") != NULL)
   {
-    for (int i = 0; i < 5; i++) { sec[i] = 0; calls[i] = 0; }
+    for (int i = 0; i < 6; i++) { sec[i] = 0; calls[i] = 0; }
     for (int k = 0; k < 2; k++) for (int a = 0; a < 17; a++) for (int b = 0; b < 17; b++) { shape_sec[k][a][b] = 0; shape_calls[k][a][b] = 0; }
   }
   ~Stats()
   {
     if (!on) return;
-    static const char* name[5] = {"xPatternSearch", "xPatternSearchGT", "refUpdate", "refReset+create", "prefetch"};
-    for (int i = 0; i < 5; i++)
+    static const char* name[6] = {"xPatternSearch", "xPatternSearchGT", "refUpdate", "refReset+create", "prefetch", "hostBorder"};
+    for (int i = 0; i < 6; i++)
       fprintf(stderr, "hopshim: %-18s %9llu calls %9.3f s (%.1f us/call)\n", name[i], calls[i], sec[i],
               calls[i] ? 1e6 * sec[i] / calls[i] : 0.0);
     for (int k = 0; k < 2; k++) for (int a = 0; a < 17; a++) for (int b = 0; b < 17; b++)
@@ -146,11 +147,29 @@ inline void refReset(TComPicYuv* pic)
   s.stride = pic->getStride();
 }
 
-/* After TEncCu::xCopyYuv2SSRef copied a CU's reconstruction and re-extended the borders (TEncCu.cpp:1694-1696) */
-inline void refUpdate(TComPicYuv* pic, int x, int y, int w, int h)
+/* Tail of TEncCu::xCopyYuv2SSRef after copyToPicYuv put a CU's reconstruction into the SS reference
+ * (TEncCu.cpp:1694-1696): re-extend the picture border and bring the device mirror up to date.  For the mirrored
+ * plane the host border is re-extended incrementally (hop_border.h: same samples as the reference's full pass,
+ * which costs megabytes per CU on large pictures); HOP_HOST_BORDER=full keeps the reference's own call. */
+inline bool hostBorderIncremental() { static int f = -1; if (f < 0) { const char* e = getenv("HOP_HOST_BORDER"); f = (e && e[0] == 'f') ? 0 : 1; } return f != 0; }
+
+inline void refCommit(TComPicYuv* pic, int x, int y, int w, int h)
 {
   State& s = state();
-  if (pic->getLumaAddr() != s.origin) return;     // not the mirrored plane
+  const bool mine = pic->getLumaAddr() == s.origin;
+  if (mine && hostBorderIncremental()) {
+    Timer tb(5);
+    const int m = pic->getLumaMargin(), mc = pic->getChromaMargin();
+    hop_extend_patch_border(pic->getLumaAddr(), pic->getStride(), pic->getWidth(), pic->getHeight(), m, m, x, y, w, h);
+    hop_extend_patch_border(pic->getCbAddr(), pic->getCStride(), pic->getWidth() >> 1, pic->getHeight() >> 1, mc, mc, x >> 1, y >> 1, w >> 1, h >> 1);
+    hop_extend_patch_border(pic->getCrAddr(), pic->getCStride(), pic->getWidth() >> 1, pic->getHeight() >> 1, mc, mc, x >> 1, y >> 1, w >> 1, h >> 1);
+    pic->setBorderExtension(true);
+  } else {
+    Timer tb(5);
+    pic->setBorderExtension(false);
+    pic->extendPicBorder();
+  }
+  if (!mine) return;     // not the mirrored plane
   Timer tm(2);
   check(hop_ref_update(s.ctx, x, y, w, h, pic->getLumaAddr() + (size_t)y * pic->getStride() + x, pic->getStride()),
         "hop_ref_update");

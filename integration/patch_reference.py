@@ -25,6 +25,8 @@ def patch(text, anchor, insert, where="after", count=1):
         raise SystemExit("anchor %r found %d times (expected %d)" % (anchor[:60], n, count))
     if where == "after":
         return text.replace(anchor, anchor + insert)
+    if where == "replace":
+        return text.replace(anchor, insert)
     return text.replace(anchor, insert + anchor)
 
 
@@ -95,9 +97,12 @@ def main():
     # --- TEncCu.cpp -------------------------------------------------------------------------------
     t = rd("TLibEncoder/TEncCu.cpp")
     t = patch(t, '#include "TEncCu.h"\n', '#include "hop_shim.h"   // libhopgpu\n')
+    # xCopyYuv2SSRef: the border re-extension and the device mirror update in one call (the two reference lines
+    # stay reachable through hopshim::refCommit for planes that are not mirrored and with HOP_HOST_BORDER=full)
     t = patch(t,
               "    rpcPic->getPicYuvRec()->setBorderExtension(false);\n    rpcPic->getPicYuvRec()->extendPicBorder();\n",
-              "    hopshim::refUpdate( rpcPic->getPicYuvRec(), uiLPelX, uiTPelY, g_uiMaxCUWidth>>uiDepth, g_uiMaxCUHeight>>uiDepth );   // libhopgpu\n")
+              "    hopshim::refCommit( rpcPic->getPicYuvRec(), uiLPelX, uiTPelY, g_uiMaxCUWidth>>uiDepth, g_uiMaxCUHeight>>uiDepth );   // libhopgpu\n",
+              where="replace")
     # speculation window: the reference's own xCheckRDCostInter is run once per partition mode
     # with the shim in "enqueue, do not wait" mode -- it derives the AMVP list and search window of the mode's
     # first PU exactly as the real pass will, hands the request to the GPU and returns through the reference's

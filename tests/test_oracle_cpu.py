@@ -233,3 +233,38 @@ def test_product_does_not_reference_oracle():
                     if re.search(r"hop_oracle|libhoporacle|libhopref|_oracle\b|orc_[a-z]", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_host_incremental_border_equals_full_extension(tmp_path):
+    """include/hop_border.h (what the shim runs on the HOST plane after every CU of xCopyYuv2SSRef) against the
+    reference's full re-extension (oracle restatement of TComPicYuv.cpp:247-274) after every commit of a CTU walk."""
+    import subprocess
+    so = str(tmp_path / "libborder.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "helpers", "border_harness.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.border_extend_patch.argtypes = [C.c_void_p] + [C.c_int] * 8
+    lib.border_extend_patch.restype = None
+    rng = np.random.default_rng(3)
+    for (pic_w, pic_h, m) in [(64, 64, 80), (136, 104, 80), (200, 72, 40)]:
+        stride = pic_w + 2 * m
+        inc = np.full((pic_h + 2 * m, stride), -1, dtype=np.int16)
+        full = inc.copy()
+        img = rng.integers(0, 256, size=(pic_h, pic_w)).astype(np.int16)
+        # quadtree-like commits: every 8x8 block in raster-of-CTU order, then the enclosing 16 / 32 / 64 blocks again
+        blocks = []
+        for cy in range(0, pic_h, 64):
+            for cx in range(0, pic_w, 64):
+                for size in (8, 16, 32, 64):
+                    for by in range(cy, min(cy + 64, pic_h), size):
+                        for bx in range(cx, min(cx + 64, pic_w), size):
+                            if bx + size <= pic_w and by + size <= pic_h:
+                                blocks.append((bx, by, size))
+        for (bx, by, size) in blocks:
+            blk = img[by:by + size, bx:bx + size] ^ (size & 8)
+            for p in (inc, full):
+                p[m + by:m + by + size, m + bx:m + bx + size] = blk
+            origin = inc.ctypes.data + 2 * (m * stride + m)
+            lib.border_extend_patch(origin, stride, pic_w, pic_h, m, bx, by, size, size)
+            _oracle.extend_border_oracle(full, pic_w, pic_h, m)
+            assert (inc == full).all(), (pic_w, pic_h, bx, by, size)
