@@ -20,17 +20,18 @@ CFG_LOWDELAY_P = os.path.join(ROOT, "integration", "hop_lowdelay_p.cfg")   # ISS
 
 
 def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=None, keep=False, retries=0,
-           crop_of=None, cfg=None, env_extra=None, frames=1, extra_args=(), launcher=None):
+           crop_of=None, cfg=None, env_extra=None, frames=1, extra_args=(), launcher=None, input_yuv=None):
     """Encode one synthetic lenslet frame; returns dict(bitstream=bytes, seconds=float, rec=bytes, log=str).
 
     crop_of=(W, H): the frame is the top-left width x height region of the W x H image with this seed;
     cfg: another encoder configuration file than integration/hop_intra.cfg; env_extra: extra environment;
-    frames > 1: frame k is the lenslet image with seed + k (low-delay P cfg: ISS frame followed by PSS frames)."""
+    frames > 1: frame k is the lenslet image with seed + k (low-delay P cfg: ISS frame followed by PSS frames);
+    input_yuv: an already written input file of that geometry (several encodes of one image, e.g. a QP sweep)."""
     if not os.path.exists(binary):
         raise FileNotFoundError(binary + " not built (python __graft_entry__.py in the build container)")
     tmp = workdir or tempfile.mkdtemp(prefix="hopenc_")
-    yuv = os.path.join(tmp, "in.yuv")
-    for k in range(frames):
+    yuv = input_yuv or os.path.join(tmp, "in.yuv")
+    for k in range(0 if input_yuv else frames):
         write_yuv420(yuv, lenslet_luma(width, height, seed=seed + k, bit_depth=bit_depth, crop_of=crop_of), bit_depth=bit_depth,
                      append=k > 0)
     cmd = [binary, "-c", cfg or CFG, "-i", yuv, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", str(frames),
