@@ -37,6 +37,10 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 SHAPES = [(8, 8), (16, 16), (32, 32), (64, 64)]
+# one string for both arms: the GPU arm runs the whole workload per step, the reference arm a bounded sample of it
+WORKLOAD = ("configs[2]: standalone HOP candidate-search microbench, %d PUs of each of 8x8/16x16/32x32/64x64 "
+            "per GPU, full diamond grid (3/4/5/6 passes x 56 affine candidates), 1 start vector, HadamardME, "
+            "8-bit, QP32 lambda")
 FP64_OPS_PER_PIXEL = 24      # Fx,Fy 8 + p,q 4 + bilinear 11 + rounding 1
 INT_OPS_PER_PIXEL = 15       # Hadamard 9 + clamps 6
 
@@ -50,8 +54,10 @@ def parse():
     ap.add_argument("--pus", type=int, default=4096, help="PUs per shape per GPU")
     ap.add_argument("--cpu-sample", type=int, default=512, help="PUs per shape in the CPU baseline sample (~16 s on one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--encode-size", type=int, default=1024, help="edge of the square lenslet image encoded per GPU; 0 = skip")
-    ap.add_argument("--sweep-pus", type=int, default=256, help="PUs (16x16, Main10) of the sharded exhaustive sweep; 0 = skip")
+    ap.add_argument("--encode-size", type=int, default=1024, help="edge of the square lenslet images of the encode leg; 0 = skip")
+    ap.add_argument("--encode-procs", type=int, default=0, help="encoder processes per GPU (sharing it through MPS); 0 = host cores / 8, at least 1")
+    ap.add_argument("--encode-images", type=int, default=0, help="images per GPU in the encode leg; 0 = one per encoder process")
+    ap.add_argument("--sweep-pus", type=int, default=4096, help="PUs (Main10, 8x8/16x16/32x32/16x8 mix) of the sharded exhaustive sweep; 0 = skip")
     ap.add_argument("--k1-pus", type=int, default=592, help="PUs per shape for the secondary K1 (SS full search) measurement (592 = two waves of the 2 CTAs resident per SM); 0 = skip")
     return ap.parse_args()
 
@@ -177,9 +183,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
         "data": "synthetic",
-        "config": {"workload": "configs[2]: standalone HOP candidate-search microbench, PUs 8x8/16x16/32x32/64x64, "
-                               "full diamond grid, 1 start vector, HadamardME, 8-bit, QP32 lambda (bounded CPU sample)"},
-        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": c, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD % args.pus},
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": c, "kind": kind,
+                         "sample": sample + " per step (a bounded sample of the workload: the CPU needs ~4 h per full step on one core)"},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -189,28 +195,65 @@ def run_reference(args):
 # lenslet encode s/image: the reference encoder with the drop-in patch, one process + context per GPU
 # ---------------------------------------------------------------------------------------------------
 def measure_encode(args, rank, world, local, dist, torch, dev):
+    """Lenslet encode s/image (BASELINE configs[0] / configs[3] shape): every rank (= GPU) runs P encoder processes
+    that share its GPU through MPS and encode `images` independent 1024x1024 frames; no collective on the data path."""
     import hashlib
-    from hevc_hop_b200 import encoder
+    from hevc_hop_b200 import encoder, batch
     if args.encode_size <= 0 or not os.path.exists(encoder.HOP_ENCODER):
         return None
     n = args.encode_size
+    cores = os.cpu_count() or 8
+    procs = args.encode_procs or max(1, cores // 8)          # the 8-GPU box runs 8 ranks: never more processes than cores
+    images = args.encode_images or procs
+    mps = False
+    if procs > 1:
+        if local == 0:
+            mps = batch.mps_start()
+        if dist is not None:
+            dist.barrier()
+        mps = batch.mps_running()
+        if not mps:
+            procs = 1                                        # without MPS the driver time-slices whole contexts: no gain
+    # rank 0's first image is the golden one (seed 0: its CPU bitstream is pinned in tests/golden/encode_golden.json)
+    seeds = [0 if (rank == 0 and i == 0) else 100 + rank * images + i for i in range(images)]
+    tasks = [dict(width=n, height=n, seed=sd) for sd in seeds]
     if dist is not None:
         dist.barrier()
-    r = encoder.encode(encoder.HOP_ENCODER, n, n, seed=100 + rank, device=local)
-    t = torch.tensor([r["seconds"]], dtype=torch.float64, device=dev)
+    res, makespan = batch.encode_batch(tasks, device=local, procs=procs, use_mps=mps)
+    errors = [r["error"] for r in res if "error" in r]
+    secs = [r["seconds"] for r in res if "error" not in r]
+    t = torch.tensor([makespan, sum(secs), len(secs), max(secs) if secs else 0.0, len(errors)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    if mps and local == 0:
+        batch.mps_stop()
     if rank != 0:
         return None
+    total = int(t[2].item())
     ctus = ((n + 63) // 64) ** 2
-    enc = {"image": "%dx%d synthetic lenslet, HOP intra cfg, QP 32, 1 frame" % (n, n), "images": world,
-           "s_per_image": float(t.item()), "images_per_s": world / float(t.item()), "ctus_per_image": ctus,
-           "s_per_ctu": float(t.item()) / ctus, "bytes": len(r["bitstream"]),
-           "note": "wall clock of the encoder process incl. CUDA context creation; max over ranks"}
+    mk = float(tmax[0].item())
+    enc = {"image": "%dx%d synthetic lenslet, HOP intra cfg, QP 32, 1 frame" % (n, n), "images": total,
+           "gpus": world, "encoder_processes_per_gpu": procs, "mps": bool(mps), "host_cores": cores,
+           "makespan_s": mk, "images_per_s": total / mk if mk > 0 else None,
+           "s_per_image": float(t[1].item()) / max(1, total), "s_per_image_max": float(tmax[3].item()),
+           "ctus_per_image": ctus, "s_per_ctu": float(t[1].item()) / max(1, total) / ctus, "errors": int(t[4].item()),
+           "note": "s_per_image = mean wall clock of an encoder process incl. CUDA start-up, over all images of all ranks; "
+                   "makespan = slowest rank; images are independent (no collective)"}
+    gpath = os.path.join(ROOT, "tests", "golden", "encode_golden.json")
+    if n == 1024 and os.path.exists(gpath) and "error" not in res[0]:
+        g = json.load(open(gpath)).get("c0_1024x1024_qp32")
+        if g:
+            enc["bitstream_identical"] = bool(res[0]["md5"] == g["bitstream_md5"] and res[0]["bytes"] == g["bitstream_bytes"])
+            enc["cpu_reference"] = {"s_per_image": g["cpu_seconds"], "s_per_ctu": g["cpu_seconds"] / ctus, "cores": 1,
+                                    "measured": "unmodified reference encoder, same 1024x1024 frame (seed 0), build container CPU; "
+                                                "md5 / size / seconds in tests/golden/encode_golden.json"}
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle
     if world == 1 and not args.no_cpu_baseline and os.path.exists(_oracle.REF_ENCODER):
-        # bounded CPU sample: the unmodified reference on a 256x256 image, the patched encoder on the same image
+        # bounded CPU sample on THIS box: the unmodified reference on a 256x256 image, the patched encoder on the same image
         try:
             ref = _oracle.encode_reference(256, 256, seed=7)
             hop = encoder.encode(encoder.HOP_ENCODER, 256, 256, seed=7, device=local)
@@ -224,45 +267,96 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
-# exhaustive HOP parameter sweep (configs[4]): candidates sharded over the ranks, NCCL all-reduce-min
+# exhaustive HOP parameter sweep (configs[4]): candidate range sharded over the ranks; the exchange is done by
+# the sweep kernel itself (atomicMin into every rank's merge words over NVLink); NCCL all-reduce form beside it
 # ---------------------------------------------------------------------------------------------------
+SWEEP_MIX = [((8, 8), 0.5), ((16, 16), 0.375), ((32, 32), 0.109375), ((16, 8), 0.015625)]
+
+
 def measure_sweep(hop, ctx, torch, dist, dev, tstream, pus, rank, world):
     if pus <= 0:
         return None
     from hevc_hop_b200 import sweep
     from hevc_hop_b200.workload import PuBatch
-    b = PuBatch(16, 16, pus, seed=4242, bit_depth=10, sr=32, n_start=1)      # same inputs on every rank
     up = lambda a: torch.from_numpy(a.view(np.uint8)).to(dev)
-    d_jobs, d_org, d_ref = up(b.gt_jobs), up(b.org), up(b.ref)
-    d_out = torch.zeros(b.n * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+    groups = []
+    for gi, ((c, r), share) in enumerate(SWEEP_MIX):
+        n = max(1, int(round(pus * share)))
+        b = PuBatch(c, r, n, seed=4242 + gi, bit_depth=10, sr=32, n_start=1)      # same inputs on every rank
+        groups.append({"b": b, "jobs": up(b.gt_jobs), "org": up(b.org), "ref": up(b.ref),
+                       "out": torch.zeros(n * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)})
+    total = sum(g["b"].n for g in groups)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 3
-    for it in range(iters + 1):
-        if it == 1:
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0.record(tstream)
-        sweep.sweep_on_device(ctx, torch, dist, b.n, d_jobs, d_org, d_ref, 16, 16, d_out, rank, world, ctx.stream)
-    e1.record(tstream)
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    try:
+        xch = sweep.SweepExchange(ctx, dist, max(g["b"].n for g in groups), rank, world)
+        xerr = None
+    except Exception as e:                      # no peer access between the GPUs: only the collective form runs
+        xch, xerr = None, str(e)[:200]
+    flags = torch.tensor([1 if xch is not None else 0], device=dev)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        return None
-    ms = float(t.item())
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if int(flags.item()) == 0:
+        xch = None
+
+    def run_peer():
+        for g in groups:
+            b = g["b"]
+            xch.sweep(b.n, g["jobs"], g["org"], g["ref"], b.cols, b.rows, g["out"], ctx.stream)
+
+    def run_coll():
+        for g in groups:
+            b = g["b"]
+            sweep.sweep_on_device(ctx, torch, dist, b.n, g["jobs"], g["org"], g["ref"], b.cols, b.rows, g["out"], rank, world, ctx.stream)
+
+    def timed(fn, iters=3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(iters + 1):
+            if it == 1:
+                torch.cuda.synchronize()
+                if dist is not None:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0.record(tstream)
+            fn()
+        e1.record(tstream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle
-    got = d_out.cpu().numpy().view(hop.GT_RES_DT)[:2]
-    want = _oracle.gt_sweep(b.gt_jobs[:2], b.org, b.ref)
-    ok = bool((got["cost"] == want["cost"]).all() and got["gt"].tobytes() == want["gt"].tobytes() and
-              (got["best_index"] == want["best_index"]).all())
-    return {"workload": "%d PUs 16x16 Main10, reference mode IT_GT_SEARCH 1 (N=2): %d affine corner sets per PU, "
-                        "candidate range sharded over %d GPU(s), one all-reduce-min of %d x 8 B" % (pus, hop.HOP_SWEEP_CANDS, world, pus),
-            "scaling": "strong", "ms": ms, "candidates_per_s": pus * hop.HOP_SWEEP_CANDS / (ms * 1e-3),
-            "collective": "ncclAllReduce(min) on int64 keys" if world > 1 else "none (1 rank)", "parity_spot_check": ok}
+
+    def check():
+        ok = True
+        for g in groups:
+            b = g["b"]
+            got = g["out"].cpu().numpy().view(hop.GT_RES_DT)[:2]
+            want = _oracle.gt_sweep(b.gt_jobs[:2], b.org, b.ref)
+            ok &= bool((got["cost"] == want["cost"]).all() and got["gt"].tobytes() == want["gt"].tobytes() and
+                       (got["best_index"] == want["best_index"]).all() and (got["n_candidates"] == want["n_candidates"]).all())
+        return ok
+
+    ms_peer = ok_peer = None
+    if xch is not None:
+        ms_peer = timed(run_peer)
+        ok_peer = check() if rank == 0 else None
+    ms_coll = timed(run_coll)
+    ok_coll = check() if rank == 0 else None
+    if rank != 0:
+        return None
+    ms = ms_peer if ms_peer is not None else ms_coll
+    return {"workload": "%d PUs Main10 (%s), reference mode IT_GT_SEARCH 1 (N=2): %d affine corner sets per PU, candidate range "
+                        "sharded over %d GPU(s), one launch pair per shape" % (
+                            total, ", ".join("%d x %dx%d" % (g["b"].n, g["b"].cols, g["b"].rows) for g in groups), hop.HOP_SWEEP_CANDS, world),
+            "scaling": "strong", "ms": ms, "candidates_per_s": total * hop.HOP_SWEEP_CANDS / (ms * 1e-3),
+            "exchange": ("in-kernel atomicMin into every rank's merge words over peer memory (NVLink), arrival counters; no collective call"
+                         if ms_peer is not None else "collective (peer exchange unavailable: %s)" % xerr),
+            "parity_spot_check": ok_peer if ms_peer is not None else ok_coll,
+            "collective_form": {"ms": ms_coll, "candidates_per_s": total * hop.HOP_SWEEP_CANDS / (ms_coll * 1e-3),
+                                "what": "same kernels + all_reduce(MIN) on keys and all_reduce(SUM) on counts (NCCL)" if world > 1 else "single rank, no exchange",
+                                "parity_spot_check": ok_coll}}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -289,6 +383,12 @@ def measure_k1(hop, ctx, torch, dev, tstream, pus, peaks):
         e1.record(tstream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2
+        # parity spot check of what was just timed, at its own size (SearchRange 128): first PUs against the oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _oracle
+        got = d_out.cpu().numpy().view(hop.SEARCH_RES_DT)[:2]
+        res["parity_spot_check"] = bool(res.get("parity_spot_check", True) and
+                                        got.tobytes() == _oracle.oracle().pattern_search(b.search_jobs[:2], b.org, b.ref).tobytes())
         j = b.search_jobs[0]
         npos = int((j["rng_right"] - j["rng_left"] + 1) * (j["rng_bottom"] - j["rng_top"] + 1)) * b.n
         px = npos * c * (r // 2 if r > 8 else r)
@@ -517,9 +617,7 @@ def run_ours(args):
         "metric": "HOP candidates/s", "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
-        "config": {"workload": "configs[2]: standalone HOP candidate-search microbench, %d PUs of each of 8x8/16x16/32x32/64x64 "
-                               "per GPU, full diamond grid (3/4/5/6 passes x 56 affine candidates), 1 start vector, HadamardME, "
-                               "8-bit, QP32 lambda" % args.pus,
+        "config": {"workload": WORKLOAD % args.pus,
                    "l2": "inputs larger than L2 (%.0f MB per step per GPU)" % (in_bytes / 1e6),
                    "candidates_per_step_per_gpu": cands_per_step},
         "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,

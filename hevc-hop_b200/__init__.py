@@ -174,6 +174,9 @@ ABI = [
     ("hop_dist_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_gt_sweep_keys_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     ("hop_gt_sweep_finalize_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    ("hop_sweep_exchange_create", C.c_int, [_P, C.c_int, _P]),
+    ("hop_sweep_exchange_connect", C.c_int, [_P, C.c_int, C.c_int, _P]),
+    ("hop_gt_sweep_sharded_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, C.c_int, C.c_int, _P, _P]),
     ("hop_gt_sweep_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_ctx_launch_count", C.c_uint64, [_P]),
     ("hop_ctx_stats", C.c_int, [_P, _P]),
@@ -343,6 +346,19 @@ class HopContext:
 
     def gt_sweep_finalize_dev(self, n, d_jobs, d_keys, d_counts, d_out, stream=None):
         self._check(self.lib.hop_gt_sweep_finalize_dev(self.h, n, d_jobs, d_keys, d_counts, d_out, stream))
+
+    def sweep_exchange_create(self, max_pus):
+        """-> 64-byte handle of this rank's merge words (to be all-gathered over the ranks)."""
+        h = (C.c_ubyte * 64)()
+        self._check(self.lib.hop_sweep_exchange_create(self.h, int(max_pus), C.byref(h)))
+        return bytes(h)
+
+    def sweep_exchange_connect(self, world, rank, handles):
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._check(self.lib.hop_sweep_exchange_connect(self.h, world, rank, C.byref(buf)))
+
+    def gt_sweep_sharded_dev(self, n, d_jobs, d_org, d_ref, ref_samples, max_cols, max_rows, d_out, stream=None):
+        self._check(self.lib.hop_gt_sweep_sharded_dev(self.h, n, d_jobs, d_org, d_ref, ref_samples, max_cols, max_rows, d_out, stream))
 
     def probe_alu(self, what):
         g, ms = C.c_double(), C.c_double()

@@ -91,6 +91,12 @@ struct HopCtx {
   uint64_t     ref_version = 0;            // bumped by every change of the SS mirror
   cudaEvent_t  ref_event = nullptr;        // recorded on `stream` after the latest mirror change ...
   uint64_t     ref_event_version = ~0ull;  // ... of this version
+  // sharded sweep: this rank's exchange block (IPC-exported), the peers' blocks mapped here, local merge words
+  unsigned char* xch_block = nullptr;
+  unsigned char* xch_peer[SWEEP_MAX_RANKS] = {nullptr};
+  unsigned char* xch_local = nullptr;      // keys[max_pus] | counts[max_pus] | pu_done[max_pus] | grid_done
+  int          xch_max_pus = 0, xch_world = 0, xch_rank = 0;
+  unsigned     xch_epoch = 0;
   HopCtxStats  stats = {};
   double       spin_timeout_s = 20.0;      // HOP_TIMEOUT_MS: a kernel that never publishes its flag is an error, not a hang
   bool           use_clusters = true;   // HOP_CLUSTERS=0 turns the cluster form of the latency path off
@@ -223,6 +229,10 @@ void hop_ctx_destroy(HopCtx* ctx)
   if (ctx->ref_event) cudaEventDestroy(ctx->ref_event);
   if (ctx->pin_base_h) cudaFreeHost(ctx->pin_base_h);
   if (ctx->slot_words) cudaFree(ctx->slot_words);
+  for (int r = 0; r < SWEEP_MAX_RANKS; r++)
+    if (ctx->xch_peer[r] && ctx->xch_peer[r] != ctx->xch_block) cudaIpcCloseMemHandle(ctx->xch_peer[r]);
+  if (ctx->xch_block) cudaFree(ctx->xch_block);
+  if (ctx->xch_local) cudaFree(ctx->xch_local);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (auto& sl : ctx->slots) {
     Scratch* ss[] = {&sl.jobs, &sl.org, &sl.ref, &sl.out};
@@ -1004,6 +1014,102 @@ int hop_gt_sweep_finalize_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const 
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   int l = 0;
   CU(sweep_finalize_launch(n, d_jobs, (const unsigned long long*)d_keys, d_counts, d_out, s, &l));
+  ctx->launches += l;
+  return HOP_OK;
+}
+
+// ---- sharded sweep over peer memory (no collective call) ------------------------------------------------------
+namespace {
+inline size_t xch_gkeys_bytes(int max_pus)  { return sizeof(unsigned long long) * 2 * (size_t)max_pus; }
+inline size_t xch_gcounts_bytes(int max_pus) { return (sizeof(unsigned int) * 2 * (size_t)max_pus + 63) & ~(size_t)63; }
+inline size_t xch_block_bytes(int max_pus)  { return xch_gkeys_bytes(max_pus) + xch_gcounts_bytes(max_pus) + 64; }
+}
+
+int hop_sweep_exchange_create(HopCtx* ctx, int max_pus, HopSweepHandle* mine)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (max_pus <= 0 || !mine) return fail(HOP_ERR_ARG, "bad exchange geometry");
+  if (ctx->xch_block) return fail(HOP_ERR_STATE, "exchange already created");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(HopSweepHandle), "handle size");
+  const size_t bytes = xch_block_bytes(max_pus);
+  CU(cudaMalloc((void**)&ctx->xch_block, bytes));
+  CU(cudaMemsetAsync(ctx->xch_block, 0, bytes, ctx->stream));
+  CU(cudaMemsetAsync(ctx->xch_block, 0xFF, xch_gkeys_bytes(max_pus), ctx->stream));          // merge words idle = all-ones
+  const size_t local = (sizeof(unsigned long long) + 2 * sizeof(unsigned int)) * (size_t)max_pus + 64;
+  CU(cudaMalloc((void**)&ctx->xch_local, local));
+  CU(cudaMemsetAsync(ctx->xch_local, 0, local, ctx->stream));
+  CU(cudaMemsetAsync(ctx->xch_local, 0xFF, sizeof(unsigned long long) * (size_t)max_pus, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->xch_block));
+  memset(mine, 0, sizeof(*mine));
+  memcpy(mine, &h, sizeof(h));
+  ctx->xch_max_pus = max_pus;
+  ctx->xch_world = 0;
+  return HOP_OK;
+}
+
+int hop_sweep_exchange_connect(HopCtx* ctx, int world, int rank, const HopSweepHandle* all)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (!ctx->xch_block) return fail(HOP_ERR_STATE, "hop_sweep_exchange_connect before hop_sweep_exchange_create");
+  if (world < 1 || world > SWEEP_MAX_RANKS || rank < 0 || rank >= world || !all)
+    return fail(HOP_ERR_ARG, "world %d / rank %d out of range (at most %d ranks)", world, rank, SWEEP_MAX_RANKS);
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { ctx->xch_peer[r] = ctx->xch_block; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, &all[r], sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(HOP_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (no peer access between the GPUs?)", r, cudaGetErrorString(e)); }
+    ctx->xch_peer[r] = (unsigned char*)p;
+  }
+  ctx->xch_world = world;
+  ctx->xch_rank = rank;
+  ctx->xch_epoch = 0;
+  return HOP_OK;
+}
+
+int hop_gt_sweep_sharded_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                             size_t ref_samples, int max_cols, int max_rows, HopGtResult* d_out, void* stream)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (ctx->xch_world < 1) return fail(HOP_ERR_STATE, "sharded sweep before hop_sweep_exchange_connect");
+  if (n <= 0 || n > ctx->xch_max_pus) return fail(HOP_ERR_ARG, "%d PUs, the exchange holds %d", n, ctx->xch_max_pus);
+  if (!d_jobs || !d_org || !d_ref || !d_out) return fail(HOP_ERR_ARG, "NULL device buffer");
+  if (max_cols < 4 || max_cols > HOP_MAX_PU || max_rows < 4 || max_rows > HOP_MAX_PU)
+    return fail(HOP_ERR_ARG, "shape bound %dx%d out of range", max_cols, max_rows);
+  if ((st = sweep_table_ready(ctx))) return st;
+  RefBounds rb;
+  if ((st = dev_bounds(ctx, d_ref, ref_samples, &rb))) return st;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  const int world = ctx->xch_world, rank = ctx->xch_rank, mp = ctx->xch_max_pus;
+  // contiguous slice of the flattened candidate range owned by this rank (sizes differ by at most one)
+  const int base = SWEEP_CANDS / world, rem = SWEEP_CANDS % world;
+  const int cand_begin = rank * base + (rank < rem ? rank : rem), cand_end = cand_begin + base + (rank < rem ? 1 : 0);
+  const unsigned epoch = ++ctx->xch_epoch;
+  SweepXchg xc = {};
+  for (int r = 0; r < world; r++) {
+    xc.gkeys[r] = (unsigned long long*)ctx->xch_peer[r];
+    xc.gcounts[r] = (unsigned int*)(ctx->xch_peer[r] + xch_gkeys_bytes(mp));
+    xc.arrived[r] = (unsigned int*)(ctx->xch_peer[r] + xch_gkeys_bytes(mp) + xch_gcounts_bytes(mp));
+  }
+  unsigned long long* l_keys = (unsigned long long*)ctx->xch_local;
+  unsigned int* l_counts = (unsigned int*)(l_keys + mp);
+  xc.pu_done = l_counts + mp;
+  xc.grid_done = xc.pu_done + mp;
+  xc.world = world; xc.rank = rank; xc.max_pus = mp; xc.parity = epoch & 1u;
+  const int batches = (cand_end - cand_begin + GT_CANDS - 1) / GT_CANDS;
+  int chunks = (12 * ctx->sm_count + n - 1) / n;
+  if (chunks > batches) chunks = batches;
+  if (chunks < 1) chunks = 1;
+  int l = 0;
+  CU(sweep_keys_launch(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, l_keys, l_counts, s, &l, rb, &xc));
+  CU(sweep_finalize_x_launch(n, d_jobs, xc.gkeys[rank] + (size_t)xc.parity * mp, xc.gcounts[rank] + (size_t)xc.parity * mp,
+                             xc.arrived[rank], epoch * (unsigned)world, d_out, s, &l));
   ctx->launches += l;
   return HOP_OK;
 }

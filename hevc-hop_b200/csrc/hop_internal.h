@@ -46,11 +46,25 @@ constexpr int SWEEP_CANDS = 7200;
 struct SweepCand { int8_t o[8]; uint32_t flat; };   // x0,y0,...,x3,y3 in [-2,2]; flat 8-deep loop index
 void        sweep_build_table(SweepCand* table, int* count);
 cudaError_t sweep_upload_table(const SweepCand* table);
+// Peer-memory exchange of the sharded sweep: per rank, device pointers (valid on THIS GPU, peers' memory mapped over
+// NVLink) to the merge words [2][max_pus] every rank keeps in its own HBM, and to its arrival counter.  world == 0: off.
+constexpr int SWEEP_MAX_RANKS = 8;
+struct SweepXchg {
+  unsigned long long* gkeys[SWEEP_MAX_RANKS];
+  unsigned int*       gcounts[SWEEP_MAX_RANKS];
+  unsigned int*       arrived[SWEEP_MAX_RANKS];
+  unsigned int*       pu_done;      // local: tickets per PU, zero between sweeps
+  unsigned int*       grid_done;    // local: ticket of the grid
+  int world, rank, max_pus;
+  unsigned parity;                  // sweep number & 1: which half of the merge words this sweep uses
+};
 cudaError_t sweep_init_launch(int n, unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches);
 cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                               int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
                               unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches,
-                              RefBounds rb = REF_UNBOUNDED);
+                              RefBounds rb = REF_UNBOUNDED, const SweepXchg* xchg = nullptr);
+cudaError_t sweep_finalize_x_launch(int n, const HopGtJob* d_jobs, unsigned long long* d_gkeys, unsigned int* d_gcounts,
+                                    const unsigned int* d_arrived, unsigned int target, HopGtResult* d_out, cudaStream_t stream, int* launches);
 cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,
                                   const unsigned int* d_counts, HopGtResult* d_out, cudaStream_t stream, int* launches);
 struct InlinePu;

@@ -824,11 +824,17 @@ void sweep_build_table(SweepCand* table, int* count)
   *count = n;
 }
 
+// Sharded form (SweepXchg.world > 0): the partial argmin of a PU leaves this GPU the moment the PU's last CTA is
+// done -- one 64-bit atomicMin (and one 32-bit atomicAdd of the candidate count) per rank into the merge words that
+// every rank keeps in its own HBM, straight through peer-mapped memory over NVLink, overlapped with the CTAs
+// still computing.  The last CTA of the whole grid then bumps an arrival counter on every rank.  No collective
+// call, no extra launch: the all-reduce-min of SURVEY.md 8e is done by the kernel that produces the keys.
 template <int WS>
 __global__ void __launch_bounds__(gt_class_threads(WS), 2)
 k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
             const int16_t* __restrict__ ref_buf, int cand_begin, int cand_end,
-            unsigned long long* __restrict__ keys, unsigned int* __restrict__ counts, RefBounds rb)
+            unsigned long long* __restrict__ keys, unsigned int* __restrict__ counts, RefBounds rb,
+            const __grid_constant__ SweepXchg xc)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GtShared& sh = *reinterpret_cast<GtShared*>(smem_raw);
@@ -928,6 +934,26 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
   if (threadIdx.x == 0) {
     if (best != ~0ull) atomicMin(&keys[job_id], best);
     if (counts && scored) atomicAdd(&counts[job_id], scored);
+    if (xc.world > 0) {
+      __threadfence();
+      if (atomicAdd(&xc.pu_done[job_id], 1u) == gridDim.y - 1) {          // last CTA of this PU on this GPU
+        __threadfence();
+        const unsigned long long key = atomicExch(&keys[job_id], ~0ull);  // merge words return to their idle state
+        const unsigned int cnt = atomicExch(&counts[job_id], 0u);
+        xc.pu_done[job_id] = 0;
+        const size_t slot = (size_t)xc.parity * xc.max_pus + job_id;
+        for (int r = 0; r < xc.world; r++) {
+          if (key != ~0ull) atomicMin_system(xc.gkeys[r] + slot, key);
+          if (cnt) atomicAdd_system(xc.gcounts[r] + slot, cnt);
+        }
+        __threadfence_system();
+        if (atomicAdd(xc.grid_done, 1u) == gridDim.x - 1) {               // last PU of the grid: everything is out
+          *xc.grid_done = 0;
+          __threadfence_system();
+          for (int r = 0; r < xc.world; r++) atomicAdd_system(xc.arrived[r], 1u);
+        }
+      }
+    }
   }
 }
 
@@ -938,13 +964,8 @@ __global__ void k2_sweep_init(int n, unsigned long long* keys, unsigned int* cou
 }
 
 // key -> the outputs xPatternSearchGT (mode 1) leaves (:5070-5090)
-__global__ void k2_sweep_finalize(int n, const HopGtJob* __restrict__ jobs, const unsigned long long* __restrict__ keys,
-                                  const unsigned int* __restrict__ counts, HopGtResult* __restrict__ out)
+__device__ __forceinline__ void sweep_result(const HopGtJob& job, unsigned long long key, unsigned int count, HopGtResult* out)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const HopGtJob job = jobs[i];
-  const unsigned long long key = keys[i];
   const int cols = job.cols, rows = job.rows, N = 2;
   HopGtResult r;
   r.gt_flag = 0;
@@ -952,7 +973,7 @@ __global__ void k2_sweep_finalize(int n, const HopGtJob* __restrict__ jobs, cons
   r.cost = job.threshold;
   r.mv_int.hor = 0; r.mv_int.ver = 0;
   r.best_index = -1;
-  r.n_candidates = counts ? counts[i] : 0;
+  r.n_candidates = count;
   if (key != ~0ull && (uint32_t)(key >> 32) < job.threshold) {                               // uiDist < uiDistBest
     uint32_t flat = (uint32_t)key;
     int o[8];
@@ -971,7 +992,46 @@ __global__ void k2_sweep_finalize(int n, const HopGtJob* __restrict__ jobs, cons
       r.best_index = (int32_t)(uint32_t)key;
     }
   }
-  out[i] = r;
+  *out = r;
+}
+
+__global__ void k2_sweep_finalize(int n, const HopGtJob* __restrict__ jobs, const unsigned long long* __restrict__ keys,
+                                  const unsigned int* __restrict__ counts, HopGtResult* __restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sweep_result(jobs[i], keys[i], counts ? counts[i] : 0, &out[i]);
+}
+
+// Second and last kernel of the sharded sweep: wait until every rank's grid has reported, then turn the merged
+// words into results (every rank computes the same ones) and hand the words back in their idle state for the
+// sweep after next (they are double buffered by sweep parity: a fast peer may already be pushing the next sweep).
+__global__ void k2_sweep_finalize_x(int n, const HopGtJob* __restrict__ jobs, unsigned long long* gkeys, unsigned int* gcounts,
+                                    const unsigned int* arrived, unsigned int target, HopGtResult* __restrict__ out)
+{
+  __shared__ int s_timed_out;
+  if (threadIdx.x == 0) {
+    // a peer that never reports (its process died) must not hang this GPU: give up after 10 s and say so
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int late = 0;
+    while ((int)(*(volatile const unsigned int*)arrived - target) < 0) {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) { late = 1; break; }
+    }
+    s_timed_out = late;
+    __threadfence_system();
+  }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = *(volatile unsigned long long*)(gkeys + i);
+  const unsigned int cnt = *(volatile unsigned int*)(gcounts + i);
+  gkeys[i] = ~0ull;
+  gcounts[i] = 0;
+  sweep_result(jobs[i], key, cnt, &out[i]);
+  if (s_timed_out) { out[i].gt_flag = -1; out[i].best_index = -2; }    // incomplete exchange: never a silent partial result
 }
 
 static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
@@ -1046,7 +1106,8 @@ cudaError_t gt_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const
 template <int WS>
 static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                                       int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
-                                      unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, RefBounds rb)
+                                      unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, RefBounds rb,
+                                      const SweepXchg& xc)
 {
   static SmemOptIn opt_in;
   {
@@ -1063,7 +1124,7 @@ static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
   k2_gt_sweep<WS><<<dim3(n, chunks), threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(
-      n, d_jobs, d_org, d_ref, cand_begin, cand_end, d_keys, d_counts, rb);
+      n, d_jobs, d_org, d_ref, cand_begin, cand_end, d_keys, d_counts, rb, xc);
   return cudaGetLastError();
 }
 
@@ -1076,16 +1137,27 @@ cudaError_t sweep_init_launch(int n, unsigned long long* d_keys, unsigned int* d
 
 cudaError_t sweep_keys_launch(int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                               int max_cols, int max_rows, int cand_begin, int cand_end, int chunks,
-                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches, RefBounds rb)
+                              unsigned long long* d_keys, unsigned int* d_counts, cudaStream_t stream, int* launches, RefBounds rb,
+                              const SweepXchg* xchg)
 {
+  static const SweepXchg none = {};
+  const SweepXchg& xc = xchg ? *xchg : none;
   const int win_w = max_cols + (max_cols < max_rows ? max_cols : max_rows);
   if (launches) (*launches)++;
   switch (gt_stride_class(win_w)) {
-    case WS_A:  return sweep_launch_class<WS_A>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
-    case WS_B:  return sweep_launch_class<WS_B>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
-    case WS_C:  return sweep_launch_class<WS_C>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
-    default:  return sweep_launch_class<WS_D>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb);
+    case WS_A:  return sweep_launch_class<WS_A>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb, xc);
+    case WS_B:  return sweep_launch_class<WS_B>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb, xc);
+    case WS_C:  return sweep_launch_class<WS_C>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb, xc);
+    default:  return sweep_launch_class<WS_D>(n, d_jobs, d_org, d_ref, max_cols, max_rows, cand_begin, cand_end, chunks, d_keys, d_counts, stream, rb, xc);
   }
+}
+
+cudaError_t sweep_finalize_x_launch(int n, const HopGtJob* d_jobs, unsigned long long* d_gkeys, unsigned int* d_gcounts,
+                                    const unsigned int* d_arrived, unsigned int target, HopGtResult* d_out, cudaStream_t stream, int* launches)
+{
+  k2_sweep_finalize_x<<<(n + 255) / 256, 256, 0, stream>>>(n, d_jobs, d_gkeys, d_gcounts, d_arrived, target, d_out);
+  if (launches) (*launches)++;
+  return cudaGetLastError();
 }
 
 cudaError_t sweep_finalize_launch(int n, const HopGtJob* d_jobs, const unsigned long long* d_keys,

@@ -46,18 +46,49 @@ def allreduce_min_keys(t, dist=None, group=None):
 
 
 def sweep_on_device(ctx, torch, dist, n, d_jobs, d_org, d_ref, max_cols, max_rows, d_out, rank=0, world=1, stream=None):
-    """One sharded sweep over device-resident inputs (torch uint8 tensors); returns the key tensor."""
+    """One sharded sweep over device-resident inputs (torch uint8 tensors) with the COLLECTIVE exchange
+    (all_reduce MIN on the keys, SUM on the counts: NCCL on GPUs, gloo in the CPU tests); returns the key tensor.
+    This is the baseline form; `SweepExchange` is the product path on an NVLink node.
+
+    The kernels run on the context's stream; the torch ops and the collectives in between are issued on the
+    same stream (ExternalStream), so the order is the program order whatever torch's current stream is."""
     dev = d_jobs.device
     begin, end = shard_range(HOP_SWEEP_CANDS, rank, world)
-    keys = torch.empty(n, dtype=torch.int64, device=dev)
-    counts = torch.zeros(n, dtype=torch.int32, device=dev)
-    ctx.gt_sweep_keys_dev(n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_ref.numel() // 2, max_cols, max_rows, begin, end,
-                          keys.data_ptr(), counts.data_ptr(), stream)
-    if world > 1:
-        # all-ones (nothing scored) is -1 as int64: lift it above every real key before the MIN
-        keys = torch.where(keys < 0, torch.full_like(keys, int(NONE_KEY)), keys)
-        allreduce_min_keys(keys, dist)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-        keys = torch.where(keys == int(NONE_KEY), torch.full_like(keys, -1), keys)
-    ctx.gt_sweep_finalize_dev(n, d_jobs.data_ptr(), keys.data_ptr(), counts.data_ptr(), d_out.data_ptr(), stream)
+    ext = torch.cuda.ExternalStream(stream or ctx.stream, device=dev)
+    with torch.cuda.stream(ext):
+        keys = torch.empty(n, dtype=torch.int64, device=dev)
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        ctx.gt_sweep_keys_dev(n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_ref.numel() // 2, max_cols, max_rows,
+                              begin, end, keys.data_ptr(), counts.data_ptr(), ext.cuda_stream)
+        if world > 1:
+            # all-ones (nothing scored) is -1 as int64: lift it above every real key before the MIN
+            keys = torch.where(keys < 0, torch.full_like(keys, int(NONE_KEY)), keys)
+            allreduce_min_keys(keys, dist)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+            keys = torch.where(keys == int(NONE_KEY), torch.full_like(keys, -1), keys)
+        ctx.gt_sweep_finalize_dev(n, d_jobs.data_ptr(), keys.data_ptr(), counts.data_ptr(), d_out.data_ptr(), ext.cuda_stream)
     return keys
+
+
+class SweepExchange:
+    """Sharded sweep WITHOUT a collective call: every rank exports one merge word per PU (CUDA IPC), the sweep
+    kernel min-reduces its partial keys into all ranks' words through peer-mapped memory over NVLink while it is
+    still computing, a second kernel waits for every rank's arrival counter and finalises (include/hop_gpu.h,
+    hop_gt_sweep_sharded_dev).  torch.distributed only carries the 64-byte handles once, at set-up."""
+
+    def __init__(self, ctx, dist, max_pus, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        mine = ctx.sweep_exchange_create(max_pus)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, mine)      # also the barrier behind which every rank's words are initialised
+        else:
+            handles[0] = mine
+        ctx.sweep_exchange_connect(world, rank, handles)
+        if world > 1:
+            dist.barrier()                             # nobody pushes before everybody has mapped everybody
+
+    def sweep(self, n, d_jobs, d_org, d_ref, max_cols, max_rows, d_out, stream=None):
+        """Two kernel launches on the context's stream; d_out holds the finalised results when the stream is done."""
+        self.ctx.gt_sweep_sharded_dev(n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_ref.numel() // 2,
+                                      max_cols, max_rows, d_out.data_ptr(), stream)

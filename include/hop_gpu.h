@@ -276,6 +276,18 @@ int hop_gt_sweep_keys_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int1
                           uint64_t* d_keys, uint32_t* d_counts /* may be NULL */, void* stream);
 int hop_gt_sweep_finalize_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const uint64_t* d_keys,
                               const uint32_t* d_counts /* may be NULL */, HopGtResult* d_out, void* stream);
+/* Sharded sweep without a collective call (one process per GPU, all GPUs of one NVLink / NVSwitch node): every rank
+ * keeps one merge word per PU in its own HBM and exports it (CUDA IPC); hop_gt_sweep_sharded_dev scores this rank's
+ * slice of the candidate range and its kernel min-reduces the partial keys into EVERY rank's merge words through
+ * peer-mapped memory (64-bit atomicMin over NVLink, issued as each PU completes, overlapped with the CTAs still
+ * computing); a second kernel waits for all ranks' arrival counters and finalises.  Every rank calls with the same
+ * n / jobs / inputs and obtains the same results as hop_gt_sweep_batch.  Set-up: create -> exchange the handles of
+ * all ranks by any means (e.g. torch.distributed.all_gather_object) -> connect. */
+typedef struct HopSweepHandle { unsigned char bytes[64]; } HopSweepHandle;
+int hop_sweep_exchange_create(HopCtx* ctx, int max_pus, HopSweepHandle* mine);
+int hop_sweep_exchange_connect(HopCtx* ctx, int world, int rank, const HopSweepHandle* all /* [world] */);
+int hop_gt_sweep_sharded_dev(HopCtx* ctx, int n, const HopGtJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
+                             size_t ref_samples, int max_cols, int max_rows, HopGtResult* d_out, void* stream);
 /* host convenience: whole candidate range on this GPU */
 int hop_gt_sweep_batch(HopCtx* ctx, int n, const HopGtJob* jobs, const int16_t* org, size_t org_samples,
                        const int16_t* ref, size_t ref_samples, HopGtResult* out);

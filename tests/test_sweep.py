@@ -142,3 +142,75 @@ def test_gpu_sharded_keys_min_equals_full_sweep(ctx, world):
     ctx.sync()
     got = d_out.cpu().numpy().view(hop.GT_RES_DT)
     assert same(got, _oracle.gt_sweep(b.gt_jobs, b.org, b.ref), extras=True)
+
+
+# ---- sharded sweep over peer memory: one process per GPU, no collective on the data path -----------------------
+def _peer_rank(rank, world, port, result):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # carries the 64-byte handles and barriers only
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    cx = hop.HopContext(rank)
+    xch = sweep.SweepExchange(cx, dist, 64, rank, world)
+    ok = True
+    up = lambda a: torch.from_numpy(a.view(np.uint8).copy()).to(dev)
+    # different shapes, bit depths and batch sizes back to back (the merge words alternate by sweep parity)
+    cases = [(8, 8, 5, 8), (16, 16, 7, 10), (16, 12, 3, 8), (32, 32, 2, 8), (8, 4, 64, 8), (16, 16, 1, 8), (4, 8, 9, 10)]
+    for it, (c, r, n, bd) in enumerate(cases * 2):
+        b = PuBatch(c, r, n, seed=900 + it, bit_depth=bd, sr=20, n_start=1, use_had=it % 3 != 0)
+        if it % 5 == 4:
+            b.gt_jobs["threshold"] = 0           # nothing can be accepted: flag 0, counts still exchanged
+        d_jobs, d_org, d_ref = up(b.gt_jobs), up(b.org), up(b.ref)
+        d_out = torch.zeros(n * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        xch.sweep(n, d_jobs, d_org, d_ref, c, r, d_out, cx.stream)
+        cx.sync()
+        got = d_out.cpu().numpy().view(hop.GT_RES_DT)
+        ok &= same(got, _oracle.gt_sweep(b.gt_jobs, b.org, b.ref), extras=True)
+    r = torch.tensor([1 if ok else 0])
+    dist.all_reduce(r, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        result.put(int(r.item()))
+    dist.barrier()
+    cx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_gpu_peer_memory_sweep_equals_serial_sweep():
+    """One process per GPU: atomicMin of the partial keys into every rank's merge words over NVLink, arrival
+    counters instead of a collective -- results equal the unsharded oracle sweep on every rank."""
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs two GPUs with peer access")
+    import torch.multiprocessing as mp
+    mctx = mp.get_context("spawn")
+    q = mctx.Queue()
+    procs = [mctx.Process(target=_peer_rank, args=(r, world, 29641, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == 1
+
+
+@pytest.mark.gpu
+def test_gpu_peer_memory_sweep_single_rank(ctx):
+    """world = 1 goes through the same two kernels (the rank pushes into its own merge words)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    xch = sweep.SweepExchange(ctx, None, 16, 0, 1)
+    up = lambda a: torch.from_numpy(a.view(np.uint8).copy()).to(dev)
+    for it, (c, r, n) in enumerate([(8, 8, 4), (16, 8, 16), (32, 16, 2), (8, 8, 1)]):
+        b = PuBatch(c, r, n, seed=40 + it, sr=20, n_start=1)
+        d_jobs, d_org, d_ref = up(b.gt_jobs), up(b.org), up(b.ref)
+        d_out = torch.zeros(n * hop.GT_RES_DT.itemsize, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        xch.sweep(n, d_jobs, d_org, d_ref, c, r, d_out, ctx.stream)
+        ctx.sync()
+        assert same(d_out.cpu().numpy().view(hop.GT_RES_DT), _oracle.gt_sweep(b.gt_jobs, b.org, b.ref), extras=True), it
