@@ -92,6 +92,21 @@ class HopMotionResult(C.Structure):
     _fields_ = [("search", HopSearchResult), ("refined", C.c_int32), ("frac", HopFracResult), ("gt", HopGtResult)]
 
 
+class HopPredJob(C.Structure):
+    _fields_ = [
+        ("ref_off", C.c_int64), ("org_off", C.c_int64), ("dst_off", C.c_int64),
+        ("ref_stride", C.c_int32), ("org_stride", C.c_int32), ("dst_stride", C.c_int32),
+        ("cols", C.c_int32), ("rows", C.c_int32), ("comp", C.c_int32), ("mv", HopMv),
+        ("gt_flag", C.c_int32), ("gt", HopMv * 4), ("bit_depth", C.c_int32), ("dist_func", C.c_int32),
+        ("template_cost", C.c_int32), ("is_ss", C.c_int32), ("mv_probe", HopMv), ("mvp_bits", C.c_uint32),
+        ("lambda_sad", C.c_uint32),
+    ]
+
+
+class HopPredResult(C.Structure):
+    _fields_ = [("valid", C.c_int32), ("dist", C.c_uint32), ("cost", C.c_uint32)]
+
+
 class HopCtxStats(C.Structure):
     _fields_ = [("single_calls", C.c_uint64), ("cache_hits", C.c_uint64), ("cache_misses", C.c_uint64),
                 ("prefetched", C.c_uint64), ("prefetch_dropped", C.c_uint64), ("candidates", C.c_uint64)]
@@ -134,6 +149,14 @@ MOTION_JOB_DT = np.dtype([("search", SEARCH_JOB_DT), ("use_had", "<i4"), ("use_g
                           ("amvp", MV_DT, (HOP_MAX_PRED,))], align=True)
 MOTION_RES_DT = np.dtype([("search", SEARCH_RES_DT), ("refined", "<i4"), ("frac", FRAC_RES_DT), ("gt", GT_RES_DT)], align=True)
 
+PRED_JOB_DT = np.dtype([
+    ("ref_off", "<i8"), ("org_off", "<i8"), ("dst_off", "<i8"), ("ref_stride", "<i4"), ("org_stride", "<i4"), ("dst_stride", "<i4"),
+    ("cols", "<i4"), ("rows", "<i4"), ("comp", "<i4"), ("mv", MV_DT), ("gt_flag", "<i4"), ("gt", MV_DT, (4,)),
+    ("bit_depth", "<i4"), ("dist_func", "<i4"), ("template_cost", "<i4"), ("is_ss", "<i4"), ("mv_probe", MV_DT),
+    ("mvp_bits", "<u4"), ("lambda_sad", "<u4")], align=True)
+PRED_RES_DT = np.dtype([("valid", "<i4"), ("dist", "<u4"), ("cost", "<u4")], align=True)
+assert PRED_JOB_DT.itemsize == C.sizeof(HopPredJob) == 104, (PRED_JOB_DT.itemsize, C.sizeof(HopPredJob))
+assert PRED_RES_DT.itemsize == C.sizeof(HopPredResult) == 12
 assert FRAC_JOB_DT.itemsize == C.sizeof(HopFracJob), (FRAC_JOB_DT.itemsize, C.sizeof(HopFracJob))
 assert FRAC_RES_DT.itemsize == C.sizeof(HopFracResult) == 16
 assert MOTION_JOB_DT.itemsize == C.sizeof(HopMotionJob), (MOTION_JOB_DT.itemsize, C.sizeof(HopMotionJob))
@@ -168,6 +191,7 @@ ABI = [
     ("hop_dist_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_frac_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_motion_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    ("hop_predict_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_motion_search_prefetch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
     ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, C.c_int, C.c_int, _P]),
@@ -301,6 +325,16 @@ class HopContext:
         self._check(self.lib.hop_motion_search_batch(
             self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size, _ptr(out)))
         return out
+
+    def predict(self, jobs, org, ref, dst_samples=0):
+        """K6: motion-compensated prediction (+ distortion / template cost).  Returns (results, dst buffer)."""
+        jobs = np.ascontiguousarray(jobs, dtype=PRED_JOB_DT)
+        out = np.zeros(len(jobs), dtype=PRED_RES_DT)
+        dst = np.zeros(max(1, dst_samples), dtype=np.int16)
+        self._check(self.lib.hop_predict_batch(
+            self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size,
+            _ptr(dst) if dst_samples else None, dst_samples, _ptr(out)))
+        return out, dst
 
     def motion_prefetch(self, jobs, org):
         """Enqueue speculative single-PU motion searches against the SS mirror (hop_motion_search_prefetch)."""

@@ -872,6 +872,57 @@ int hop_frac_search_batch(HopCtx* ctx, int n, const HopFracJob* jobs, const int1
   return HOP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6: motion-compensated prediction (+ distortion / AMVP template cost)
+// ---------------------------------------------------------------------------------------------
+int hop_predict_batch(HopCtx* ctx, int n, const HopPredJob* jobs, const int16_t* org, size_t org_samples,
+                      const int16_t* ref, size_t ref_samples, int16_t* dst, size_t dst_samples, HopPredResult* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  int max_cols = 4, max_rows = 4;
+  bool any_gt = false, any_org = false, any_dst = false;
+  for (int i = 0; i < n; i++) {
+    const HopPredJob& j = jobs[i];
+    if (!shape_ok(j.cols, j.rows) || j.bit_depth < 8 || j.bit_depth > 12 || (j.comp != 0 && j.comp != 1) ||
+        (j.dist_func != 0 && j.dist_func != HOP_DF_SAD && j.dist_func != HOP_DF_HADS))
+      return fail(HOP_ERR_ARG, "job %d: unsupported PU %dx%d / bit depth %d / component %d / distortion %d", i, j.cols, j.rows, j.bit_depth, j.comp, j.dist_func);
+    if (j.comp && ((j.cols | j.rows) & 1)) return fail(HOP_ERR_ARG, "job %d: chroma of an odd-sized PU", i);
+    if (j.template_cost && j.comp) return fail(HOP_ERR_ARG, "job %d: the template cost is a luma quantity", i);
+    if (!ref && j.comp) return fail(HOP_ERR_ARG, "job %d: the SS mirror holds luma only; chroma jobs need an explicit plane", i);
+    const int bw = j.comp ? j.cols >> 1 : j.cols, bh = j.comp ? j.rows >> 1 : j.rows;
+    if (j.dist_func || j.template_cost) {
+      any_org = true;
+      if (!org || j.org_off < 0 || (size_t)j.org_off + (size_t)(bh - 1) * j.org_stride + bw > org_samples)
+        return fail(HOP_ERR_ARG, "job %d: original block outside the org buffer", i);
+    }
+    if (j.dst_off >= 0) {
+      any_dst = true;
+      if (!dst || (size_t)j.dst_off + (size_t)(bh - 1) * j.dst_stride + bw > dst_samples)
+        return fail(HOP_ERR_ARG, "job %d: prediction outside the dst buffer", i);
+    }
+    any_gt |= j.gt_flag != 0;
+    if (j.cols > max_cols) max_cols = j.cols;
+    if (j.rows > max_rows) max_rows = j.rows;
+  }
+  static const int16_t dummy_org = 0;
+  const int16_t* d_ref = nullptr;
+  st = stage_inputs(ctx, n, jobs, sizeof(HopPredJob), any_org ? org : &dummy_org, any_org ? org_samples : 1, ref, ref_samples,
+                    sizeof(HopPredResult) * (size_t)n, &d_ref);
+  if (st) return st;
+  if (any_dst && (st = ensure(ctx, ctx->sink, dst_samples * sizeof(int16_t) + 64))) return st;
+  int l = 0;
+  CU(predict_launch(n, (const HopPredJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, any_dst ? (int16_t*)ctx->sink.p : nullptr,
+                    (HopPredResult*)ctx->out.p, max_cols, max_rows, any_gt, ctx->stream, &l, bounds_for(ctx, ref == nullptr, ref_samples)));
+  ctx->launches += l;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopPredResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (any_dst) CU(cudaMemcpyAsync(dst, ctx->sink.p, dst_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
 int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const int16_t* org, size_t org_samples,
                             const int16_t* ref, size_t ref_samples, HopMotionResult* out)
 {

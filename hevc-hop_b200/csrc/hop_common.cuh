@@ -46,6 +46,47 @@ __host__ __device__ __forceinline__ bool sad_width_has_subshift(int cols)
          cols == 24 || cols == 48;
 }
 
+// One N x N Hadamard tile of the difference org - cur with the reference's per-tile rounding
+// (xCalcHADs2x2 / 4x4 / 8x8, TComRdCost.cpp:1366-1575): generic form for the stand-alone kernels (K3, K6).
+template <int N>
+__device__ __forceinline__ uint32_t had_tile(const int16_t* __restrict__ org, int so,
+                                             const int16_t* __restrict__ cur, int sc)
+{
+  int d[N * N];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int x = 0; x < N; x++) d[y * N + x] = (int)org[y * so + x] - (int)cur[y * sc + x];
+#pragma unroll
+  for (int y = 0; y < N; y++)
+#pragma unroll
+    for (int len = 1; len < N; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < N; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          int a = d[y * N + j], b = d[y * N + j + len];
+          d[y * N + j] = a + b; d[y * N + j + len] = a - b;
+        }
+#pragma unroll
+  for (int x = 0; x < N; x++)
+#pragma unroll
+    for (int len = 1; len < N; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < N; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          int a = d[j * N + x], b = d[(j + len) * N + x];
+          d[j * N + x] = a + b; d[(j + len) * N + x] = a - b;
+        }
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < N * N; k++) s += abs(d[k]);
+  if (N == 8) return (uint32_t)((s + 2) >> 2);
+  if (N == 4) return (uint32_t)((s + 1) >> 1);
+  return (uint32_t)s;
+}
+
 // block-wide min of a 64-bit key; result valid in every thread. `scratch` holds >= 32 entries.
 __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v,
                                                             unsigned long long* scratch)

@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, FRAC_JOB_DT, MOTION_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
+from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, FRAC_JOB_DT, MOTION_JOB_DT, PRED_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
 from .lenslet import lenslet_luma
 
 SEARCH_RANGE = 128
@@ -222,3 +222,66 @@ class GtBatch:
 
     def input_bytes(self):
         return self.org.nbytes + self.ref.nbytes + self.gt_jobs.nbytes
+
+
+class PredBatch:
+    """K6 jobs (motion-compensated prediction, GT and plain, luma and chroma, distortion / AMVP template cost) over
+    one picture-like plane: every PU sits far enough from the plane edges for its 2W x 2H region, the vector and the
+    8-tap support.  kind: "plain", "gt", "dist", "template"."""
+
+    def __init__(self, shapes, n_per_shape, seed=0, bit_depth=8, comp=0, kind="gt", frac=True, with_invalid=False):
+        rng = np.random.default_rng(seed)
+        pw, ph = 640, 400
+        plane = lenslet_luma(pw, ph, seed=seed, bit_depth=bit_depth).astype(np.int16)
+        if with_invalid:
+            plane[ph // 2:, pw // 2:] = -1            # not yet coded: the reference copies / filters these samples as they are
+        self.ref = plane.reshape(-1)
+        jobs, orgs, dst_off = [], [], 0
+        for (c, r) in shapes:
+            for _ in range(n_per_shape):
+                j = np.zeros(1, dtype=PRED_JOB_DT)
+                bw, bh = (c >> 1, r >> 1) if comp else (c, r)
+                px = int(rng.integers(200, pw - 200)); py = int(rng.integers(160, ph - 160))
+                j["ref_off"] = py * pw + px
+                j["ref_stride"] = pw
+                j["cols"], j["rows"], j["comp"], j["bit_depth"] = c, r, comp, bit_depth
+                mvx = int(rng.integers(-60, 60)) * 4; mvy = int(rng.integers(-60, 60)) * 4
+                if frac and kind != "gt":
+                    mvx += int(rng.integers(0, 4)); mvy += int(rng.integers(0, 4))
+                if kind == "gt" and comp:
+                    pass                                   # integer luma vectors: chroma sees 0 or half-pel fractions
+                if kind == "gt" and frac and rng.integers(0, 4) == 0:
+                    mvx += int(rng.integers(0, 4)); mvy += int(rng.integers(0, 4))   # the reference handles it; the search never produces it
+                j["mv"]["hor"], j["mv"]["ver"] = mvx, mvy
+                if kind == "gt":
+                    j["gt_flag"] = 1
+                    w = min(c, r) >> 1
+                    if rng.integers(0, 8) == 0:
+                        g = np.zeros((4, 2), dtype=np.int64)       # flag set, all-zero vectors: plain branch
+                    else:
+                        d0 = rng.integers(-w + 1, w, size=2); d1 = rng.integers(-w + 1, w, size=2); d2 = rng.integers(-w + 1, w, size=2)
+                        g = np.stack([d0, d1, d2, d0 - d1 + d2])   # parallelogram: what the affine search produces
+                        g = np.clip(g, -w + 1, w - 1)
+                    j["gt"]["hor"][0], j["gt"]["ver"][0] = g[:, 0], g[:, 1]
+                org = np.clip(plane[py:py + bh, px:px + bw] + rng.integers(-12, 13, size=(bh, bw)), 0, (1 << bit_depth) - 1).astype(np.int16)
+                j["org_off"] = sum(o.size for o in orgs)
+                j["org_stride"] = bw
+                orgs.append(org.reshape(-1))
+                j["dst_off"] = dst_off
+                j["dst_stride"] = bw
+                dst_off += bw * bh
+                if kind == "dist":
+                    j["dist_func"] = HOP_DF_HADS if rng.integers(0, 2) else HOP_DF_SAD
+                    if rng.integers(0, 2):
+                        j["gt_flag"] = 1
+                        j["gt"]["hor"][0] = [1, 2, 2, 1]; j["gt"]["ver"][0] = [-1, -1, 1, 1]
+                        j["mv"]["hor"], j["mv"]["ver"] = (mvx >> 2) << 2, (mvy >> 2) << 2
+                if kind == "template":
+                    j["template_cost"], j["is_ss"] = 1, int(rng.integers(0, 2))
+                    j["mv_probe"]["hor"] = mvx + int(rng.integers(-8, 9)); j["mv_probe"]["ver"] = mvy + int(rng.integers(-8, 9))
+                    j["mvp_bits"] = int(rng.integers(1, 4))
+                    j["lambda_sad"] = lambda_motion_sad(int(rng.integers(22, 38)))
+                jobs.append(j)
+        self.jobs = np.concatenate(jobs)
+        self.org = np.concatenate(orgs)
+        self.dst_samples = dst_off

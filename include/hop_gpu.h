@@ -174,6 +174,44 @@ typedef struct HopDistJob {
 } HopDistJob;
 
 /* ---------------------------------------------------------------------------------------------
+ * K6 -- motion-compensated prediction of one PU from one reference (uni-prediction, bi = false) and what the
+ * encoder computes from it:
+ *   TComPrediction::xPredInterLumaBlk / xPredInterChromaBlk  (TLibCommon/TComPrediction.cpp:639-720, 1235-1347)
+ *     - no GT: 8-tap / 4-tap DCT-IF interpolation at the vector's fraction (TComInterpolationFilter.cpp:92-420)
+ *     - GT   : the 2W x 2H region around the block is fetched (interpolated when the vector is fractional) and
+ *              warped by xPredGTLuma / xPredGTChroma (:723-805, 1351-1420) with calcParamProjective[C] (:807-859)
+ *              and ProjectiveTransform (:904-1030); chroma uses the half GT vectors in binary64
+ *   dist_func != 0: the distortion of the prediction against the original block, setDistParam(.., bHadamard) +
+ *              DistFunc as TEncSearch::xGetInterPredictionError (TLibEncoder/TEncSearch.cpp:2951-2977)
+ *   template != 0 : TEncSearch::xGetTemplateCost (:4390-4477): isValidPattern gate on the unclipped candidate
+ *              (TComRdCost.cpp:430-442), luma prediction at the clipped candidate, SAD, calcRdCost(bits, sad, DF_SAD)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HopPredJob {
+  int64_t  ref_off;        /* the PU's own position in the reference plane of `comp` (luma, Cb or Cr plane)  */
+  int64_t  org_off;        /* original block of that component (dist / template), ignored otherwise           */
+  int64_t  dst_off;        /* where the prediction goes in the dst buffer; < 0: not stored                     */
+  int32_t  ref_stride, org_stride, dst_stride;
+  int32_t  cols, rows;     /* LUMA size of the PU; a chroma job predicts cols/2 x rows/2                       */
+  int32_t  comp;           /* 0 = luma, 1 = chroma (either chroma plane)                                        */
+  HopMv    mv;             /* quarter-pel luma vector, already clipped (TComDataCU::clipMv is host code)        */
+  int32_t  gt_flag;        /* bUseGT; all-zero GT vectors take the plain branch as in the reference             */
+  HopMv    gt[4];          /* mGT0..mGT3                                                                        */
+  int32_t  bit_depth;      /* g_bitDepthY / g_bitDepthC                                                         */
+  int32_t  dist_func;      /* 0 = none, HOP_DF_SAD, HOP_DF_HADS                                                 */
+  int32_t  template_cost;  /* 1 = xGetTemplateCost semantics (luma, no GT)                                      */
+  int32_t  is_ss;          /* template: the reference is the SS reference => isValidPattern gate applies        */
+  HopMv    mv_probe;       /* template: cMvCand before clipMv                                                   */
+  uint32_t mvp_bits;       /* template: m_auiMVPIdxCost[iMVPIdx][iMVPNum]                                       */
+  uint32_t lambda_sad;     /* template: m_uiLambdaMotionSAD                                                     */
+} HopPredJob;
+
+typedef struct HopPredResult {
+  int32_t  valid;          /* template: 0 when the gate rejected the candidate (cost = MAX_INT then); else 1    */
+  uint32_t dist;           /* DistFunc result (0 when dist_func == 0 and template_cost == 0)                    */
+  uint32_t cost;           /* template: the returned uiCost; otherwise == dist                                  */
+} HopPredResult;
+
+/* ---------------------------------------------------------------------------------------------
  * Context: one per encoder instance = per GPU.  Owns a stream, scratch buffers and (optionally) the
  * device mirror of the SS reference luma plane (TEncTop::m_cSSRef / TComPicYuv, margin 80).
  * ------------------------------------------------------------------------------------------- */
@@ -233,6 +271,13 @@ int hop_frac_search_batch(HopCtx* ctx, int n, const HopFracJob* jobs,
                           const int16_t* org, size_t org_samples,
                           const int16_t* ref, size_t ref_samples,
                           HopFracResult* out);
+/* K6.  `ref` is the plane (of the component) the jobs' ref_off index; `dst` (dst_samples int16) receives the
+ * predictions of the jobs with dst_off >= 0 and may be NULL when no job stores one.  ref == NULL: luma jobs read the
+ * context's SS mirror. */
+int hop_predict_batch(HopCtx* ctx, int n, const HopPredJob* jobs,
+                      const int16_t* org, size_t org_samples,
+                      const int16_t* ref, size_t ref_samples,
+                      int16_t* dst, size_t dst_samples, HopPredResult* out);
 int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs,
                             const int16_t* org, size_t org_samples,
                             const int16_t* ref, size_t ref_samples,

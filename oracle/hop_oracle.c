@@ -4,10 +4,11 @@
  * Each function cites the reference lines (relative to /root/reference/source/Lib) it restates.
  * Build: gcc -O2 -ffp-contract=off, x86-64 baseline (SSE2 doubles, no FMA) -- the warp is IEEE
  * binary64 in the reference (build/linux/common/makefile.base:50,66: -O3, no -march) and must not be
- * contracted.  Parity pin: tests/test_oracle_vs_ref.py and tests/golden/ compare this file with the
+ * contracted.  Parity pin: tests/test_oracle_cpu.py (+ test_frac_motion.py, test_sweep.py, test_predict.py) and tests/golden/ compare this file with the
  * compiled reference itself (oracle/_ref/libhopref.so).
  */
 #include "hop_oracle.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -682,4 +683,170 @@ void orc_extend_border(int16_t* origin, int stride, int pic_w, int pic_h, int ma
   for (int y = 0; y < margin; y++) memcpy(pi + (y + 1) * stride, pi, sizeof(int16_t) * (pic_w + (margin << 1)));
   pi -= ((pic_h - 1) * stride);
   for (int y = 0; y < margin; y++) memcpy(pi - (y + 1) * stride, pi, sizeof(int16_t) * (pic_w + (margin << 1)));
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K6 -- motion-compensated prediction (uni-prediction) + what the encoder derives from it.
+ * xPredInterLumaBlk / xPredInterChromaBlk (TLibCommon/TComPrediction.cpp:639-720, 1235-1347) with the DCT-IF
+ * (TComInterpolationFilter.cpp:92-420), xPredGTLuma / xPredGTChroma (:723-805, 1351-1420),
+ * calcParamProjectiveC (:834-859), xGetInterPredictionError (TLibEncoder/TEncSearch.cpp:2951-2977),
+ * xGetTemplateCost (:4390-4477), isValidPattern (TLibCommon/TComRdCost.cpp:430-442), calcRdCost DF_SAD (:59-111).
+ * ---------------------------------------------------------------------------------------------- */
+static const int16_t CHROMA_FILTER[8][4] = {               /* m_chromaFilter, TComInterpolationFilter.cpp:63-73 */
+  {0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
+
+/* One sample of the block the three-way branch of xPredInter{Luma,Chroma}Blk writes for bi == false:
+ *   yFrac == 0 : filterHor(isLast)            (frac 0: filterCopy first == last, a plain copy: NOT_VALID stays -1)
+ *   xFrac == 0 : filterVer(isFirst, isLast)
+ *   else       : filterHor(!isLast) into the 14-bit intermediate, filterVer(!isFirst, isLast)
+ * `src` points at the integer position of the block's sample (0,0); taps = 8 (luma) or 4 (chroma). */
+static int16_t mc_sample(const int16_t* src, int stride, int x, int y, int fx, int fy, int taps, int bit_depth)
+{
+  const int half = taps / 2 - 1;
+  const int head = 14 - bit_depth;                            /* IF_INTERNAL_PREC - bitDepth */
+  const int16_t max_val = (int16_t)((1 << bit_depth) - 1);
+  const int16_t* cx = taps == 8 ? LUMA_FILTER[fx] : CHROMA_FILTER[fx];
+  const int16_t* cy = taps == 8 ? LUMA_FILTER[fy] : CHROMA_FILTER[fy];
+  const int16_t* s = src + y * stride + x;
+  if (fy == 0) {
+    if (fx == 0) return s[0];
+    int sum = 0;
+    for (int k = 0; k < taps; k++) sum += s[k - half] * cx[k];
+    int16_t v = (int16_t)((sum + 32) >> 6);                    /* isFirst && isLast: shift 6, offset 1 << 5 */
+    if (v < 0) v = 0;
+    if (v > max_val) v = max_val;
+    return v;
+  }
+  if (fx == 0) {
+    int sum = 0;
+    for (int k = 0; k < taps; k++) sum += s[(k - half) * stride] * cy[k];
+    int16_t v = (int16_t)((sum + 32) >> 6);
+    if (v < 0) v = 0;
+    if (v > max_val) v = max_val;
+    return v;
+  }
+  int sum2 = 0;
+  for (int r = 0; r < taps; r++) {
+    const int16_t* row = s + (r - half) * stride;
+    int sum = 0;
+    for (int k = 0; k < taps; k++) sum += row[k - half] * cx[k];
+    const int shift = 6 - head;                                /* isFirst && !isLast */
+    const int offset = -8192 << shift;
+    const int16_t t = (int16_t)((sum + offset) >> shift);
+    sum2 += t * cy[r];
+  }
+  const int shift = 6 + head;                                  /* !isFirst && isLast */
+  const int offset = (1 << (shift - 1)) + (8192 << 6);
+  int16_t v = (int16_t)((sum2 + offset) >> shift);
+  if (v < 0) v = 0;
+  if (v > max_val) v = max_val;
+  return v;
+}
+
+/* calcParamProjectiveC, TComPrediction.cpp:834-859 (corners in binary64) */
+static void calc_param_projective_c(const double x[4], const double y[4], double h[9], int width, int height)
+{
+  double H, W, dx[4], dy[4];
+  W = (double)width - 1.0;
+  H = (double)height - 1.0;
+  dx[1] = x[1] - x[2];
+  dx[2] = x[3] - x[2];
+  dx[3] = x[0] - x[1] + x[2] - x[3];
+  dy[1] = y[1] - y[2];
+  dy[2] = y[3] - y[2];
+  dy[3] = y[0] - y[1] + y[2] - y[3];
+  h[2] = ((dx[3] * dy[2] - dx[2] * dy[3]) / (dx[1] * dy[2] - dx[2] * dy[1])) / W;
+  h[5] = ((dx[1] * dy[3] - dx[3] * dy[1]) / (dx[1] * dy[2] - dx[2] * dy[1])) / H;
+  h[0] = (x[1] - x[0]) / W + h[2] * x[1];
+  h[3] = (x[3] - x[0]) / H + h[5] * x[3];
+  h[6] = x[0];
+  h[1] = (y[1] - y[0]) / W + h[2] * y[1];
+  h[4] = (y[3] - y[0]) / H + h[5] * y[3];
+  h[7] = y[0];
+  h[8] = 1.0;
+}
+
+void orc_predict(const HopPredJob* job, const int16_t* org_buf, const int16_t* ref_buf, int16_t* dst_buf, HopPredResult* out)
+{
+  const int chroma = job->comp != 0;
+  const int bw = chroma ? job->cols >> 1 : job->cols, bh = chroma ? job->rows >> 1 : job->rows;   /* block of this component */
+  const int taps = chroma ? 4 : 8;
+  const int fmask = chroma ? 7 : 3, fshift = chroma ? 3 : 2;
+  const int16_t* ref = ref_buf + job->ref_off;
+  const int stride = job->ref_stride;
+  int16_t* pred = (int16_t*)malloc(sizeof(int16_t) * bw * bh);
+  out->valid = 1; out->dist = 0; out->cost = 0;
+
+  if (job->template_cost && job->is_ss) {                                 /* TEncSearch.cpp:4420-4436, TComRdCost.cpp:430-442 */
+    const int16_t* cur = ref + (job->mv_probe.hor >> 2) + (job->mv_probe.ver >> 2) * stride;
+    const int16_t* lb = cur + (job->rows + 4) * stride;
+    const int16_t* rb = lb + (job->cols + 4);
+    if (*lb == HOP_NOT_VALID || *rb == HOP_NOT_VALID) {
+      out->valid = 0; out->cost = 0x7fffffffu;                            /* MAX_INT */
+      free(pred);
+      return;
+    }
+  }
+  const int gt_any = job->gt[0].hor | job->gt[1].hor | job->gt[2].hor | job->gt[3].hor |
+                     job->gt[0].ver | job->gt[1].ver | job->gt[2].ver | job->gt[3].ver;
+  const int fx = job->mv.hor & fmask, fy = job->mv.ver & fmask;
+  if (!job->gt_flag || !gt_any || job->template_cost) {                   /* plain branch (:651, 1246) */
+    const int16_t* src = ref + (job->mv.hor >> fshift) + (job->mv.ver >> fshift) * stride;
+    for (int y = 0; y < bh; y++)
+      for (int x = 0; x < bw; x++) pred[y * bw + x] = mc_sample(src, stride, x, y, fx, fy, taps, job->bit_depth);
+  } else {
+    /* the 2W x 2H region around the block (:683-712 luma, :1292-1330 chroma; width / 4 is on the LUMA width) */
+    const int ox = chroma ? job->cols / 4 : job->cols / 2, oy = chroma ? job->rows / 4 : job->rows / 2;
+    const int16_t* src = ref + (job->mv.hor >> fshift) - ox + ((job->mv.ver >> fshift) - oy) * stride;
+    const int W2 = 2 * bw, H2 = 2 * bh;
+    int16_t* reg = (int16_t*)malloc(sizeof(int16_t) * W2 * H2);
+    for (int y = 0; y < H2; y++)
+      for (int x = 0; x < W2; x++) reg[y * W2 + x] = mc_sample(src, stride, x, y, fx, fy, taps, job->bit_depth);
+    /* xPredGTLuma / xPredGTChroma on the component's block size (:723-805, 1351-1420) */
+    int nss = ((bh < bw) ? bh : bw) >> 1;
+    nss *= 2;                                                             /* IT_GT_GRID_SIZE */
+    int last_step = nss >> 6;                                             /* IT_MAX_NSS_Iteration */
+    if (last_step == 0) last_step = 1;
+    double h[9];
+    if (!chroma) {
+      int32_t cx[4], cy[4];
+      cx[0] = job->gt[0].hor * last_step;              cy[0] = job->gt[0].ver * last_step;
+      cx[1] = job->gt[1].hor * last_step + bw * 2 - 1; cy[1] = job->gt[1].ver * last_step;
+      cx[2] = job->gt[2].hor * last_step + bw * 2 - 1; cy[2] = job->gt[2].ver * last_step + bh * 2 - 1;
+      cx[3] = job->gt[3].hor * last_step;              cy[3] = job->gt[3].ver * last_step + bh * 2 - 1;
+      orc_calc_param_projective(cx, cy, h, bw * 2, bh * 2);
+    } else {
+      const double ls = (double)last_step;                                /* Double lastIterationStep (:1366) */
+      double cx[4], cy[4];
+      cx[0] = ((double)job->gt[0].hor / 2) * ls;                cy[0] = ((double)job->gt[0].ver / 2) * ls;
+      cx[1] = (((double)job->gt[1].hor / 2) * ls) + bw * 2 - 1; cy[1] = ((double)job->gt[1].ver / 2) * ls;
+      cx[2] = (((double)job->gt[2].hor / 2) * ls) + bw * 2 - 1; cy[2] = (((double)job->gt[2].ver / 2) * ls) + bh * 2 - 1;
+      cx[3] = ((double)job->gt[3].hor / 2) * ls;                cy[3] = (((double)job->gt[3].ver / 2) * ls) + bh * 2 - 1;
+      calc_param_projective_c(cx, cy, h, bw * 2, bh * 2);
+    }
+    orc_projective_transform(reg + bw / 2 + (bh / 2) * W2, pred, h, bw * 2, bh * 2, W2, (((bh < bw) ? bh : bw) >> 1) * 2);
+    free(reg);
+  }
+  if (job->dst_off >= 0 && dst_buf)
+    for (int y = 0; y < bh; y++)
+      for (int x = 0; x < bw; x++) dst_buf[job->dst_off + y * job->dst_stride + x] = pred[y * bw + x];
+  if (job->template_cost) {
+    /* getDistPart(.., DF_SAD) then calcRdCost(bits, dist, false, DF_SAD) (TEncSearch.cpp:4473-4474) */
+    const uint32_t sad = orc_sad(org_buf + job->org_off, job->org_stride, pred, bw, bw, bh, 0, job->bit_depth);
+    const double lambda = (double)job->lambda_sad;
+    double c = ((double)sad + (double)((int)(job->mvp_bits * lambda + .5) >> 16));
+    c = (double)(uint32_t)floor(c);
+    out->dist = sad;
+    out->cost = (uint32_t)c;
+  } else if (job->dist_func) {
+    out->dist = job->dist_func == HOP_DF_HADS ? orc_hads(org_buf + job->org_off, job->org_stride, pred, bw, bw, bh, job->bit_depth)
+                                              : orc_sad(org_buf + job->org_off, job->org_stride, pred, bw, bw, bh, 0, job->bit_depth);
+    out->cost = out->dist;
+  }
+  free(pred);
+}
+
+void orc_predict_batch(int n, const HopPredJob* jobs, const int16_t* org, const int16_t* ref, int16_t* dst, HopPredResult* out)
+{
+  for (int i = 0; i < n; i++) orc_predict(&jobs[i], org, ref, dst, &out[i]);
 }

@@ -6,7 +6,7 @@
  *
  * Parity pin: the reference ships no tests or golden vectors.  This restatement is
  * pinned against the reference ITSELF: oracle/_ref/libhopref.so is the unmodified reference compiled
- * from /root/reference/source plus ref_harness.cpp, and tests/test_oracle_vs_ref.py +
+ * from /root/reference/source plus ref_harness.cpp, and tests/test_oracle_cpu.py +
  * tests/golden/ (made by tests/golden/make_golden.py from libhopref.so) hold the outputs of the real
  * xPatternSearch / xPatternSearchGT / DistFunc on seeded inputs.
  *
@@ -78,6 +78,11 @@ void orc_gt_sweep_finalize(const HopGtJob* job, uint64_t key, HopGtResult* out);
 void orc_gt_sweep_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref, HopGtResult* out);
 void orc_gt_sweep_keys_batch(int n, const HopGtJob* jobs, const int16_t* org, const int16_t* ref,
                              int cand_begin, int cand_end, uint64_t* keys);
+
+/* K6: xPredInterLumaBlk / xPredInterChromaBlk incl. the GT branches (TComPrediction.cpp:639-805, 1235-1420), and
+ * xGetInterPredictionError / xGetTemplateCost on top (TEncSearch.cpp:2951-2977, 4390-4477). */
+void orc_predict(const HopPredJob* job, const int16_t* org, const int16_t* ref, int16_t* dst, HopPredResult* out);
+void orc_predict_batch(int n, const HopPredJob* jobs, const int16_t* org, const int16_t* ref, int16_t* dst, HopPredResult* out);
 
 /* K4: TComPicYuv::extendPicBorder luma part, TComPicYuv.cpp:236-274. plane points at sample (0,0). */
 void orc_extend_border(int16_t* origin, int stride, int pic_w, int pic_h, int margin);

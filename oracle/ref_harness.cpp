@@ -11,6 +11,25 @@
  * Used (a) to pin oracle/hop_oracle.c and to generate tests/golden/, (b) as the "reference" CPU
  * baseline of bench.py.  The job/result structs are those of include/hop_gpu.h.
  */
+// K6 drives xPredInterLumaBlk / xPredInterChromaBlk, which take a TComDataCU* and a TComPicYuv* only to turn
+// (CU address, z-order index) into a sample address.  The harness points a TComPicYuv at the caller's buffer by
+// setting its (private) geometry members directly -- access specifiers are opened for THIS translation unit only;
+// the reference's sources and objects are untouched and the class layouts do not depend on access specifiers.
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <list>
+#include <map>
+#include <string>
+#include <vector>
+#define private public
+#define protected public
 #include "TLibEncoder/TEncSearch.h"
 #include "TLibEncoder/TEncCfg.h"
 #include "TLibCommon/TComRdCost.h"
@@ -18,6 +37,10 @@
 #include "TLibCommon/TComPattern.h"
 #include "TLibCommon/TComPicYuv.h"
 #include "TLibCommon/TComRom.h"
+
+#include "TLibCommon/TComYuv.h"
+#undef private
+#undef protected
 
 #include "../include/hop_gpu.h"
 #include <string.h>
@@ -39,6 +62,7 @@ public:
     rd.init();                  // TComRdCost.cpp:177-233, fills m_afpDistortFunc
     initTempBuff();             // TComPrediction.cpp:81, allocates m_filteredBlock*
     m_cDistParam.bApplyWeight = false;   // what setWpScalingDistParam leaves for SS slices
+    predYuv = NULL;
   }
 
   void setCost(const HopCostState& cs)
@@ -134,6 +158,64 @@ public:
   void calcParam(Int* x, Int* y, Double* h, Int w, Int hh) { calcParamProjective(x, y, h, w, hh); }
   void warp(Pel* r, Pel* aux, Double* h, Int W, Int H, Int stride, Int nss) { ProjectiveTransform(r, aux, h, W, H, stride, nss); }
 
+  // K6: the reference's own xPredInterLumaBlk / xPredInterChromaBlk on the caller's plane (TComPrediction.cpp:639-720,
+  // 1235-1347), then -- in the order of xGetInterPredictionError (TEncSearch.cpp:2951-2977) and xGetTemplateCost
+  // (:4390-4477) -- the reference's own setDistParam / DistFunc, isValidPattern, getDistPart and calcRdCost.
+  TComYuv* predYuv;
+  UInt     zero_offsets[256];
+  void predict(const HopPredJob* j, const int16_t* org, const int16_t* refbuf, int16_t* dst, HopPredResult* out)
+  {
+    const bool chroma = j->comp != 0;
+    g_bitDepthY = j->bit_depth; g_bitDepthC = j->bit_depth;
+    if (!predYuv) { predYuv = new TComYuv; predYuv->create(64, 64); memset(zero_offsets, 0, sizeof(zero_offsets)); }
+    TComPicYuv pic;                                   // a view of the caller's plane: origin = the PU's own position
+    pic.m_cuOffsetY = (Int*)zero_offsets; pic.m_cuOffsetC = (Int*)zero_offsets;
+    pic.m_buOffsetY = (Int*)zero_offsets; pic.m_buOffsetC = (Int*)zero_offsets;
+    pic.m_piPicOrgY = (Pel*)refbuf + j->ref_off; pic.m_piPicOrgU = (Pel*)refbuf + j->ref_off; pic.m_piPicOrgV = (Pel*)refbuf + j->ref_off;
+    pic.m_iLumaMarginX = 0; pic.m_iChromaMarginX = 0;
+    pic.m_iPicWidth = chroma ? 2 * j->ref_stride : j->ref_stride;      // getStride() / getCStride() == ref_stride
+    cu.m_uiCUAddr = 0; cu.m_uiAbsIdxInLCU = 0;
+    TComMv mv(j->mv.hor, j->mv.ver), g0(j->gt[0].hor, j->gt[0].ver), g1(j->gt[1].hor, j->gt[1].ver),
+           g2(j->gt[2].hor, j->gt[2].ver), g3(j->gt[3].hor, j->gt[3].ver), zero(0, 0);
+    memset(out, 0, sizeof(*out));
+    out->valid = 1;
+    const int bw = chroma ? j->cols >> 1 : j->cols, bh = chroma ? j->rows >> 1 : j->rows;
+    if (j->template_cost) {
+      TComMv probe(j->mv_probe.hor, j->mv_probe.ver);
+      if (j->is_ss && !rd.isValidPattern(pic.getLumaAddr(0, 0), pic.getStride(), probe, j->cols, j->rows)) {   // :4420-4436
+        out->valid = 0; out->cost = MAX_INT;
+        pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL; pic.m_piPicOrgY = pic.m_piPicOrgU = pic.m_piPicOrgV = NULL;
+        return;
+      }
+      xPredInterLumaBlk(&cu, &pic, 0, &mv, j->cols, j->rows, predYuv, false, false, &zero, &zero, &zero, &zero);   // :4451-4455
+      double s = ((double)j->lambda_sad + 0.5) / 65536.0;      // m_uiLambdaMotionSAD is private: set it through setLambda
+      rd.setLambda(s * s);
+      UInt c = rd.getDistPart(g_bitDepthY, predYuv->getLumaAddr(0), predYuv->getStride(), (Pel*)org + j->org_off, j->org_stride,
+                              j->cols, j->rows, TEXT_LUMA, DF_SAD);                                                 // :4473
+      out->dist = c;
+      out->cost = (UInt)rd.calcRdCost(j->mvp_bits, c, false, DF_SAD);                                               // :4474
+    } else {
+      if (!chroma) xPredInterLumaBlk(&cu, &pic, 0, &mv, j->cols, j->rows, predYuv, false, j->gt_flag != 0, &g0, &g1, &g2, &g3);
+      else         xPredInterChromaBlk(&cu, &pic, 0, &mv, j->cols, j->rows, predYuv, false, j->gt_flag != 0, &g0, &g1, &g2, &g3);
+      if (j->dist_func) {
+        DistParam dp;
+        dp.bApplyWeight = false;
+        Pel* p = chroma ? predYuv->getCbAddr(0) : predYuv->getLumaAddr(0);
+        rd.setDistParam(dp, j->bit_depth, (Pel*)org + j->org_off, j->org_stride, p, chroma ? predYuv->getCStride() : predYuv->getStride(),
+                        bw, bh, j->dist_func == HOP_DF_HADS);                                                      // :2971-2975
+        out->dist = dp.DistFunc(&dp);
+        out->cost = out->dist;
+      }
+    }
+    if (j->dst_off >= 0 && dst) {
+      Pel* p = chroma ? predYuv->getCbAddr(0) : predYuv->getLumaAddr(0);
+      const int st = chroma ? predYuv->getCStride() : predYuv->getStride();
+      for (int y = 0; y < bh; y++) for (int x = 0; x < bw; x++) dst[j->dst_off + y * j->dst_stride + x] = p[y * st + x];
+    }
+    // the view owns nothing: detach before the destructor of TComPicYuv runs
+    pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL; pic.m_piPicOrgY = pic.m_piPicOrgU = pic.m_piPicOrgV = NULL;
+  }
+
   uint32_t dist(const HopDistJob* j, const int16_t* org, const int16_t* cur)
   {
     DistParam dp;
@@ -183,6 +265,9 @@ void ref_pattern_search_gt_batch(int n, const HopGtJob* jobs, const int16_t* org
 
 void ref_frac_search_batch(int n, const HopFracJob* jobs, const int16_t* org, const int16_t* refbuf, HopFracResult* out)
 { for (int i = 0; i < n; i++) ref()->fracSearch(&jobs[i], org, refbuf, &out[i]); }
+
+void ref_predict_batch(int n, const HopPredJob* jobs, const int16_t* org, const int16_t* refbuf, int16_t* dst, HopPredResult* out)
+{ for (int i = 0; i < n; i++) ref()->predict(&jobs[i], org, refbuf, dst, &out[i]); }
 
 void ref_frac_plane(int ver, int hor, int16_t* dst, int cols, int rows) { ref()->fracPlane(ver, hor, dst, cols, rows); }
 

@@ -128,6 +128,19 @@ def motion_search(jobs, org, ref):
     return out
 
 
+def predict(jobs, org, ref, dst_samples, which="orc"):
+    """K6 (prediction + distortion / template cost): C restatement ("orc") or the compiled reference ("ref")."""
+    chk = oracle() if which == "orc" else ref_lib()
+    hop = oracle().hop
+    jobs = np.ascontiguousarray(jobs, dtype=hop.PRED_JOB_DT)
+    out = np.zeros(len(jobs), dtype=hop.PRED_RES_DT)
+    dst = np.zeros(max(1, dst_samples), dtype=np.int16)
+    fn = getattr(chk.lib, ("orc_" if which == "orc" else "ref_") + "predict_batch")
+    fn.argtypes = [C.c_int, _P, _P, _P, _P, _P]; fn.restype = None
+    fn(len(jobs), _np(jobs), _np(org), _np(ref), _np(dst), _np(out))
+    return out, dst
+
+
 def ref_lib():
     return ref()
 
