@@ -912,7 +912,11 @@ int hop_predict_batch(HopCtx* ctx, int n, const HopPredJob* jobs, const int16_t*
   st = stage_inputs(ctx, n, jobs, sizeof(HopPredJob), any_org ? org : &dummy_org, any_org ? org_samples : 1, ref, ref_samples,
                     sizeof(HopPredResult) * (size_t)n, &d_ref);
   if (st) return st;
-  if (any_dst && (st = ensure(ctx, ctx->sink, dst_samples * sizeof(int16_t) + 64))) return st;
+  if (any_dst) {
+    if ((st = ensure(ctx, ctx->sink, dst_samples * sizeof(int16_t) + 64))) return st;
+    // samples no job writes (gaps, candidates the template gate rejected) come back as the caller's buffer holds them
+    CU(cudaMemcpyAsync(ctx->sink.p, dst, dst_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
   int l = 0;
   CU(predict_launch(n, (const HopPredJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, any_dst ? (int16_t*)ctx->sink.p : nullptr,
                     (HopPredResult*)ctx->out.p, max_cols, max_rows, any_gt, ctx->stream, &l, bounds_for(ctx, ref == nullptr, ref_samples)));
