@@ -107,6 +107,11 @@ class HopPredResult(C.Structure):
     _fields_ = [("valid", C.c_int32), ("dist", C.c_uint32), ("cost", C.c_uint32)]
 
 
+class HopIntraJob(C.Structure):
+    _fields_ = [("org_off", C.c_int64), ("refs_off", C.c_int64), ("org_stride", C.c_int32), ("size", C.c_int32),
+                ("above_avail", C.c_int32), ("left_avail", C.c_int32), ("bit_depth", C.c_int32), ("reserved", C.c_int32)]
+
+
 class HopCtxStats(C.Structure):
     _fields_ = [("single_calls", C.c_uint64), ("cache_hits", C.c_uint64), ("cache_misses", C.c_uint64),
                 ("prefetched", C.c_uint64), ("prefetch_dropped", C.c_uint64), ("candidates", C.c_uint64)]
@@ -154,6 +159,10 @@ PRED_JOB_DT = np.dtype([
     ("cols", "<i4"), ("rows", "<i4"), ("comp", "<i4"), ("mv", MV_DT), ("gt_flag", "<i4"), ("gt", MV_DT, (4,)),
     ("bit_depth", "<i4"), ("dist_func", "<i4"), ("template_cost", "<i4"), ("is_ss", "<i4"), ("mv_probe", MV_DT),
     ("mvp_bits", "<u4"), ("lambda_sad", "<u4")], align=True)
+INTRA_JOB_DT = np.dtype([("org_off", "<i8"), ("refs_off", "<i8"), ("org_stride", "<i4"), ("size", "<i4"), ("above_avail", "<i4"),
+                         ("left_avail", "<i4"), ("bit_depth", "<i4"), ("reserved", "<i4")], align=True)
+HOP_INTRA_MODES = 35
+assert INTRA_JOB_DT.itemsize == C.sizeof(HopIntraJob) == 40
 PRED_RES_DT = np.dtype([("valid", "<i4"), ("dist", "<u4"), ("cost", "<u4")], align=True)
 assert PRED_JOB_DT.itemsize == C.sizeof(HopPredJob) == 104, (PRED_JOB_DT.itemsize, C.sizeof(HopPredJob))
 assert PRED_RES_DT.itemsize == C.sizeof(HopPredResult) == 12
@@ -192,6 +201,7 @@ ABI = [
     ("hop_frac_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_motion_search_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_predict_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    ("hop_intra_prescreen_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_motion_search_prefetch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
     ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, C.c_int, C.c_int, _P]),
@@ -335,6 +345,14 @@ class HopContext:
             self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(ref), 0 if ref is None else ref.size,
             _ptr(dst) if dst_samples else None, dst_samples, _ptr(out)))
         return out, dst
+
+    def intra_prescreen(self, jobs, org, refs):
+        """K7: Hadamard cost of the 35 intra predictions of every PU -> (n, 35) uint32."""
+        jobs = np.ascontiguousarray(jobs, dtype=INTRA_JOB_DT)
+        refs = np.ascontiguousarray(refs, dtype=np.int32)
+        out = np.zeros((len(jobs), HOP_INTRA_MODES), dtype=np.uint32)
+        self._check(self.lib.hop_intra_prescreen_batch(self.h, len(jobs), _ptr(jobs), _ptr(org), org.size, _ptr(refs), refs.size, _ptr(out)))
+        return out
 
     def motion_prefetch(self, jobs, org):
         """Enqueue speculative single-PU motion searches against the SS mirror (hop_motion_search_prefetch)."""

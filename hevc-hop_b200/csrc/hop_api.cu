@@ -927,6 +927,43 @@ int hop_predict_batch(HopCtx* ctx, int n, const HopPredJob* jobs, const int16_t*
   return HOP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7: intra mode pre-screen
+// ---------------------------------------------------------------------------------------------
+int hop_intra_prescreen_batch(HopCtx* ctx, int n, const HopIntraJob* jobs, const int16_t* org, size_t org_samples,
+                              const int32_t* refs, size_t refs_count, uint32_t* out)
+{
+  int st = bind(ctx);
+  if (st) return st;
+  if (n < 0 || (n > 0 && (!jobs || !org || !refs || !out))) return fail(HOP_ERR_ARG, "NULL argument");
+  if (n == 0) return HOP_OK;
+  int max_size = 4;
+  for (int i = 0; i < n; i++) {
+    const HopIntraJob& j = jobs[i];
+    if ((j.size != 4 && j.size != 8 && j.size != 16 && j.size != 32 && j.size != 64) || j.bit_depth < 8 || j.bit_depth > 12)
+      return fail(HOP_ERR_ARG, "job %d: unsupported block %dx%d / bit depth %d", i, j.size, j.size, j.bit_depth);
+    if (j.org_off < 0 || (size_t)j.org_off + (size_t)(j.size - 1) * j.org_stride + j.size > org_samples)
+      return fail(HOP_ERR_ARG, "job %d: original block outside the org buffer", i);
+    if (j.refs_off < 0 || (size_t)j.refs_off + 4 * (size_t)(2 * j.size + 1) > refs_count)
+      return fail(HOP_ERR_ARG, "job %d: reference samples outside the refs buffer", i);
+    if (j.size > max_size) max_size = j.size;
+  }
+  if ((st = ensure(ctx, ctx->jobs, sizeof(HopIntraJob) * (size_t)n))) return st;
+  if ((st = ensure(ctx, ctx->org, org_samples * sizeof(int16_t)))) return st;
+  if ((st = ensure(ctx, ctx->ref, refs_count * sizeof(int32_t)))) return st;
+  if ((st = ensure(ctx, ctx->out, sizeof(uint32_t) * HOP_INTRA_MODES * (size_t)n))) return st;
+  CU(cudaMemcpyAsync(ctx->jobs.p, jobs, sizeof(HopIntraJob) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->org.p, org, org_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->ref.p, refs, refs_count * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  int l = 0;
+  CU(intra_launch(n, (const HopIntraJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, (const int32_t*)ctx->ref.p, (uint32_t*)ctx->out.p,
+                  max_size, ctx->stream, &l));
+  ctx->launches += l;
+  CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(uint32_t) * HOP_INTRA_MODES * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
 int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const int16_t* org, size_t org_samples,
                             const int16_t* ref, size_t ref_samples, HopMotionResult* out)
 {

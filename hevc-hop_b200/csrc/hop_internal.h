@@ -107,6 +107,9 @@ cudaError_t dist_launch(int n, const HopDistJob* d_jobs, const int16_t* d_org, c
 cudaError_t predict_launch(int n, const HopPredJob* d_jobs, const int16_t* d_org, const int16_t* d_ref, int16_t* d_dst,
                            HopPredResult* d_out, int max_cols, int max_rows, bool any_gt, cudaStream_t stream, int* launches,
                            RefBounds rb = REF_UNBOUNDED);
+// K7
+cudaError_t intra_launch(int n, const HopIntraJob* d_jobs, const int16_t* d_org, const int32_t* d_refs, uint32_t* d_out,
+                         int max_size, cudaStream_t stream, int* launches);
 // K4
 cudaError_t ref_fill_launch(int16_t* d_plane, size_t samples, int value, cudaStream_t stream, int* launches);
 cudaError_t ref_extend_launch(int16_t* d_origin, int stride, int pic_w, int pic_h, int margin,

@@ -12,7 +12,7 @@ import math
 
 import numpy as np
 
-from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, FRAC_JOB_DT, MOTION_JOB_DT, PRED_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
+from . import GT_JOB_DT, SEARCH_JOB_DT, DIST_JOB_DT, FRAC_JOB_DT, MOTION_JOB_DT, PRED_JOB_DT, INTRA_JOB_DT, HOP_DF_HADS, HOP_DF_SAD
 from .lenslet import lenslet_luma
 
 SEARCH_RANGE = 128
@@ -285,3 +285,36 @@ class PredBatch:
         self.jobs = np.concatenate(jobs)
         self.org = np.concatenate(orgs)
         self.dst_samples = dst_off
+
+
+def intra_jobs(sizes, n_per_size, seed=0, bit_depth=8):
+    """K7 jobs: per PU an original block and the four reference-sample arrays (unfiltered / filtered, above / left,
+    2N+1 entries each, entry 0 = corner) as TComPattern::initAdiPattern would leave them: the unfiltered samples come
+    from the picture around the block, the filtered ones are their [1 2 1] smoothing (any values exercise the
+    predictors; the pre-screen only reads them)."""
+    rng = np.random.default_rng(seed)
+    maxv = (1 << bit_depth) - 1
+    src = lenslet_luma(512, 512, seed=seed, bit_depth=bit_depth).astype(np.int64)
+    jobs, orgs, refs = [], [], []
+    for n in sizes:
+        for _ in range(n_per_size):
+            j = np.zeros(1, dtype=INTRA_JOB_DT)
+            y, x = int(rng.integers(1, 512 - 2 * n - 1)), int(rng.integers(1, 512 - 2 * n - 1))
+            org = src[y:y + n, x:x + n]
+            above = src[y - 1, x - 1:x + 2 * n].copy()            # corner + 2N above
+            left = src[y - 1:y + 2 * n, x - 1].copy()             # corner + 2N left
+            if rng.integers(0, 4) == 0:
+                above[:] = left[:] = 1 << (bit_depth - 1)         # no neighbours: the default fill
+            line = np.concatenate([left[:0:-1], above])           # bottom-left ... corner ... top-right
+            fl = line.copy()
+            fl[1:-1] = (line[:-2] + 2 * line[1:-1] + line[2:] + 2) >> 2
+            f_left, f_above = fl[2 * n::-1].copy(), fl[2 * n:].copy()
+            j["org_off"] = sum(o.size for o in orgs)
+            j["org_stride"] = n
+            j["refs_off"] = sum(r.size for r in refs)
+            j["size"], j["bit_depth"] = n, bit_depth
+            j["above_avail"], j["left_avail"] = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            orgs.append(np.clip(org + rng.integers(-6, 7, size=org.shape), 0, maxv).astype(np.int16).reshape(-1))
+            refs.append(np.concatenate([above, left, f_above, f_left]).astype(np.int32))
+            jobs.append(j)
+    return np.concatenate(jobs), np.concatenate(orgs), np.concatenate(refs)

@@ -212,6 +212,31 @@ typedef struct HopPredResult {
 } HopPredResult;
 
 /* ---------------------------------------------------------------------------------------------
+ * K7 -- intra mode pre-screen of one PU: the 35 predictions of TComPrediction::predIntraLumaAng
+ * (TLibCommon/TComPrediction.cpp:316-348: xPredIntraPlanar :1468-1510, xPredIntraAng :192-314 with the DC value
+ * :129-170, the edge filters of the pure horizontal / vertical modes and xDCPredFiltering :1524-1546 for blocks up
+ * to 16x16) and their Hadamard cost TComRdCost::calcHAD (TLibCommon/TComRdCost.cpp:391-425) against the original
+ * block -- the loop TEncSearch::estIntraPredQT runs per PU (TLibEncoder/TEncSearch.cpp:2451-2464).  The mode bits
+ * (CABAC state) and the candidate list stay on the host.
+ * Reference samples: what TComPattern::initAdiPattern left in m_piYuvExt, border row / column only, int32:
+ *   refs[refs_off + 0*(2N+1) + k] = unfiltered above  (k = 0 is the corner sample, k = 1..2N the row above)
+ *   refs[refs_off + 1*(2N+1) + k] = unfiltered left   (k = 0 the corner again, k = 1..2N the column to the left)
+ *   refs[refs_off + 2*(2N+1) + k], [.. + 3*(2N+1) + k] = the same two from the filtered buffer
+ * (TComPattern::getPredictorPtr :583-607 picks filtered / unfiltered per mode and size.)
+ * ------------------------------------------------------------------------------------------- */
+#define HOP_INTRA_MODES 35
+typedef struct HopIntraJob {
+  int64_t  org_off;        /* original block, size x size                                                  */
+  int64_t  refs_off;       /* into the int32 refs buffer, 4 * (2 * size + 1) entries                        */
+  int32_t  org_stride;
+  int32_t  size;           /* N = 4, 8, 16, 32 or 64                                                        */
+  int32_t  above_avail;    /* bAbove / bLeft of initAdiPattern: only the DC mode reads them                  */
+  int32_t  left_avail;
+  int32_t  bit_depth;
+  int32_t  reserved;
+} HopIntraJob;
+
+/* ---------------------------------------------------------------------------------------------
  * Context: one per encoder instance = per GPU.  Owns a stream, scratch buffers and (optionally) the
  * device mirror of the SS reference luma plane (TEncTop::m_cSSRef / TComPicYuv, margin 80).
  * ------------------------------------------------------------------------------------------- */
@@ -278,6 +303,10 @@ int hop_predict_batch(HopCtx* ctx, int n, const HopPredJob* jobs,
                       const int16_t* org, size_t org_samples,
                       const int16_t* ref, size_t ref_samples,
                       int16_t* dst, size_t dst_samples, HopPredResult* out);
+/* K7.  out receives HOP_INTRA_MODES values per job (mode 0 = planar, 1 = DC, 2..34 angular): uiSad of :2458. */
+int hop_intra_prescreen_batch(HopCtx* ctx, int n, const HopIntraJob* jobs,
+                              const int16_t* org, size_t org_samples,
+                              const int32_t* refs, size_t refs_count, uint32_t* out);
 int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs,
                             const int16_t* org, size_t org_samples,
                             const int16_t* ref, size_t ref_samples,

@@ -850,3 +850,143 @@ void orc_predict_batch(int n, const HopPredJob* jobs, const int16_t* org, const 
 {
   for (int i = 0; i < n; i++) orc_predict(&jobs[i], org, ref, dst, &out[i]);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * K7 -- intra mode pre-screen: predIntraLumaAng for the 35 modes + calcHAD
+ * (TLibCommon/TComPrediction.cpp:129-170, 192-348, 1468-1546; TComPattern.cpp:49-56, 583-607;
+ *  TComRdCost.cpp:391-425; the caller's loop TLibEncoder/TEncSearch.cpp:2451-2464).
+ * above[k] = pSrc[k - srcStride - 1], left[k] = pSrc[(k - 1) * srcStride - 1]  (k = 0: the corner sample).
+ * ---------------------------------------------------------------------------------------------- */
+static const unsigned char INTRA_FILTER[5] = {10, 7, 1, 0, 10};      /* m_aucIntraFilter, TComPattern.cpp:49-56 */
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
+void orc_intra_predict(const int32_t* above, const int32_t* left, int n, int mode, int bit_depth, int above_avail, int left_avail,
+                       int16_t* dst /* n x n, stride n */)
+{
+  const int filter_edges = n <= 16;                                   /* predIntraLumaAng :333-346 */
+  if (n < 4 || n > 64) return;
+  if (mode == 0) {                                                    /* xPredIntraPlanar :1468-1510 */
+    int left_col[65], top_row[65], bottom_row[64], right_col[64];
+    const int shift1 = ilog2(n), shift2 = shift1 + 1;
+    for (int k = 0; k < n + 1; k++) { top_row[k] = above[k + 1]; left_col[k] = left[k + 1]; }
+    const int bottom_left = left_col[n], top_right = top_row[n];
+    for (int k = 0; k < n; k++) {
+      bottom_row[k] = bottom_left - top_row[k];
+      right_col[k] = top_right - left_col[k];
+      top_row[k] <<= shift1;
+      left_col[k] <<= shift1;
+    }
+    for (int k = 0; k < n; k++) {
+      int hor = left_col[k] + n;
+      for (int l = 0; l < n; l++) {
+        hor += right_col[k];
+        top_row[l] += bottom_row[l];
+        dst[k * n + l] = (int16_t)((hor + top_row[l]) >> shift2);
+      }
+    }
+    return;
+  }
+  if (mode == 1) {                                                    /* DC: predIntraGetPredValDC :129-170 */
+    int sum = 0;
+    int16_t dc;
+    if (above_avail) for (int i = 0; i < n; i++) sum += above[i + 1];
+    if (left_avail) for (int i = 0; i < n; i++) sum += left[i + 1];
+    if (above_avail && left_avail) dc = (int16_t)((sum + n) / (n + n));
+    else if (above_avail) dc = (int16_t)((sum + n / 2) / n);
+    else if (left_avail) dc = (int16_t)((sum + n / 2) / n);
+    else dc = (int16_t)left[1];                                        /* pSrc[-1] */
+    for (int k = 0; k < n * n; k++) dst[k] = dc;
+    if (filter_edges && above_avail && left_avail) {                  /* xDCPredFiltering :1524-1546 */
+      dst[0] = (int16_t)((above[1] + left[1] + 2 * dst[0] + 2) >> 2);
+      for (int x = 1; x < n; x++) dst[x] = (int16_t)((above[x + 1] + 3 * dst[x] + 2) >> 2);
+      for (int y = 1; y < n; y++) dst[y * n] = (int16_t)((left[y + 1] + 3 * dst[y * n] + 2) >> 2);
+    }
+    return;
+  }
+  /* xPredIntraAng :192-314 */
+  static const int ang_table[9] = {0, 2, 5, 9, 13, 17, 21, 26, 32};
+  static const int inv_ang_table[9] = {0, 4096, 1638, 910, 630, 482, 390, 315, 256};
+  const int mode_hor = mode < 18, mode_ver = !mode_hor;
+  int angle = mode_ver ? mode - 26 : -(mode - 10);
+  int abs_ang = abs(angle);
+  const int sign = angle < 0 ? -1 : 1;
+  const int inv_angle = inv_ang_table[abs_ang];
+  abs_ang = ang_table[abs_ang];
+  angle = sign * abs_ang;
+  int16_t ref_above[2 * 64 + 1], ref_left[2 * 64 + 1];
+  int16_t *ref_main, *ref_side;
+  if (angle < 0) {
+    for (int k = 0; k < n + 1; k++) ref_above[k + n - 1] = (int16_t)above[k];
+    for (int k = 0; k < n + 1; k++) ref_left[k + n - 1] = (int16_t)left[k];
+    ref_main = (mode_ver ? ref_above : ref_left) + (n - 1);
+    ref_side = (mode_ver ? ref_left : ref_above) + (n - 1);
+    int inv_sum = 128;
+    for (int k = -1; k > (n * angle) >> 5; k--) {
+      inv_sum += inv_angle;
+      ref_main[k] = ref_side[inv_sum >> 8];
+    }
+  } else {
+    for (int k = 0; k < 2 * n + 1; k++) ref_above[k] = (int16_t)above[k];
+    for (int k = 0; k < 2 * n + 1; k++) ref_left[k] = (int16_t)left[k];
+    ref_main = mode_ver ? ref_above : ref_left;
+    ref_side = mode_ver ? ref_left : ref_above;
+  }
+  if (angle == 0) {
+    for (int k = 0; k < n; k++)
+      for (int l = 0; l < n; l++) dst[k * n + l] = ref_main[l + 1];
+    if (filter_edges) {
+      const int max_val = (1 << bit_depth) - 1;
+      for (int k = 0; k < n; k++) {
+        int v = dst[k * n] + ((ref_side[k + 1] - ref_side[0]) >> 1);
+        dst[k * n] = (int16_t)(v < 0 ? 0 : (v > max_val ? max_val : v));
+      }
+    }
+  } else {
+    int delta_pos = 0;
+    for (int k = 0; k < n; k++) {
+      delta_pos += angle;
+      const int delta_int = delta_pos >> 5, delta_fract = delta_pos & 31;
+      if (delta_fract) {
+        for (int l = 0; l < n; l++) {
+          const int idx = l + delta_int + 1;
+          dst[k * n + l] = (int16_t)(((32 - delta_fract) * ref_main[idx] + delta_fract * ref_main[idx + 1] + 16) >> 5);
+        }
+      } else {
+        for (int l = 0; l < n; l++) dst[k * n + l] = ref_main[l + delta_int + 1];
+      }
+    }
+  }
+  if (mode_hor)                                                       /* flip */
+    for (int k = 0; k < n - 1; k++)
+      for (int l = k + 1; l < n; l++) { int16_t t = dst[k * n + l]; dst[k * n + l] = dst[l * n + k]; dst[l * n + k] = t; }
+}
+
+void orc_intra_prescreen(const HopIntraJob* job, const int16_t* org_buf, const int32_t* refs, uint32_t* out /* 35 */)
+{
+  const int n = job->size, sw = 2 * n + 1, lg = ilog2(n);
+  const int32_t* r = refs + job->refs_off;
+  int16_t* pred = (int16_t*)malloc(sizeof(int16_t) * n * n);
+  for (int mode = 0; mode < HOP_INTRA_MODES; mode++) {
+    /* TComPattern::getPredictorPtr :583-607 */
+    int diff = abs(mode - 10) < abs(mode - 26) ? abs(mode - 10) : abs(mode - 26);
+    int filt = diff > INTRA_FILTER[lg - 2] ? 1 : 0;
+    if (mode == 1) filt = 0;
+    const int32_t* above = r + (filt ? 2 : 0) * sw;
+    const int32_t* left = above + sw;
+    orc_intra_predict(above, left, n, mode, job->bit_depth, job->above_avail, job->left_avail, pred);
+    /* calcHAD :391-425: 8x8 tiles when both sizes are multiples of 8, else 4x4 */
+    const int t = (n % 8 == 0) ? 8 : 4;
+    uint32_t sum = 0;
+    const int16_t* org = org_buf + job->org_off;
+    for (int y = 0; y < n; y += t)
+      for (int x = 0; x < n; x += t) sum += had_tile(org + y * job->org_stride + x, pred + y * n + x, job->org_stride, n, t);
+    out[mode] = sum >> DIST_SHIFT(job->bit_depth);
+  }
+  free(pred);
+}
+
+void orc_intra_prescreen_batch(int n, const HopIntraJob* jobs, const int16_t* org, const int32_t* refs, uint32_t* out)
+{
+  for (int i = 0; i < n; i++) orc_intra_prescreen(&jobs[i], org, refs, out + (size_t)i * HOP_INTRA_MODES);
+}

@@ -84,6 +84,12 @@ void orc_gt_sweep_keys_batch(int n, const HopGtJob* jobs, const int16_t* org, co
 void orc_predict(const HopPredJob* job, const int16_t* org, const int16_t* ref, int16_t* dst, HopPredResult* out);
 void orc_predict_batch(int n, const HopPredJob* jobs, const int16_t* org, const int16_t* ref, int16_t* dst, HopPredResult* out);
 
+/* K7: the 35 intra predictions of predIntraLumaAng (TComPrediction.cpp:129-170, 192-348, 1468-1546) and calcHAD
+ * (TComRdCost.cpp:391-425) for one PU -- the pre-screen loop of estIntraPredQT (TEncSearch.cpp:2451-2464). */
+void orc_intra_predict(const int32_t* above, const int32_t* left, int n, int mode, int bit_depth, int above_avail, int left_avail, int16_t* dst);
+void orc_intra_prescreen(const HopIntraJob* job, const int16_t* org, const int32_t* refs, uint32_t* out);
+void orc_intra_prescreen_batch(int n, const HopIntraJob* jobs, const int16_t* org, const int32_t* refs, uint32_t* out);
+
 /* K4: TComPicYuv::extendPicBorder luma part, TComPicYuv.cpp:236-274. plane points at sample (0,0). */
 void orc_extend_border(int16_t* origin, int stride, int pic_w, int pic_h, int margin);
 

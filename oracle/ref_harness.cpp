@@ -216,6 +216,28 @@ public:
     pic.m_cuOffsetY = pic.m_cuOffsetC = pic.m_buOffsetY = pic.m_buOffsetC = NULL; pic.m_piPicOrgY = pic.m_piPicOrgU = pic.m_piPicOrgV = NULL;
   }
 
+  // K7: the reference's own predIntraLumaAng + calcHAD for the 35 modes (TEncSearch.cpp:2451-2464).  m_piYuvExt gets the
+  // caller's reference samples in the layout initAdiPattern leaves (border row / column of the unfiltered buffer, then of
+  // the filtered one, TComPattern.cpp:583-607); the interior of the two buffers is never read by the predictors.
+  void intraPrescreen(const HopIntraJob* j, const int16_t* org, const int32_t* refs, uint32_t* out)
+  {
+    g_bitDepthY = j->bit_depth;
+    const int n = j->size, sw = 2 * n + 1;
+    const int32_t* r = refs + j->refs_off;
+    for (int f = 0; f < 2; f++) {
+      Int* buf = m_piYuvExt + f * sw * sw;
+      for (int k = 0; k < sw; k++) { buf[k] = r[(2 * f) * sw + k]; buf[k * sw] = r[(2 * f + 1) * sw + k]; }
+      buf[0] = r[(2 * f) * sw];
+    }
+    if (!predYuv) { predYuv = new TComYuv; predYuv->create(64, 64); memset(zero_offsets, 0, sizeof(zero_offsets)); }
+    Pel* pred = predYuv->getLumaAddr(0);
+    const UInt stride = predYuv->getStride();
+    for (UInt mode = 0; mode < 35; mode++) {
+      predIntraLumaAng(&pattern, mode, pred, stride, n, n, j->above_avail != 0, j->left_avail != 0);
+      out[mode] = rd.calcHAD(g_bitDepthY, (Pel*)org + j->org_off, j->org_stride, pred, stride, n, n);
+    }
+  }
+
   uint32_t dist(const HopDistJob* j, const int16_t* org, const int16_t* cur)
   {
     DistParam dp;
@@ -268,6 +290,9 @@ void ref_frac_search_batch(int n, const HopFracJob* jobs, const int16_t* org, co
 
 void ref_predict_batch(int n, const HopPredJob* jobs, const int16_t* org, const int16_t* refbuf, int16_t* dst, HopPredResult* out)
 { for (int i = 0; i < n; i++) ref()->predict(&jobs[i], org, refbuf, dst, &out[i]); }
+
+void ref_intra_prescreen_batch(int n, const HopIntraJob* jobs, const int16_t* org, const int32_t* refs, uint32_t* out)
+{ for (int i = 0; i < n; i++) ref()->intraPrescreen(&jobs[i], org, refs, out + (size_t)i * HOP_INTRA_MODES); }
 
 void ref_frac_plane(int ver, int hor, int16_t* dst, int cols, int rows) { ref()->fracPlane(ver, hor, dst, cols, rows); }
 

@@ -141,6 +141,19 @@ def predict(jobs, org, ref, dst_samples, which="orc"):
     return out, dst
 
 
+def intra_prescreen(jobs, org, refs, which="orc"):
+    """K7: 35 x (predIntraLumaAng + calcHAD) per PU: C restatement ("orc") or the compiled reference ("ref")."""
+    chk = oracle() if which == "orc" else ref_lib()
+    hop = oracle().hop
+    jobs = np.ascontiguousarray(jobs, dtype=hop.INTRA_JOB_DT)
+    refs = np.ascontiguousarray(refs, dtype=np.int32)
+    out = np.zeros((len(jobs), hop.HOP_INTRA_MODES), dtype=np.uint32)
+    fn = getattr(chk.lib, ("orc_" if which == "orc" else "ref_") + "intra_prescreen_batch")
+    fn.argtypes = [C.c_int, _P, _P, _P, _P]; fn.restype = None
+    fn(len(jobs), _np(jobs), _np(org), _np(refs), _np(out))
+    return out
+
+
 def ref_lib():
     return ref()
 
