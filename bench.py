@@ -379,7 +379,8 @@ def measure_k1(hop, ctx, torch, dev, tstream, pus, peaks):
         for it in range(3):
             if it == 1:
                 e0.record(tstream)
-            ctx.pattern_search_dev(b.n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_out.data_ptr(), ctx.stream)
+            ctx.pattern_search_dev(b.n, d_jobs.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_out.data_ptr(), ctx.stream,
+                                   cols=c, rows=r, nx_max=2 * b.sr + 1, ny_max=b.sr)
         e1.record(tstream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2

@@ -203,7 +203,7 @@ ABI = [
     ("hop_predict_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_intra_prescreen_batch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     ("hop_motion_search_prefetch", C.c_int, [_P, C.c_int, _P, _P, C.c_size_t]),
-    ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    ("hop_pattern_search_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     ("hop_pattern_search_gt_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, C.c_int, C.c_int, _P]),
     ("hop_dist_batch_dev", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     ("hop_gt_sweep_keys_dev", C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
@@ -372,8 +372,9 @@ class HopContext:
         return out
 
     # ---- device entry points (addresses of HBM-resident buffers, e.g. torch tensors' data_ptr()) ----
-    def pattern_search_dev(self, n, d_jobs, d_org, d_ref, d_out, stream=None):
-        self._check(self.lib.hop_pattern_search_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out, stream))
+    def pattern_search_dev(self, n, d_jobs, d_org, d_ref, d_out, stream=None, cols=0, rows=0, nx_max=0, ny_max=0):
+        """cols / rows / nx_max / ny_max: the batch's single PU shape and window bound (zeros = mixed batch)."""
+        self._check(self.lib.hop_pattern_search_batch_dev(self.h, n, d_jobs, d_org, d_ref, d_out, cols, rows, nx_max, ny_max, stream))
 
     def pattern_search_gt_dev(self, n, d_jobs, d_org, d_ref, ref_samples, d_out, max_cols, max_rows, stream=None):
         """ref_samples: int16 samples addressable behind d_ref (bounds the window reads)."""

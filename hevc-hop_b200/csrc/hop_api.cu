@@ -396,9 +396,28 @@ int k1_slices(const HopCtx* ctx, int n)
   int slices = (2 * ctx->sm_count + n - 1) / n;
   return slices > K1_MAX_SLICES ? K1_MAX_SLICES : (slices < 1 ? 1 : slices);
 }
+// A batch (n > 1) whose jobs all have one width and 8-bit content runs the per-width kernel k1_batch<W>:
+// returns W (= cols / 4) and the shared memory it needs, or 0 (the all-widths kernel) for mixed batches.
+int batch_width_hint(const HopCtx* ctx, int n, const HopSearchJob* first, size_t job_stride, size_t* smem_out)
+{
+  if (n <= 1) return 0;
+  const int cols = first->cols;
+  if (cols % 4 != 0 || cols < 4 || cols > HOP_MAX_PU) return 0;
+  const int slices = (2 * ctx->sm_count + n - 1) / n > K1_MAX_SLICES ? K1_MAX_SLICES : ((2 * ctx->sm_count + n - 1) / n < 1 ? 1 : (2 * ctx->sm_count + n - 1) / n);
+  size_t smem = 0;
+  for (int i = 0; i < n; i++) {
+    const HopSearchJob& j = *reinterpret_cast<const HopSearchJob*>(reinterpret_cast<const char*>(first) + (size_t)i * job_stride);
+    if (j.cols != cols || j.bit_depth != 8) return 0;
+    const size_t b = search_batch_smem_bytes(j, slices);
+    if (b > smem) smem = b;
+  }
+  *smem_out = smem > (size_t)(160 * 1024) ? (size_t)(160 * 1024) : smem;
+  return cols / 4;
+}
+
 int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                HopSearchResult* d_out, int smem_bytes, cudaStream_t s, unsigned* done_flag = nullptr, unsigned seq = 0,
-               int job_stride = 0, const InlinePu* inl = nullptr, const PuSlot* slot = nullptr)
+               int job_stride = 0, const InlinePu* inl = nullptr, const PuSlot* slot = nullptr, int words_hint = 0)
 {
   if (slot) {        // single-PU launch of a slot: its own merge words, so that slots may run concurrently
     int l = 0;
@@ -417,20 +436,31 @@ int search_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_
   if (ctx->done.cap != dcap) CU(cudaMemsetAsync(ctx->done.p, 0, ctx->done.cap, s));
   int l = 0;
   CU(search_launch(n, d_jobs, d_org, d_ref, d_out, (unsigned long long*)ctx->keys.p, (unsigned int*)ctx->done.p,
-                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq, job_stride, inl));
+                   k1_slices(ctx, n), smem_bytes, s, &l, done_flag, seq, job_stride, inl, words_hint));
   ctx->launches += l;
   return HOP_OK;
 }
 }  // namespace
 
 int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs, const int16_t* d_org,
-                                 const int16_t* d_ref, HopSearchResult* d_out, void* stream)
+                                 const int16_t* d_ref, HopSearchResult* d_out, int cols, int rows, int nx_max, int ny_max,
+                                 void* stream)
 {
   int st = bind(ctx);
   if (st) return st;
   if (n < 0 || (n > 0 && (!d_jobs || !d_org || !d_ref || !d_out))) return fail(HOP_ERR_ARG, "NULL device buffer");
   if (n == 0) return HOP_OK;
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  if (n > 1 && cols >= 4 && cols <= HOP_MAX_PU && cols % 4 == 0 && rows >= 4 && rows <= HOP_MAX_PU && nx_max > 0 && ny_max > 0) {
+    // the caller vouches for one PU shape and a window bound: per-width kernel with exactly the shared memory it needs
+    HopSearchJob shape;
+    memset(&shape, 0, sizeof(shape));
+    shape.cols = cols; shape.rows = rows; shape.is_ss = 1; shape.fast_enc = 1; shape.bit_depth = 8;
+    shape.rng_right = nx_max - 1; shape.rng_bottom = ny_max - 1;
+    size_t smem = search_batch_smem_bytes(shape, k1_slices(ctx, n));
+    if (smem > (size_t)(160 * 1024)) smem = 160 * 1024;
+    return search_dev(ctx, n, d_jobs, d_org, d_ref, d_out, (int)smem, s, nullptr, 0, 0, nullptr, nullptr, cols / 4);
+  }
   return search_dev(ctx, n, d_jobs, d_org, d_ref, d_out, K1_DEFAULT_SMEM, s);
 }
 
@@ -720,12 +750,17 @@ int hop_pattern_search_batch(HopCtx* ctx, int n, const HopSearchJob* jobs, const
   if (st) return st;
   size_t smem = 0;
   const int slices = k1_slices(ctx, n);
-  for (int i = 0; i < n; i++) {
-    const size_t b = search_smem_bytes(jobs[i], slices);
-    if (b > smem) smem = b;
-  }
+  size_t smem_w = 0;
+  const int words = batch_width_hint(ctx, n, jobs, sizeof(HopSearchJob), &smem_w);
+  if (words) smem = smem_w;
+  else
+    for (int i = 0; i < n; i++) {
+      const size_t b = search_smem_bytes(jobs[i], slices);
+      if (b > smem) smem = b;
+    }
   st = search_dev(ctx, n, (const HopSearchJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref,
-                  (HopSearchResult*)ctx->out.p, (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream);
+                  (HopSearchResult*)ctx->out.p, (int)(smem > (size_t)(160 * 1024) ? 160 * 1024 : smem), ctx->stream,
+                  nullptr, 0, 0, nullptr, nullptr, words);
   if (st) return st;
   CU(cudaMemcpyAsync(out, ctx->out.p, sizeof(HopSearchResult) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1008,13 +1043,16 @@ int hop_motion_search_batch(HopCtx* ctx, int n, const HopMotionJob* jobs, const 
     if (b > smem) smem = b;
   }
   if (smem > (size_t)(160 * 1024)) smem = 160 * 1024;
+  size_t smem_w = 0;
+  const int words = batch_width_hint(ctx, n, &jobs[0].search, sizeof(HopMotionJob), &smem_w);
+  if (words) smem = smem_w;
   if ((st = ensure(ctx, ctx->k1res, sizeof(HopSearchResult) * (size_t)n))) return st;
   HopSearchResult* d_k1 = (HopSearchResult*)ctx->k1res.p;
   const int16_t* d_ref = nullptr;
   st = stage_inputs(ctx, n, jobs, sizeof(HopMotionJob), org, org_samples, ref, ref_samples, sizeof(HopMotionResult) * (size_t)n, &d_ref);
   if (st) return st;
   st = search_dev(ctx, n, (const HopSearchJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, d_k1, (int)smem, ctx->stream,
-                  nullptr, 0, (int)sizeof(HopMotionJob));
+                  nullptr, 0, (int)sizeof(HopMotionJob), nullptr, nullptr, words);
   if (st) return st;
   int l = 0;
   CU(motion_tail_launch(n, (const HopMotionJob*)ctx->jobs.p, (const int16_t*)ctx->org.p, d_ref, d_k1,

@@ -90,7 +90,10 @@ cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_or
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
                           int smem_bytes, cudaStream_t stream, int* launches,
                           unsigned* done_flag = nullptr, unsigned seq = 0, int job_stride = 0,
-                          const InlinePu* inl = nullptr);
+                          const InlinePu* inl = nullptr, int words_hint = 0);
+// words_hint = cols / 4 when every job of a batch (n > 1) has that width and 8-bit content: the per-width throughput
+// kernel k1_batch<W> runs, with the shared memory search_batch_smem_bytes() says; 0 = the all-widths kernel
+size_t      search_batch_smem_bytes(const HopSearchJob& job, int slices);
 // K5 + fused motion search
 cudaError_t frac_launch(int n, const HopFracJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                         HopFracResult* d_out, int max_cols, int max_rows, cudaStream_t stream, int* launches);

@@ -372,11 +372,327 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
   }
 }
 
+// =====================================================================================================================
+// Batched form (n > 1 PUs of one width): k1_batch<W>, W = cols / 4 at compile time.
+//
+// Same exact byte path as above, re-balanced for throughput -- the VABSDIFF4 instruction shares its (half-rate) ALU
+// pipe with every compare, shift and logic instruction, so everything that is not a SAD is cut down or moved off it:
+//   * one kernel per width: the register tile is sized for THAT width (4-wide .. 16-wide PUs take 40-64 registers
+//     instead of the 128 of the all-widths kernel), and the launch asks for the shared memory the jobs need, so 4
+//     CTAs (32 warps) are resident per SM for narrow PUs instead of 2 (16 warps);
+//   * staging reads 4 samples per 8-byte load and packs / classifies them with SIMD-in-register operations (the
+//     window is shifted by its misalignment `mis` so that every load is aligned; the 0-3 extra positions on the left
+//     are masked by the per-row bound);
+//   * the SS gates become ONE compare per position: the causal gate (x >= offset_x && y > offset_y) and the staircase
+//     form of isValidPattern both say "x below a bound that depends on the row", precomputed per row;
+//   * the motion cost is (lbx[x] + lby[y]) >> 16 with lambda folded into the two tables (u32 arithmetic distributes);
+//   * the reference-row loop is split into head / steady / tail, so the steady state has no per-row validity tests;
+//   * positions of one row are compared on 32-bit sums (their raster index grows with x), the 64-bit ordered key is
+//     touched once per row of four positions.
+struct K1bGeom {
+  int nx, ny, y_lo, y_hi, step, rused, st_rows, st_cols, mis, ngx, sw;
+};
+
+__host__ __device__ inline K1bGeom k1b_geom(const HopSearchJob& job, int slice, int slices, int mis)
+{
+  K1bGeom g;
+  g.nx = job.rng_right - job.rng_left + 1;
+  g.ny = job.rng_bottom - job.rng_top + 1;
+  const int rows_per = (g.ny + slices - 1) / slices;
+  g.y_lo = slice * rows_per;
+  g.y_hi = g.y_lo + rows_per < g.ny ? g.y_lo + rows_per : g.ny;
+  g.step = 1 << k1_sub_shift(job);
+  g.rused = job.rows / g.step;
+  const int ny_s = g.y_hi - g.y_lo;
+  g.st_rows = ny_s + (job.is_ss ? job.rows + 4 : (g.rused - 1) * g.step);
+  g.st_cols = g.nx + (job.is_ss ? job.cols + 4 : job.cols - 1);
+  g.mis = mis;
+  g.ngx = (g.nx + mis + 3) / 4;
+  g.sw = ((4 * g.ngx + job.cols + 8) + 15) & ~15;
+  return g;
+}
+
+__host__ __device__ inline size_t k1b_smem_bytes(const HopSearchJob& job, const K1bGeom& g)
+{
+  // [window bytes][org words][first_invalid, invalid count per staged row][lbx per shifted x][lby, bound per position row]
+  size_t b = (size_t)g.st_rows * g.sw + 16;
+  b += ((size_t)g.rused * job.cols + 15) & ~(size_t)15;
+  b += sizeof(int) * 2 * (size_t)g.st_rows;
+  b += sizeof(int) * ((size_t)4 * g.ngx + 2 * (size_t)(g.y_hi - g.y_lo));
+  return b + 64;
+}
+
+template <int W>
+__device__ __forceinline__ void k1b_load_row(const unsigned char* col0, int sw, int srow, unsigned (&sh)[4][W])
+{
+  const unsigned* rw = reinterpret_cast<const unsigned*>(col0 + (size_t)srow * sw);
+  unsigned w0 = rw[0];
+#pragma unroll
+  for (int k = 0; k < W; k++) {
+    const unsigned w1 = rw[k + 1];
+    sh[0][k] = w0;
+    sh[1][k] = __funnelshift_r(w0, w1, 8);
+    sh[2][k] = __funnelshift_r(w0, w1, 16);
+    sh[3][k] = __funnelshift_r(w0, w1, 24);
+    w0 = w1;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void k1b_accum(const unsigned* __restrict__ ow, const unsigned (&sh)[4][W], unsigned (&acc)[4])
+{
+#pragma unroll
+  for (int k = 0; k < W; k++) {
+    const unsigned o = ow[k];
+#pragma unroll
+    for (int a = 0; a < 4; a++) acc[a] = vsad4_acc(o, sh[a][k], acc[a]);
+  }
+}
+
+template <int W>
+__device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, const K1bGeom& g,
+                                                       const unsigned char* __restrict__ s_win, const unsigned* __restrict__ s_org,
+                                                       const unsigned* __restrict__ s_lbx, const unsigned* __restrict__ s_lby,
+                                                       const int* __restrict__ s_bound)
+{
+  constexpr int Q = 4;
+  const int S = g.step, R = g.rused, ny_s = g.y_hi - g.y_lo, ngx = g.ngx;
+  const int sub_shift = k1_sub_shift(job);
+  const int t0 = (ny_s + S - 1) / S, g0 = (t0 + Q - 1) / Q;              // position rows of parity class 0 / their groups
+  const int t1 = S > 1 ? (ny_s - 1 + S - 1) / S : 0, g1 = (t1 + Q - 1) / Q;
+  const int ntask = ngx * (g0 + g1);
+  const int last_row = g.st_rows - 1;
+  unsigned long long best = ~0ull;
+  for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+    const int xg = task % ngx;
+    int ty = task / ngx, pi = 0;
+    if (ty >= g0) { ty -= g0; pi = 1; }
+    const int q0 = pi + S * (ty * Q);             // first position row of the task (relative to the slice)
+    unsigned acc[Q][4];
+#pragma unroll
+    for (int j = 0; j < Q; j++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) acc[j][a] = 0;
+    const unsigned char* col0 = s_win + 4 * xg;
+    unsigned sh[4][W];
+    // reference row m serves block row m - j of position row j; rows past the staged window only feed padded positions
+    // head: m = 0 .. Q-2, position rows j <= m
+#pragma unroll
+    for (int m = 0; m < Q - 1; m++) {
+      k1b_load_row<W>(col0, g.sw, min(q0 + S * m, last_row), sh);
+#pragma unroll
+      for (int j = 0; j <= m; j++) k1b_accum<W>(s_org + (m - j) * W, sh, acc[j]);
+    }
+    // steady state: every position row takes part
+    for (int m = Q - 1; m < R; m++) {
+      k1b_load_row<W>(col0, g.sw, min(q0 + S * m, last_row), sh);
+#pragma unroll
+      for (int j = 0; j < Q; j++) k1b_accum<W>(s_org + (m - j) * W, sh, acc[j]);
+    }
+    // tail: m = R .. R+Q-2, position rows j > m - R
+#pragma unroll
+    for (int t = 0; t < Q - 1; t++) {
+      k1b_load_row<W>(col0, g.sw, min(q0 + S * (R + t), last_row), sh);
+#pragma unroll
+      for (int j = t + 1; j < Q; j++) k1b_accum<W>(s_org + (R + t - j) * W, sh, acc[j]);
+    }
+    // epilogue: one bound compare per position, 32-bit comparison within a row, ordered 64-bit key per row
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+      const int q = q0 + S * j;
+      if (q >= ny_s) continue;
+      const int bound = s_bound[q];               // shifted coordinates: valid iff mis <= pxs < bound
+      const unsigned lby = s_lby[q];
+      unsigned bs = 0xffffffffu;
+      int bi = 0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int pxs = 4 * xg + a;
+        const unsigned sum = (acc[j][a] << sub_shift) + ((s_lbx[pxs] + lby) >> 16);
+        if (pxs >= g.mis && pxs < bound && sum < bs) { bs = sum; bi = pxs; }
+      }
+      if (bs != 0xffffffffu) {
+        const unsigned long long key = ((unsigned long long)bs << 32) | (unsigned)((g.y_lo + q) * g.nx + bi - g.mis);
+        best = key < best ? key : best;
+      }
+    }
+  }
+  return best;
+}
+
+template <int W> struct K1bCfg { static constexpr int MINB = W <= 4 ? 4 : (W <= 8 ? 3 : 2); };
+
+template <int W>
+__global__ void __launch_bounds__(K1_THREADS, K1bCfg<W>::MINB)
+k1_batch(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __restrict__ org_buf,
+         const int16_t* __restrict__ ref_buf, unsigned long long* __restrict__ keys,
+         unsigned int* __restrict__ done, HopSearchResult* __restrict__ out, int smem_limit, int job_stride)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ unsigned long long s_red[32];
+  __shared__ int s_unclean;
+  const int job_id = blockIdx.x;
+  const HopSearchJob job = *reinterpret_cast<const HopSearchJob*>(reinterpret_cast<const char*>(jobs) + (size_t)job_id * job_stride);
+  const int cols = job.cols, rows = job.rows;
+  const int16_t* org = org_buf + job.org_off;
+  const int16_t* ref_y = ref_buf + job.ref_off;
+  // window origin of this slice and its misalignment to 8 bytes (4 samples); rows keep it when the stride is a multiple of 4
+  const K1Geom g_old = k1_geom(job, blockIdx.y, gridDim.y);
+  const bool empty = g_old.nx <= 0 || g_old.ny <= 0 || g_old.y_lo >= g_old.y_hi;
+  const int16_t* win0 = ref_y + (long long)(job.rng_top + g_old.y_lo) * job.ref_stride + job.rng_left;
+  const bool vec = (job.ref_stride & 3) == 0;
+  const int mis = vec ? (int)((reinterpret_cast<unsigned long long>(win0) >> 1) & 3ull) : 0;
+  const K1bGeom g = k1b_geom(job, blockIdx.y, gridDim.y, mis);
+  bool bytes_ok = !empty && job.bit_depth == 8 && cols == 4 * W && rows <= HOP_MAX_PU && k1b_smem_bytes(job, g) <= (size_t)smem_limit;
+  unsigned long long best = ~0ull;
+  if (bytes_ok) {
+    unsigned char* s_win = smem;
+    unsigned* s_org = reinterpret_cast<unsigned*>(smem + (((size_t)g.st_rows * g.sw + 15) & ~(size_t)15));
+    int* s_first_invalid = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_org) + (((size_t)g.rused * cols + 15) & ~(size_t)15));
+    int* s_cnt_invalid = s_first_invalid + g.st_rows;
+    unsigned* s_lbx = reinterpret_cast<unsigned*>(s_cnt_invalid + g.st_rows);
+    unsigned* s_lby = s_lbx + 4 * g.ngx;
+    int* s_bound = reinterpret_cast<int*>(s_lby + (g.y_hi - g.y_lo));
+    const int ny_s = g.y_hi - g.y_lo;
+    if (threadIdx.x == 0) s_unclean = 0;
+    for (int i = threadIdx.x; i < g.st_rows; i += blockDim.x) { s_first_invalid[i] = 0x7fffffff; s_cnt_invalid[i] = 0; }
+    // lambda * bits tables (TComRdCost.h:196-199; (l * (bx + by)) >> 16 == (l*bx + l*by) >> 16 in UInt arithmetic)
+    for (int i = threadIdx.x; i < 4 * g.ngx; i += blockDim.x)
+      s_lbx[i] = job.cost.lambda_cost * component_bits(((job.rng_left + i - mis) << job.cost.cost_scale) - job.cost.pred.hor);
+    for (int i = threadIdx.x; i < ny_s; i += blockDim.x)
+      s_lby[i] = job.cost.lambda_cost * component_bits(((job.rng_top + g.y_lo + i) << job.cost.cost_scale) - job.cost.pred.ver);
+    __syncthreads();
+    int bad = 0;
+    for (int i = threadIdx.x; i < g.rused * W; i += blockDim.x) {       // original block: the sub-sampled rows, packed to bytes
+      const int r = i / W, k = i - r * W;
+      const int16_t* o = org + (r * g.step) * job.org_stride + 4 * k;
+      unsigned w = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) { const int v = o[b]; bad |= (v < 0) | (v > 255); w |= (unsigned)(v & 255) << (8 * b); }
+      s_org[i] = w;
+    }
+    // window: staged row r holds, at byte cs, the sample of real column cs - mis; aligned groups of 4 samples are read
+    // with one 8-byte load and packed / classified with SIMD-in-register operations
+    const int wpr = g.sw / 4;
+    for (int i = threadIdx.x; i < g.st_rows * wpr; i += blockDim.x) {
+      const int r = i / wpr, k = i - r * wpr;
+      const int c0 = 4 * k - mis;                                       // real column of the group's first sample
+      const int16_t* p = win0 + (long long)r * job.ref_stride + c0;
+      unsigned w = 0;
+      int n_inv = 0, first = 0x7fffffff;
+      if (vec && c0 >= 0 && c0 + 3 < g.st_cols) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+        const unsigned e0 = __vcmpeq2(u.x, 0xffffffffu), e1 = __vcmpeq2(u.y, 0xffffffffu);   // 0xffff per NOT_VALID sample
+        bad |= (((u.x & ~e0) | (u.y & ~e1)) & 0xff00ff00u) != 0;
+        w = __byte_perm(u.x & ~e0, u.y & ~e1, 0x6420);
+        if (e0 | e1) {
+          n_inv = __popc(e0 & 0x00010001u) + __popc(e1 & 0x00010001u);
+          first = c0 + ((e0 & 0xffffu) ? 0 : (e0 ? 1 : ((e1 & 0xffffu) ? 2 : 3)));
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int c = c0 + b;
+          int v = 0;
+          if (c >= 0 && c < g.st_cols) {                                 // never read what the reference would not
+            v = __ldg(p + b);
+            if (v == HOP_NOT_VALID) { n_inv++; first = first < c ? first : c; v = 0; }
+            else bad |= (v < 0) | (v > 255);
+          }
+          w |= (unsigned)(v & 255) << (8 * b);
+        }
+      }
+      reinterpret_cast<unsigned*>(s_win + (size_t)r * g.sw)[k] = w;
+      if (n_inv) { atomicMin(&s_first_invalid[r], first); atomicAdd(&s_cnt_invalid[r], n_inv); }
+    }
+    if (bad) s_unclean = 1;
+    __syncthreads();
+    // staircase check (see the header of this file) and the per-row bound of the valid positions
+    for (int r = threadIdx.x; r < g.st_rows; r += blockDim.x) {
+      const int first = s_first_invalid[r], cnt = s_cnt_invalid[r];
+      bool ok = cnt == 0 || cnt == g.st_cols - first;
+      if (r > 0 && first > s_first_invalid[r - 1]) ok = false;
+      if (!job.is_ss && cnt != 0) ok = false;
+      if (!ok) s_unclean = 1;
+    }
+    for (int q = threadIdx.x; q < ny_s; q += blockDim.x) {
+      int b = g.nx;
+      if (job.is_ss) {
+        const int y = job.rng_top + g.y_lo + q;
+        const int fi = s_first_invalid[q + rows + 4];                    // row of the isValidPattern probes (:6330)
+        if (fi != 0x7fffffff) b = min(b, fi - cols - 4);                 // valid iff px + cols + 4 < first NOT_VALID of that row
+        if (y > job.offset_y) b = min(b, job.offset_x - job.rng_left);   // causal gate (:6328): x < offset_x
+      }
+      s_bound[q] = max(b, 0) + mis;
+    }
+    __syncthreads();
+    bytes_ok = s_unclean == 0;
+    if (bytes_ok) best = k1b_scan<W>(job, g, s_win, s_org, s_lbx, s_lby, s_bound);
+  }
+  if (!bytes_ok) best = empty ? ~0ull : k1_generic(job, g_old, org, ref_y);
+  best = block_min_u64(best, s_red);
+  if (threadIdx.x == 0) {
+    if (best != ~0ull) atomicMin(&keys[job_id], best);
+    __threadfence();
+    if (atomicAdd(&done[job_id], 1u) == gridDim.y - 1) {          // last slice of this PU
+      __threadfence();
+      const unsigned long long key = atomicExch(&keys[job_id], ~0ull);
+      done[job_id] = 0;
+      k1_write_result(job, key, &out[job_id]);
+    }
+  }
+}
+
+template <int W>
+static cudaError_t k1_batch_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref, HopSearchResult* d_out,
+                                   unsigned long long* d_keys, unsigned int* d_done, int slices, int smem_bytes, cudaStream_t stream, int job_stride)
+{
+  static SmemOptIn opt_in;
+  cudaError_t e = opt_in.ensure(k1_batch<W>, 160 * 1024);
+  if (e != cudaSuccess) return e;
+  k1_batch<W><<<dim3(n, slices), K1_THREADS, smem_bytes, stream>>>(n, d_jobs, d_org, d_ref, d_keys, d_done, d_out, smem_bytes, job_stride);
+  return cudaGetLastError();
+}
+
+// Shared memory k1_batch wants for `job` cut into `slices` (worst misalignment), host side helper.
+size_t search_batch_smem_bytes(const HopSearchJob& job, int slices)
+{
+  size_t worst = 0;
+  for (int s = 0; s < slices; s++) {
+    const K1bGeom g = k1b_geom(job, s, slices, 3);
+    if (g.y_lo >= g.y_hi) continue;
+    const size_t b = k1b_smem_bytes(job, g);
+    if (b > worst) worst = b;
+  }
+  return worst;
+}
+
 cudaError_t search_launch(int n, const HopSearchJob* d_jobs, const int16_t* d_org, const int16_t* d_ref,
                           HopSearchResult* d_out, unsigned long long* d_keys, unsigned int* d_done, int slices,
                           int smem_bytes, cudaStream_t stream, int* launches, unsigned* done_flag, unsigned seq,
-                          int job_stride, const InlinePu* inl)
+                          int job_stride, const InlinePu* inl, int words_hint)
 {
+  if (words_hint > 0 && !inl && !done_flag && n > 1) {
+    // a batch of PUs of one width (8-bit content): the per-width throughput kernel
+    const int js = job_stride ? job_stride : (int)sizeof(HopSearchJob);
+    if (slices < 1) slices = 1;
+    if (slices > K1_MAX_SLICES) slices = K1_MAX_SLICES;
+    if (smem_bytes > 160 * 1024) smem_bytes = 160 * 1024;
+    if (smem_bytes < 1024) smem_bytes = 1024;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (words_hint) {
+      case 1:  e = k1_batch_launch<1>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 2:  e = k1_batch_launch<2>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 3:  e = k1_batch_launch<3>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 4:  e = k1_batch_launch<4>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 6:  e = k1_batch_launch<6>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 8:  e = k1_batch_launch<8>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 12: e = k1_batch_launch<12>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      case 16: e = k1_batch_launch<16>(n, d_jobs, d_org, d_ref, d_out, d_keys, d_done, slices, smem_bytes, stream, js); break;
+      default: break;
+    }
+    if (e != cudaErrorInvalidValue) { if (launches) *launches += 1; return e; }
+  }
   static SmemOptIn opt_in;
   static const InlinePu no_inline = {};
   const int smem_max = 160 * 1024;

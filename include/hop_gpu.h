@@ -322,9 +322,12 @@ int hop_motion_search_prefetch(HopCtx* ctx, int n, const HopMotionJob* jobs,
                                const int16_t* org, size_t org_samples);
 
 /* ---- device entry points (everything already resident in HBM, asynchronous on `stream`) ---- */
+/* cols / rows / nx_max / ny_max: when every job of the batch has this PU shape (8-bit content) and a search window
+ * of at most nx_max x ny_max positions, the per-width throughput kernel runs with exactly the shared memory that
+ * needs; pass zeros for mixed batches.  Batched searches of one context are issued on one stream at a time. */
 int hop_pattern_search_batch_dev(HopCtx* ctx, int n, const HopSearchJob* d_jobs,
                                  const int16_t* d_org, const int16_t* d_ref,
-                                 HopSearchResult* d_out, void* stream);
+                                 HopSearchResult* d_out, int cols, int rows, int nx_max, int ny_max, void* stream);
 /* max_cols/max_rows: upper bound of the PU shapes in d_jobs (sizes the shared-memory window and CTA).
  * ref_samples: addressable int16 samples behind d_ref -- start vectors are raw AMVP vectors whose 2W x 2H window may
  * leave the buffer (the reference then reads whatever lies beyond its plane); the kernels keep every read inside

@@ -261,6 +261,14 @@ def test_device_entry_points_with_torch_buffers(ctx):
     so = d_so.cpu().numpy().view(hop.SEARCH_RES_DT)
     go = d_go.cpu().numpy().view(hop.GT_RES_DT)
     assert so.tobytes() == orc.pattern_search(b.search_jobs, b.org, b.ref).tobytes()
+    # the same batch with the shape / window hint (per-width throughput kernel), and with a hint that is too small
+    # for the windows (the kernel then takes its generic path: slower, same results)
+    for nx_max, ny_max in ((2 * 24 + 1, 24), (8, 8)):
+        d_so.zero_()
+        ctx.pattern_search_dev(b.n, d_sj.data_ptr(), d_org.data_ptr(), d_ref.data_ptr(), d_so.data_ptr(), stream,
+                               cols=16, rows=16, nx_max=nx_max, ny_max=ny_max)
+        torch.cuda.synchronize()
+        assert d_so.cpu().numpy().view(hop.SEARCH_RES_DT).tobytes() == so.tobytes()
     assert go.tobytes() == orc.pattern_search_gt(b.gt_jobs, b.org, b.ref).tobytes()
 
 
