@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--encode-procs", type=int, default=0, help="encoder processes per GPU (sharing it through MPS); 0 = host cores / 8, at least 1")
     ap.add_argument("--encode-images", type=int, default=0, help="images per GPU in the encode leg; 0 = one per encoder process")
     ap.add_argument("--sweep-pus", type=int, default=4096, help="PUs (Main10, 8x8/16x16/32x32/16x8 mix) of the sharded exhaustive sweep; 0 = skip")
-    ap.add_argument("--k1-pus", type=int, default=592, help="PUs per shape for the secondary K1 (SS full search) measurement (592 = two waves of the 2 CTAs resident per SM); 0 = skip")
+    ap.add_argument("--k1-pus", type=int, default=2368, help="PUs per shape for the secondary K1 (SS full search) measurement (2368 = 16 per SM: 4 to 8 waves of resident CTAs); 0 = skip")
     return ap.parse_args()
 
 

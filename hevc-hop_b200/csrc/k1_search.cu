@@ -392,6 +392,7 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
 struct K1bGeom {
   int nx, ny, y_lo, y_hi, step, rused, st_rows, st_cols, mis, ngx, sw;
 };
+constexpr int K1B_PAD_ROWS = 16;
 
 __host__ __device__ inline K1bGeom k1b_geom(const HopSearchJob& job, int slice, int slices, int mis)
 {
@@ -415,7 +416,9 @@ __host__ __device__ inline K1bGeom k1b_geom(const HopSearchJob& job, int slice, 
 __host__ __device__ inline size_t k1b_smem_bytes(const HopSearchJob& job, const K1bGeom& g)
 {
   // [window bytes][org words][first_invalid, invalid count per staged row][lbx per shifted x][lby, bound per position row]
-  size_t b = (size_t)g.st_rows * g.sw + 16;
+  // K1B_PAD_ROWS rows of slack behind the window: the padded positions of a parity class's last group read up to
+  // 2 * step * 4 rows past it (their sums are never used), and must stay inside the allocation
+  size_t b = (size_t)(g.st_rows + K1B_PAD_ROWS) * g.sw + 16;
   b += ((size_t)g.rused * job.cols + 15) & ~(size_t)15;
   b += sizeof(int) * 2 * (size_t)g.st_rows;
   b += sizeof(int) * ((size_t)4 * g.ngx + 2 * (size_t)(g.y_hi - g.y_lo));
@@ -461,12 +464,12 @@ __device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, 
   const int t0 = (ny_s + S - 1) / S, g0 = (t0 + Q - 1) / Q;              // position rows of parity class 0 / their groups
   const int t1 = S > 1 ? (ny_s - 1 + S - 1) / S : 0, g1 = (t1 + Q - 1) / Q;
   const int ntask = ngx * (g0 + g1);
-  const int last_row = g.st_rows - 1;
   unsigned long long best = ~0ull;
+  // (xg, ty) of the flat task index, advanced without a division per task
+  int xg = (int)threadIdx.x % ngx, tyf = (int)threadIdx.x / ngx;
+  const int dx = (int)blockDim.x % ngx, dy = (int)blockDim.x / ngx;
   for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-    const int xg = task % ngx;
-    int ty = task / ngx, pi = 0;
-    if (ty >= g0) { ty -= g0; pi = 1; }
+    const int pi = tyf >= g0 ? 1 : 0, ty = tyf - (pi ? g0 : 0);
     const int q0 = pi + S * (ty * Q);             // first position row of the task (relative to the slice)
     unsigned acc[Q][4];
 #pragma unroll
@@ -479,43 +482,63 @@ __device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, 
     // head: m = 0 .. Q-2, position rows j <= m
 #pragma unroll
     for (int m = 0; m < Q - 1; m++) {
-      k1b_load_row<W>(col0, g.sw, min(q0 + S * m, last_row), sh);
+      k1b_load_row<W>(col0, g.sw, q0 + S * m, sh);
 #pragma unroll
       for (int j = 0; j <= m; j++) k1b_accum<W>(s_org + (m - j) * W, sh, acc[j]);
     }
     // steady state: every position row takes part
     for (int m = Q - 1; m < R; m++) {
-      k1b_load_row<W>(col0, g.sw, min(q0 + S * m, last_row), sh);
+      k1b_load_row<W>(col0, g.sw, q0 + S * m, sh);
 #pragma unroll
       for (int j = 0; j < Q; j++) k1b_accum<W>(s_org + (m - j) * W, sh, acc[j]);
     }
     // tail: m = R .. R+Q-2, position rows j > m - R
 #pragma unroll
     for (int t = 0; t < Q - 1; t++) {
-      k1b_load_row<W>(col0, g.sw, min(q0 + S * (R + t), last_row), sh);
+      k1b_load_row<W>(col0, g.sw, q0 + S * (R + t), sh);
 #pragma unroll
       for (int j = t + 1; j < Q; j++) k1b_accum<W>(s_org + (R + t - j) * W, sh, acc[j]);
     }
-    // epilogue: one bound compare per position, 32-bit comparison within a row, ordered 64-bit key per row
+    // epilogue.  (acc << sub) + (t >> 16) == hi32(t * 65536) + acc * (1 << sub) runs on the multiply-add pipe.
+    // Inside a task the raster index grows with the row and with x, so "first strict minimum" is the minimum of
+    // (sum, position-in-task): the pair is packed into one word, sum * 16 + (4 j + a) < 2^25 (8-bit SADs of at most
+    // 64 x 32 x 2 samples), invalid positions become all-ones.
+    // the two multipliers go through an opaque move: known powers of two would be strength-reduced to shifts / LEAs,
+    // which execute on the ALU pipe the SADs need
+    unsigned mul, sixteen, two16;
+    asm("mov.u32 %0, %1;" : "=r"(mul) : "r"(1u << sub_shift));
+    asm("mov.u32 %0, %1;" : "=r"(sixteen) : "r"(16u));
+    asm("mov.u32 %0, %1;" : "=r"(two16) : "r"(65536u));
+    const unsigned px0 = (unsigned)(4 * xg - g.mis);          // real x of alignment 0; negative (= huge) left of the window
+    const uint4 lbx4 = *reinterpret_cast<const uint4*>(s_lbx + 4 * xg);
+    const unsigned lbx[4] = {lbx4.x, lbx4.y, lbx4.z, lbx4.w};
+    unsigned bs = 0xffffffffu;
+    int bidx = 0;
+    {
+      unsigned k32 = 0xffffffffu;
 #pragma unroll
-    for (int j = 0; j < Q; j++) {
-      const int q = q0 + S * j;
-      if (q >= ny_s) continue;
-      const int bound = s_bound[q];               // shifted coordinates: valid iff mis <= pxs < bound
-      const unsigned lby = s_lby[q];
-      unsigned bs = 0xffffffffu;
-      int bi = 0;
+      for (int j = 0; j < Q; j++) {
+        const int q = q0 + S * j;
+        const unsigned bound = q < ny_s ? (unsigned)s_bound[q] : 0u;     // padded rows: nothing is valid
+        const unsigned lby = s_lby[q < ny_s ? q : 0];
 #pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int pxs = 4 * xg + a;
-        const unsigned sum = (acc[j][a] << sub_shift) + ((s_lbx[pxs] + lby) >> 16);
-        if (pxs >= g.mis && pxs < bound && sum < bs) { bs = sum; bi = pxs; }
+        for (int a = 0; a < 4; a++) {
+          const unsigned sum = __umulhi(lbx[a] + lby, two16) + acc[j][a] * mul;
+          const unsigned cand = sum * sixteen + (unsigned)(4 * j + a);
+          k32 = min(k32, px0 + a < bound ? cand : 0xffffffffu);          // one unsigned compare decides both gates
+        }
       }
-      if (bs != 0xffffffffu) {
-        const unsigned long long key = ((unsigned long long)bs << 32) | (unsigned)((g.y_lo + q) * g.nx + bi - g.mis);
-        best = key < best ? key : best;
+      if (k32 != 0xffffffffu) {
+        bs = k32 >> 4;
+        bidx = (g.y_lo + q0 + S * (int)((k32 >> 2) & 3u)) * g.nx + (int)px0 + (int)(k32 & 3u);
       }
     }
+    if (bs != 0xffffffffu) {
+      const unsigned long long key = ((unsigned long long)bs << 32) | (unsigned)bidx;
+      best = key < best ? key : best;
+    }
+    xg += dx; tyf += dy;
+    if (xg >= ngx) { xg -= ngx; tyf++; }
   }
   return best;
 }
@@ -547,12 +570,12 @@ k1_batch(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __res
   unsigned long long best = ~0ull;
   if (bytes_ok) {
     unsigned char* s_win = smem;
-    unsigned* s_org = reinterpret_cast<unsigned*>(smem + (((size_t)g.st_rows * g.sw + 15) & ~(size_t)15));
-    int* s_first_invalid = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_org) + (((size_t)g.rused * cols + 15) & ~(size_t)15));
-    int* s_cnt_invalid = s_first_invalid + g.st_rows;
-    unsigned* s_lbx = reinterpret_cast<unsigned*>(s_cnt_invalid + g.st_rows);
+    unsigned* s_org = reinterpret_cast<unsigned*>(smem + (((size_t)(g.st_rows + K1B_PAD_ROWS) * g.sw + 15) & ~(size_t)15));
+    unsigned* s_lbx = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(s_org) + (((size_t)g.rused * cols + 15) & ~(size_t)15));   // 16-byte aligned
     unsigned* s_lby = s_lbx + 4 * g.ngx;
     int* s_bound = reinterpret_cast<int*>(s_lby + (g.y_hi - g.y_lo));
+    int* s_first_invalid = s_bound + (g.y_hi - g.y_lo);
+    int* s_cnt_invalid = s_first_invalid + g.st_rows;
     const int ny_s = g.y_hi - g.y_lo;
     if (threadIdx.x == 0) s_unclean = 0;
     for (int i = threadIdx.x; i < g.st_rows; i += blockDim.x) { s_first_invalid[i] = 0x7fffffff; s_cnt_invalid[i] = 0; }
@@ -573,37 +596,61 @@ k1_batch(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __res
     }
     // window: staged row r holds, at byte cs, the sample of real column cs - mis; aligned groups of 4 samples are read
     // with one 8-byte load and packed / classified with SIMD-in-register operations
+    // A warp takes a row at a time, a lane up to three groups of it (all loads of a row are in flight together).  Groups
+    // that lie completely inside the window are read with one aligned 8-byte load; fast path: no sample of the group
+    // has a high byte set, i.e. four plain 8-bit samples -- one OR-AND, one compare, one byte permute.  The (at most
+    // two) groups per row that straddle a window edge are filled in afterwards, one sample per thread, so that nothing
+    // outside the window is ever read.
     const int wpr = g.sw / 4;
-    for (int i = threadIdx.x; i < g.st_rows * wpr; i += blockDim.x) {
-      const int r = i / wpr, k = i - r * wpr;
-      const int c0 = 4 * k - mis;                                       // real column of the group's first sample
-      const int16_t* p = win0 + (long long)r * job.ref_stride + c0;
-      unsigned w = 0;
-      int n_inv = 0, first = 0x7fffffff;
-      if (vec && c0 >= 0 && c0 + 3 < g.st_cols) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-        const unsigned e0 = __vcmpeq2(u.x, 0xffffffffu), e1 = __vcmpeq2(u.y, 0xffffffffu);   // 0xffff per NOT_VALID sample
-        bad |= (((u.x & ~e0) | (u.y & ~e1)) & 0xff00ff00u) != 0;
-        w = __byte_perm(u.x & ~e0, u.y & ~e1, 0x6420);
-        if (e0 | e1) {
-          n_inv = __popc(e0 & 0x00010001u) + __popc(e1 & 0x00010001u);
-          first = c0 + ((e0 & 0xffffu) ? 0 : (e0 ? 1 : ((e1 & 0xffffu) ? 2 : 3)));
-        }
-      } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int k_first = (mis + 3) / 4, k_end = (g.st_cols + mis) / 4;      // groups [k_first, k_end) are complete
+    for (int r = warp; r < g.st_rows; r += nwarp) {
+      const int16_t* prow = win0 + (long long)r * job.ref_stride - mis;
+      unsigned* srow = reinterpret_cast<unsigned*>(s_win + (size_t)r * g.sw);
+      uint2 u[3];
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const int c = c0 + b;
-          int v = 0;
-          if (c >= 0 && c < g.st_cols) {                                 // never read what the reference would not
-            v = __ldg(p + b);
-            if (v == HOP_NOT_VALID) { n_inv++; first = first < c ? first : c; v = 0; }
-            else bad |= (v < 0) | (v > 255);
-          }
-          w |= (unsigned)(v & 255) << (8 * b);
-        }
+      for (int t = 0; t < 3; t++) {
+        const int k = lane + 32 * t;
+        if (vec && k >= k_first && k < k_end) u[t] = __ldg(reinterpret_cast<const uint2*>(prow + 4 * k));
       }
-      reinterpret_cast<unsigned*>(s_win + (size_t)r * g.sw)[k] = w;
-      if (n_inv) { atomicMin(&s_first_invalid[r], first); atomicAdd(&s_cnt_invalid[r], n_inv); }
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int k = lane + 32 * t;
+        if (k >= wpr) continue;
+        unsigned w = 0;
+        if (vec && k >= k_first && k < k_end) {
+          if (((u[t].x | u[t].y) & 0xff00ff00u) == 0) {
+            w = __byte_perm(u[t].x, u[t].y, 0x6420);
+          } else {
+            const unsigned e0 = __vcmpeq2(u[t].x, 0xffffffffu), e1 = __vcmpeq2(u[t].y, 0xffffffffu);   // 0xffff per NOT_VALID sample
+            bad |= (((u[t].x & ~e0) | (u[t].y & ~e1)) & 0xff00ff00u) != 0;
+            w = __byte_perm(u[t].x & ~e0, u[t].y & ~e1, 0x6420);
+            const int n_inv = __popc(e0 & 0x00010001u) + __popc(e1 & 0x00010001u);
+            if (n_inv) {
+              const int first = 4 * k - mis + ((e0 & 0xffffu) ? 0 : (e0 ? 1 : ((e1 & 0xffffu) ? 2 : 3)));
+              atomicMin(&s_first_invalid[r], first);
+              atomicAdd(&s_cnt_invalid[r], n_inv);
+            }
+          }
+        }
+        srow[k] = w;                                                     // edge and outside groups: zero for now
+      }
+    }
+    __syncthreads();
+    {
+      // samples of the window that no complete group covers: columns [0, 4 k_first - mis) and [4 k_end - mis, st_cols)
+      // (every column when the rows are not 8-byte aligned)
+      const int lo_n = vec ? min(4 * k_first - mis, g.st_cols) : g.st_cols;
+      const int hi_0 = vec ? max(4 * k_end - mis, lo_n) : g.st_cols;
+      const int per_row = lo_n + (g.st_cols - hi_0);
+      for (int i = threadIdx.x; i < g.st_rows * per_row; i += blockDim.x) {
+        const int r = i / per_row, e = i - r * per_row;
+        const int c = e < lo_n ? e : hi_0 + (e - lo_n);
+        int v = __ldg(win0 + (long long)r * job.ref_stride + c);
+        if (v == HOP_NOT_VALID) { atomicMin(&s_first_invalid[r], c); atomicAdd(&s_cnt_invalid[r], 1); v = 0; }
+        else bad |= (v < 0) | (v > 255);
+        s_win[(size_t)r * g.sw + c + mis] = (unsigned char)v;
+      }
     }
     if (bad) s_unclean = 1;
     __syncthreads();
@@ -623,7 +670,7 @@ k1_batch(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __res
         if (fi != 0x7fffffff) b = min(b, fi - cols - 4);                 // valid iff px + cols + 4 < first NOT_VALID of that row
         if (y > job.offset_y) b = min(b, job.offset_x - job.rng_left);   // causal gate (:6328): x < offset_x
       }
-      s_bound[q] = max(b, 0) + mis;
+      s_bound[q] = max(b, 0);                                            // valid iff 0 <= px < bound (one unsigned compare)
     }
     __syncthreads();
     bytes_ok = s_unclean == 0;
