@@ -392,7 +392,7 @@ k1_search(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __re
 struct K1bGeom {
   int nx, ny, y_lo, y_hi, step, rused, st_rows, st_cols, mis, ngx, sw;
 };
-constexpr int K1B_PAD_ROWS = 16;
+constexpr int K1B_PAD_ROWS = 32;
 
 __host__ __device__ inline K1bGeom k1b_geom(const HopSearchJob& job, int slice, int slices, int mis)
 {
@@ -417,7 +417,7 @@ __host__ __device__ inline size_t k1b_smem_bytes(const HopSearchJob& job, const 
 {
   // [window bytes][org words][first_invalid, invalid count per staged row][lbx per shifted x][lby, bound per position row]
   // K1B_PAD_ROWS rows of slack behind the window: the padded positions of a parity class's last group read up to
-  // 2 * step * 4 rows past it (their sums are never used), and must stay inside the allocation
+  // 2 * step * (rows per task) rows past it (their sums are never used), and must stay inside the allocation
   size_t b = (size_t)(g.st_rows + K1B_PAD_ROWS) * g.sw + 16;
   b += ((size_t)g.rused * job.cols + 15) & ~(size_t)15;
   b += sizeof(int) * 2 * (size_t)g.st_rows;
@@ -452,13 +452,13 @@ __device__ __forceinline__ void k1b_accum(const unsigned* __restrict__ ow, const
   }
 }
 
-template <int W>
+template <int W, int Q>
 __device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, const K1bGeom& g,
                                                        const unsigned char* __restrict__ s_win, const unsigned* __restrict__ s_org,
                                                        const unsigned* __restrict__ s_lbx, const unsigned* __restrict__ s_lby,
                                                        const int* __restrict__ s_bound)
 {
-  constexpr int Q = 4;
+  constexpr int IDX_BITS = Q == 8 ? 5 : 4;            // position-in-task index: 4 j + a
   const int S = g.step, R = g.rused, ny_s = g.y_hi - g.y_lo, ngx = g.ngx;
   const int sub_shift = k1_sub_shift(job);
   const int t0 = (ny_s + S - 1) / S, g0 = (t0 + Q - 1) / Q;              // position rows of parity class 0 / their groups
@@ -501,13 +501,13 @@ __device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, 
     }
     // epilogue.  (acc << sub) + (t >> 16) == hi32(t * 65536) + acc * (1 << sub) runs on the multiply-add pipe.
     // Inside a task the raster index grows with the row and with x, so "first strict minimum" is the minimum of
-    // (sum, position-in-task): the pair is packed into one word, sum * 16 + (4 j + a) < 2^25 (8-bit SADs of at most
+    // (sum, position-in-task): the pair is packed into one word, sum * 4Q + (4 j + a) < 2^26 (8-bit SADs of at most
     // 64 x 32 x 2 samples), invalid positions become all-ones.
     // the two multipliers go through an opaque move: known powers of two would be strength-reduced to shifts / LEAs,
     // which execute on the ALU pipe the SADs need
     unsigned mul, sixteen, two16;
     asm("mov.u32 %0, %1;" : "=r"(mul) : "r"(1u << sub_shift));
-    asm("mov.u32 %0, %1;" : "=r"(sixteen) : "r"(16u));
+    asm("mov.u32 %0, %1;" : "=r"(sixteen) : "r"(1u << IDX_BITS));
     asm("mov.u32 %0, %1;" : "=r"(two16) : "r"(65536u));
     const unsigned px0 = (unsigned)(4 * xg - g.mis);          // real x of alignment 0; negative (= huge) left of the window
     const uint4 lbx4 = *reinterpret_cast<const uint4*>(s_lbx + 4 * xg);
@@ -529,8 +529,8 @@ __device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, 
         }
       }
       if (k32 != 0xffffffffu) {
-        bs = k32 >> 4;
-        bidx = (g.y_lo + q0 + S * (int)((k32 >> 2) & 3u)) * g.nx + (int)px0 + (int)(k32 & 3u);
+        bs = k32 >> IDX_BITS;
+        bidx = (g.y_lo + q0 + S * (int)((k32 >> 2) & (unsigned)(Q - 1))) * g.nx + (int)px0 + (int)(k32 & 3u);
       }
     }
     if (bs != 0xffffffffu) {
@@ -674,7 +674,9 @@ k1_batch(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __res
     }
     __syncthreads();
     bytes_ok = s_unclean == 0;
-    if (bytes_ok) best = k1b_scan<W>(job, g, s_win, s_org, s_lbx, s_lby, s_bound);
+    // (eight position rows per thread, k1b_scan<W, 8>, were measured for the narrow PUs: no gain over four -- the
+    //  larger register tile costs the fourth resident CTA)
+    if (bytes_ok) best = k1b_scan<W, 4>(job, g, s_win, s_org, s_lbx, s_lby, s_bound);
   }
   if (!bytes_ok) best = empty ? ~0ull : k1_generic(job, g_old, org, ref_y);
   best = block_min_u64(best, s_red);
