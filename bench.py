@@ -219,10 +219,29 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
     tasks = [dict(width=n, height=n, seed=sd) for sd in seeds]
     if dist is not None:
         dist.barrier()
-    res, makespan = batch.encode_batch(tasks, device=local, procs=procs, use_mps=mps)
+    res, makespan = batch.encode_batch(tasks, device=local, procs=procs, use_mps=mps, stats=True)
     errors = [r["error"] for r in res if "error" in r]
     secs = [r["seconds"] for r in res if "error" not in r]
-    t = torch.tensor([makespan, sum(secs), len(secs), max(secs) if secs else 0.0, len(errors)], dtype=torch.float64, device=dev)
+    # where an encoder process spends its wall clock (HOP_STATS lines of the shim): search calls on the GPU path, SS-mirror
+    # updates, CUDA context creation; the rest is the reference's own host code (RDO, transforms, CABAC)
+    split = np.zeros(3)
+    for r in res:
+        for ln in (r.get("log") or "").splitlines():
+            f = ln.split()
+            if len(f) >= 5 and f[0] == "hopshim:" and f[3] == "calls":
+                k = {"xPatternSearch": 0, "xPatternSearchGT": 0, "prefetch": 0, "refUpdate": 1, "hostBorder": 1, "refReset+create": 2}.get(f[1])
+                if k is not None:
+                    split[k] += float(f[4])
+    # host probe: the same fixed single-threaded CPU job in as many processes as encoders ran, on all ranks at once --
+    # how much slower does a host core get when N x procs of them are busy (all-core clocks, SMT siblings, memory)?
+    if dist is not None:
+        dist.barrier()
+    probe_src = ("import time,numpy as np\nr=np.random.default_rng(1).random(1500000)\nt=time.perf_counter()\n"
+                 "for _ in range(40): np.sort(r)\nprint(time.perf_counter()-t)")
+    pp = [subprocess.Popen([sys.executable, "-c", probe_src], stdout=subprocess.PIPE, text=True) for _ in range(procs)]
+    probe = [float(p_.communicate()[0].strip() or 0) for p_ in pp]
+    t = torch.tensor([makespan, sum(secs), len(secs), max(secs) if secs else 0.0, len(errors)] + list(split) +
+                     [sum(probe), len(probe)], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -240,6 +259,14 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
            "makespan_s": mk, "images_per_s": total / mk if mk > 0 else None,
            "s_per_image": float(t[1].item()) / max(1, total), "s_per_image_max": float(tmax[3].item()),
            "ctus_per_image": ctus, "s_per_ctu": float(t[1].item()) / max(1, total) / ctus, "errors": int(t[4].item()),
+           "host_probe": {"seconds": float(t[8].item()) / max(1.0, float(t[9].item())), "processes": int(t[9].item()),
+                          "what": "a fixed single-threaded numpy job run in as many concurrent processes as encoders, all ranks at once: "
+                                  "its growth with the GPU count is the host's share of any per-image slowdown"},
+           "s_per_image_split": {"gpu_search_calls": float(t[5].item()) / max(1, total), "ss_mirror_updates": float(t[6].item()) / max(1, total),
+                                 "cuda_context_create": float(t[7].item()) / max(1, total),
+                                 "host_rdo_and_rest": (float(t[1].item()) - float(t[5].item() + t[6].item() + t[7].item())) / max(1, total),
+                                 "what": "mean over all images of all ranks, from the shim's HOP_STATS timers; host = the reference's own "
+                                         "untouched code (RDO, transform/quant, CABAC, YUV I/O)"},
            "note": "s_per_image = mean wall clock of an encoder process incl. CUDA start-up, over all images of all ranks; "
                    "makespan = slowest rank; images are independent (no collective)"}
     gpath = os.path.join(ROOT, "tests", "golden", "encode_golden.json")
