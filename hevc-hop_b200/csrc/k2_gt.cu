@@ -346,6 +346,100 @@ __device__ __forceinline__ uint32_t eval_half_tile8(double h0, double h3, double
   return (s + 1) >> 1;                             // (2*sum + 2) >> 2, xCalcHADs8x8 TComRdCost.cpp:1572
 }
 
+// ---- 8x8 tiles, two tiles per register tile (batched kernel) ------------------------------------
+// The Hadamard butterflies are plain integer adds, and every intermediate of an 8x8 SATD of <= 10-bit residuals
+// stays below 2^15 (|d| <= 1023, x8 horizontally, x4 inside the half): two tiles of the SAME candidate therefore
+// share one register tile, one per 16-bit lane.  Lanes hold value + 0x8000 (unsigned, never 0), so that a 32-bit
+//   a + b - 0x80008000   /   a - b + 0x80008000
+// is the lane-wise sum / difference with no carry or borrow between the lanes (each lane result stays inside
+// [1, 65535]) -- one IADD3 per butterfly output for TWO tiles.  The original block is staged already packed
+// (tile A in the low lane, its partner B -- half a block further down, or to the right -- in the high lane), the
+// warped sample of tile A is subtracted with multiplier 1, that of tile B with multiplier 65536 (one IMAD each,
+// as before); |x| = max(lane, 0x10000 - lane) - 0x8000 on the packed word (VIMNMX3.U16x2), the two per-tile sums
+// leave the packed domain through IDP.2A.  Same integers as the one-tile form, ~4 instructions per warped pixel less.
+constexpr unsigned PK_BIAS = 0x80008000u;
+__device__ __forceinline__ unsigned pk_add(unsigned a, unsigned b) { return a + b - PK_BIAS; }
+__device__ __forceinline__ unsigned pk_sub(unsigned a, unsigned b) { return a - b + PK_BIAS; }
+
+template <int WS>
+__device__ __forceinline__ uint32_t eval_half_tile8_pair(double h0, double h3, double h6, double h1, double h4, double h7,
+                                                         int txA, int tyA, int dxB, int dyB, int half,
+                                                         const unsigned* __restrict__ orgp, int pw, const WarpCtx& wc)
+{
+  const int off_x = wc.off_x, off_y = wc.off_y;
+  unsigned d[32];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {                    // packed original block: two 16-byte loads per row, both tiles
+    const uint4 a = *reinterpret_cast<const uint4*>(orgp + (tyA + 4 * half + r) * pw + txA);
+    const uint4 b = *reinterpret_cast<const uint4*>(orgp + (tyA + 4 * half + r) * pw + txA + 4);
+    d[r * 8 + 0] = a.x; d[r * 8 + 1] = a.y; d[r * 8 + 2] = a.z; d[r * 8 + 3] = a.w;
+    d[r * 8 + 4] = b.x; d[r * 8 + 5] = b.y; d[r * 8 + 6] = b.z; d[r * 8 + 7] = b.w;
+  }
+#pragma unroll 1
+  for (int t = 0; t < 2; t++) {                    // tile A, then tile B: the same 32-pixel body (instruction cache)
+    const int tx = txA + (t ? dxB : 0), y0 = tyA + (t ? dyB : 0) + 4 * half;
+    int negmul;
+    asm("mov.b32 %0, %1;" : "=r"(negmul) : "r"(t ? -65536 : -1));   // opaque: keeps one IMAD per pixel for both tiles
+    double h3y[4], h4y[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double yd = small_int_to_double(off_y + y0 + r);
+      h3y[r] = __dmul_rn(h3, yd);
+      h4y[r] = __dmul_rn(h4, yd);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double xd = small_int_to_double(off_x + tx + k);
+      const double h0x = __dmul_rn(h0, xd), h1x = __dmul_rn(h1, xd);
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const double Fx = __dadd_rn(__dadd_rn(h0x, h3y[r]), h6);    // (h0*x + h3*y) + h6, left to right
+        const double Fy = __dadd_rn(__dadd_rn(h1x, h4y[r]), h7);
+        d[r * 8 + k] += (unsigned)(warp_sample<WS>(wc, Fx, Fy) * negmul);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++)                      // horizontal 8-point, both tiles at once
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          const unsigned a = d[r * 8 + j], b = d[r * 8 + j + len];
+          d[r * 8 + j] = pk_add(a, b); d[r * 8 + j + len] = pk_sub(a, b);
+        }
+#pragma unroll
+  for (int k = 0; k < 8; k++)                      // vertical 4-point inside the half
+#pragma unroll
+    for (int len = 1; len < 4; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < 4; i += len << 1)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          const unsigned a = d[j * 8 + k], b = d[(j + len) * 8 + k];
+          d[j * 8 + k] = pk_add(a, b); d[(j + len) * 8 + k] = pk_sub(a, b);
+        }
+  const unsigned pair_mask = 3u << (threadIdx.x & 30u);
+  // lane sums start at -16 * 0x8000: every accumulated maximum carries the lane bias once
+  unsigned sA = 0u - 16u * 0x8000u, sB = 0u - 16u * 0x8000u;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const unsigned mine = half ? d[16 + i] : d[i];
+    const unsigned send = half ? d[i] : d[16 + i];
+    const unsigned recv = __shfl_xor_sync(pair_mask, send, 1);
+    // max(|a|, |b|) + 0x8000 per lane: a lane and its negation 0x10000 - lane (no borrow: lanes are never 0)
+    unsigned m = __vimax3_u16x2(mine, 0x00010000u - mine, recv);
+    m = __vmaxu2(m, 0x00010000u - recv);
+    sA = __dp2a_lo(m, 0x00000001u, sA);
+    sB = __dp2a_lo(m, 0x00000100u, sB);
+  }
+  sA += __shfl_xor_sync(pair_mask, sA, 1);
+  sB += __shfl_xor_sync(pair_mask, sB, 1);
+  return ((sA + 1) >> 1) + ((sB + 1) >> 1);        // per tile (2*sum + 2) >> 2, xCalcHADs8x8 TComRdCost.cpp:1572
+}
+
 // ---- task loops -----------------------------------------------------------------------------------
 // dynamic shared memory: [GtShared][org rows*cols int32][window (rows+2w) x WS uint32 high words]
 // N == 4: blockDim.x = 56 * groups, thread -> (c = tid % 56, g = tid / 56), tiles g, g+groups, ...
@@ -391,6 +485,39 @@ __device__ __forceinline__ void run_tasks8(GtShared& sh, const int* s_org, const
     acc += eval_half_tile8<WS, HAD>(h0, h3, h6, h1, h4, h7, tx, ty, half, s_org, wc, cols);
   }
   if (!HAD || half == 0) atomicAdd(&sh.dist[pb][c], acc);   // HAD: both lanes hold the tile sums, count once
+}
+
+// Pairing of the 8x8 tiles of a PU for the packed form: tile (tx, ty) with the tile half a block further down
+// (rows a multiple of 16), else with the tile half a block to the right (cols a multiple of 16).  Every PU shape
+// with 8x8 tiles except 8x8 itself pairs.  The packed original block is indexed by tile A's coordinates.
+struct PairGeom { int on, pw, ph, dxB, dyB; };
+__host__ __device__ inline PairGeom gt_pair_geom(int cols, int rows)
+{
+  PairGeom g = {0, cols, rows, 0, 0};
+  if ((cols & 7) || (rows & 7)) return g;
+  if ((rows & 15) == 0)      { g.on = 1; g.ph = rows >> 1; g.dyB = rows >> 1; }
+  else if ((cols & 15) == 0) { g.on = 1; g.pw = cols >> 1; g.dxB = cols >> 1; }
+  return g;
+}
+
+template <int WS>
+__device__ __forceinline__ void run_tasks8_pair(GtShared& sh, const unsigned* s_orgp, const uint32_t* s_win, const PairGeom pg,
+                                                int w, int cols, int rows, int off_x, int off_y, int pb)
+{
+  const int half = threadIdx.x & 1, pair = threadIdx.x >> 1;
+  const int tiles_x = pg.pw / 8, npairs = tiles_x * (pg.ph / 8);
+  const int avail = blockDim.x / (2 * GT_CANDS);
+  const int c = pair % GT_CANDS, g = pair / GT_CANDS, groups = avail < npairs ? avail : npairs;
+  if (g >= groups || !sh.valid[pb][c]) return;
+  const double h0 = sh.h0[c], h3 = sh.h3[c], h6 = sh.h6[c];
+  const double h1 = sh.h1[c], h4 = sh.h4[c], h7 = sh.h7[c];
+  const WarpCtx wc(s_win, w, cols, rows, off_x, off_y);
+  uint32_t acc = 0;
+  for (int pr = g; pr < npairs; pr += groups) {
+    const int tx = (pr % tiles_x) * 8, ty = (pr / tiles_x) * 8;
+    acc += eval_half_tile8_pair<WS>(h0, h3, h6, h1, h4, h7, tx, ty, pg.dxB, pg.dyB, half, s_orgp, pg.pw, wc);
+  }
+  if (half == 0) atomicAdd(&sh.dist[pb][c], acc);   // both lanes hold the tile sums, count once
 }
 
 // ---- latency form: one lane per tile ROW ----------------------------------------------------------
@@ -565,7 +692,7 @@ __device__ __forceinline__ void gt_stage_window(const HopGtJob& job, const int16
 // CTA stages the same window and walks the same passes, but evaluates only its share of the Hadamard tiles;
 // after a pass the per-candidate partial sums are gathered through distributed shared memory and every CTA
 // takes the same argmin decision, so no state has to be broadcast.  Rank 0 writes the result.
-template <int WS, bool CL = false>
+template <int WS, bool CL = false, bool PAIR = false>
 __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t* __restrict__ org_buf,
                                               const int16_t* __restrict__ ref_buf, unsigned char* smem_raw,
                                               HopGtResult* __restrict__ out, bool org_staged, RefBounds rb,
@@ -591,7 +718,19 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   const int dist_shift = job.bit_depth - 8;
   const int tile_n = ((rows % 8 == 0) && (cols % 8 == 0)) ? 8 : 4;
 
-  if (!org_staged)
+  // batched kernel, Hadamard cost, 8x8 tiles that pair up: the original block is staged packed, two tiles per word
+  // (eval_half_tile8_pair); it takes the place of the int32 copy, which nothing else reads in that kernel
+  const PairGeom pg = gt_pair_geom(cols, rows);
+  const bool packed = PAIR && !org_staged && pg.on && job.use_had &&
+                      !((int)gridDim.x == 1 && (cols / 8) * (rows / 8) * 8 * GT_CANDS <= (int)blockDim.x);   // not the row-per-lane form (`fine` below)
+  if (packed) {
+    unsigned* s_orgp = reinterpret_cast<unsigned*>(s_org);
+    for (int i = threadIdx.x; i < pg.ph * pg.pw; i += blockDim.x) {
+      const int y = i / pg.pw, x = i - y * pg.pw;
+      const unsigned a = (unsigned)org[y * job.org_stride + x], b = (unsigned)org[(y + pg.dyB) * job.org_stride + x + pg.dxB];
+      s_orgp[i] = (a + 0x8000u) | ((b + 0x8000u) << 16);
+    }
+  } else if (!org_staged)
     for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
       s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
   {
@@ -691,7 +830,8 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
       }
       __syncthreads();
       HOP_STAMP(g_trace_k2, 9 + b * 16 + 2 * pass);    // candidate table of the pass built
-      run_tasks<WS>(sh, s_org, win_b, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb, fine);
+      if (PAIR && packed) run_tasks8_pair<WS>(sh, reinterpret_cast<const unsigned*>(s_org), win_b, pg, w, cols, rows, cols >> 1, rows >> 1, pb);
+      else run_tasks<WS>(sh, s_org, win_b, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb, fine);
       if (CL) cg::this_cluster().sync(); else __syncthreads();
       HOP_STAMP(g_trace_k2, 10 + b * 16 + 2 * pass);   // tiles of the pass evaluated
       if (head) {
@@ -783,7 +923,7 @@ k2_gt_search(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __res
   const int job_id = blockIdx.x;
   if (job_id >= n_jobs) return;
   const HopGtJob job = jobs[job_id];
-  gt_search_cta<WS>(job, org_buf, ref_buf, smem_raw, &out[job_id], false, rb);
+  gt_search_cta<WS, false, true>(job, org_buf, ref_buf, smem_raw, &out[job_id], false, rb);
   if (threadIdx.x == 0 && done_flag) {     // single-call path: result and flag live in mapped host memory
     __threadfence_system();
     *(volatile unsigned*)done_flag = seq;
