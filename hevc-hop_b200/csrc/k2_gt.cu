@@ -995,8 +995,18 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
   const int mvx = job.ss_cand.hor, mvy = job.ss_cand.ver;       // pcMvInt
   const int Hor = (int16_t)(mvx << 2), Ver = (int16_t)(mvy << 2);   // :4713-4724 with half = quarter = 0
 
-  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
-    s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
+  const PairGeom pg = gt_pair_geom(cols, rows);
+  const bool packed = pg.on && job.use_had;                     // two tiles per register tile (eval_half_tile8_pair)
+  if (packed) {
+    unsigned* s_orgp = reinterpret_cast<unsigned*>(s_org);
+    for (int i = threadIdx.x; i < pg.ph * pg.pw; i += blockDim.x) {
+      const int y = i / pg.pw, x = i - y * pg.pw;
+      const unsigned a = (unsigned)org[y * job.org_stride + x], b = (unsigned)org[(y + pg.dyB) * job.org_stride + x + pg.dxB];
+      s_orgp[i] = (a + 0x8000u) | ((b + 0x8000u) << 16);
+    }
+  } else
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x)
+      s_org[i] = org[(i / cols) * job.org_stride + (i % cols)];
   for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
     const int wy = i / win_w, wx = i - wy * win_w;
     long long o = job.ref_off + (long long)(mvy - w + wy) * job.ref_stride + (mvx - w + wx);
@@ -1050,7 +1060,8 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
       sh.dist[0][c] = 0;
     }
     __syncthreads();
-    run_tasks<WS>(sh, s_org, s_win, w, cols, rows, 0, 0, tile_n, job.use_had);
+    if (packed) run_tasks8_pair<WS>(sh, reinterpret_cast<const unsigned*>(s_org), s_win, pg, w, cols, rows, 0, 0, 0);
+    else run_tasks<WS>(sh, s_org, s_win, w, cols, rows, 0, 0, tile_n, job.use_had);
     __syncthreads();
     if (threadIdx.x < 64) {
       const int c = threadIdx.x;
@@ -1194,7 +1205,7 @@ static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d
   // CTA = 56 candidates x `groups` tile groups x (2 lanes per 8x8 tile | 1 lane per 4x4 tile)
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
-  const int ntiles = (max_cols / tile) * (max_rows / tile);
+  const int ntiles = (max_cols / tile) * (max_rows / tile) / (gt_pair_geom(max_cols, max_rows).on && n > 1 ? 2 : 1);   // tile pairs
   const int max_groups = GtCfg<CFG>::T / per_group;
   int groups = ntiles < max_groups ? ntiles : max_groups;
   // fewest loop trips wins; on a tie the smaller CTA (less idle lanes in the last trip)
@@ -1256,7 +1267,7 @@ static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16
   }
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
   const int per_group = tile == 8 ? 2 * GT_CANDS : GT_CANDS;
-  const int ntiles = (max_cols / tile) * (max_rows / tile);
+  const int ntiles = (max_cols / tile) * (max_rows / tile) / (gt_pair_geom(max_cols, max_rows).on ? 2 : 1);   // tile pairs
   const int max_groups = gt_class_threads(WS) / per_group;
   int groups = ntiles < max_groups ? ntiles : max_groups;
   for (int g = groups - 1; g >= 1; g--)
