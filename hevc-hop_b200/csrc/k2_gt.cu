@@ -187,9 +187,14 @@ struct WarpCtx {
 //      (weights within 8e-14 of the exact rationals, samples <= 1023, a handful of roundings at 2^-44);
 //  (3) hence round-to-nearest of either is the same integer, and the 0/255 clip commutes with the rounding.
 //  The reference's literal sequence is kept under HOP_WARP_REFERENCE_OPS for A/B parity runs.
-template <int WS>
+// DXP = true (batched kernels, packed tile pairs): every window row is followed by a row of horizontal differences
+// dx[X] = sample[X + 1] - sample[X] (exact small integers, stored like the samples as the high word of their binary64
+// value), so that the horizontal lerps are one fused multiply-add each: top = A + p * dxA -- the SAME values as
+// A + p * (B - A), since B - A is computed exactly either way -- two additions per warped pixel less.
+template <int WS, bool DXP = false>
 __device__ __forceinline__ int warp_sample(const WarpCtx& wc, double Fx, double Fy)
 {
+  constexpr int RS = DXP ? 2 * WS : WS;          // row stride of the window in words
   const int wox = wc.wox, woy = wc.woy, lim_xw = wc.lim_xw, lim_yw = wc.lim_yw;
   const int Yt = __double2int_rz(Fy);            // C truncation toward zero
   const int Xt = __double2int_rz(Fx);
@@ -199,14 +204,20 @@ __device__ __forceinline__ int warp_sample(const WarpCtx& wc, double Fx, double 
   const int Xc = __vimin_s32_relu(Xt + wox, lim_xw);
   // one IMAD + one LEA: the window's 32-bit shared-memory address is kept as an integer so that the word
   // offset of the window inside the CTA's dynamic shared memory is folded into the base once per pass
-  const unsigned a = wc.win_sa + 4u * (unsigned)(Yc * WS + Xc);
-  unsigned hA, hB, hC, hD;
+  const unsigned a = wc.win_sa + 4u * (unsigned)(Yc * RS + Xc);
+  unsigned hA, hB, hC, hD;                        // DXP: hB, hD are the differences dxA, dxC
   asm("ld.shared.u32 %0, [%1];" : "=r"(hA) : "r"(a));
-  asm("ld.shared.u32 %0, [%1+4];" : "=r"(hB) : "r"(a));
-  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hC) : "r"(a), "n"(WS * 4));
-  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hD) : "r"(a), "n"(WS * 4 + 4));
-  const double A = __hiloint2double((int)hA, 0), B = __hiloint2double((int)hB, 0);
-  const double C = __hiloint2double((int)hC, 0), D = __hiloint2double((int)hD, 0);
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hB) : "r"(a), "n"(DXP ? WS * 4 : 4));
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hC) : "r"(a), "n"(RS * 4));
+  asm("ld.shared.u32 %0, [%1+%2];" : "=r"(hD) : "r"(a), "n"(DXP ? RS * 4 + WS * 4 : RS * 4 + 4));
+  const double A = __hiloint2double((int)hA, 0), C = __hiloint2double((int)hC, 0);
+#ifdef HOP_WARP_REFERENCE_OPS
+  const double B = DXP ? __dadd_rn(A, __hiloint2double((int)hB, 0)) : __hiloint2double((int)hB, 0);   // exact
+  const double D = DXP ? __dadd_rn(C, __hiloint2double((int)hD, 0)) : __hiloint2double((int)hD, 0);
+#else
+  const double dAB = DXP ? __hiloint2double((int)hB, 0) : __dsub_rn(__hiloint2double((int)hB, 0), A);
+  const double dCD = DXP ? __hiloint2double((int)hD, 0) : __dsub_rn(__hiloint2double((int)hD, 0), C);
+#endif
   // (double)Yt / (double)Xt stay I2F conversions: the kernel is issue bound, and the conversion-free form
   // (2^52 magic: LOP + MOV + DADD) measured 4 % slower (profiles/r01_k2_experiments.txt)
 #ifdef HOP_WARP_REFERENCE_OPS
@@ -222,8 +233,8 @@ __device__ __forceinline__ int warp_sample(const WarpCtx& wc, double Fx, double 
   const double q = __dsub_rn(Fy, (double)Yt);
   const double p = __dsub_rn(Fx, (double)Xt);
   // three lerps: top = A + p(B-A), bot = C + p(D-C), aux = top + q(bot-top)   (6 fp64 ops instead of 11)
-  const double top = __fma_rn(p, __dsub_rn(B, A), A);
-  const double bot = __fma_rn(p, __dsub_rn(D, C), C);
+  const double top = __fma_rn(p, dAB, A);
+  const double bot = __fma_rn(p, dCD, C);
   const double aux = __fma_rn(q, __dsub_rn(bot, top), top);
 #endif
   // Adding 1.5*2^52 leaves round-to-nearest(aux) in the low word: no double->int conversion.
@@ -361,7 +372,7 @@ constexpr unsigned PK_BIAS = 0x80008000u;
 __device__ __forceinline__ unsigned pk_add(unsigned a, unsigned b) { return a + b - PK_BIAS; }
 __device__ __forceinline__ unsigned pk_sub(unsigned a, unsigned b) { return a - b + PK_BIAS; }
 
-template <int WS>
+template <int WS, bool DXP>
 __device__ __forceinline__ uint32_t eval_half_tile8_pair(double h0, double h3, double h6, double h1, double h4, double h7,
                                                          int txA, int tyA, int dxB, int dyB, int half,
                                                          const unsigned* __restrict__ orgp, int pw, const WarpCtx& wc)
@@ -395,7 +406,7 @@ __device__ __forceinline__ uint32_t eval_half_tile8_pair(double h0, double h3, d
       for (int r = 0; r < 4; r++) {
         const double Fx = __dadd_rn(__dadd_rn(h0x, h3y[r]), h6);    // (h0*x + h3*y) + h6, left to right
         const double Fy = __dadd_rn(__dadd_rn(h1x, h4y[r]), h7);
-        d[r * 8 + k] += (unsigned)(warp_sample<WS>(wc, Fx, Fy) * negmul);
+        d[r * 8 + k] += (unsigned)(warp_sample<WS, DXP>(wc, Fx, Fy) * negmul);
       }
     }
   }
@@ -500,7 +511,7 @@ __host__ __device__ inline PairGeom gt_pair_geom(int cols, int rows)
   return g;
 }
 
-template <int WS>
+template <int WS, bool DXP>
 __device__ __forceinline__ void run_tasks8_pair(GtShared& sh, const unsigned* s_orgp, const uint32_t* s_win, const PairGeom pg,
                                                 int w, int cols, int rows, int off_x, int off_y, int pb)
 {
@@ -515,7 +526,7 @@ __device__ __forceinline__ void run_tasks8_pair(GtShared& sh, const unsigned* s_
   uint32_t acc = 0;
   for (int pr = g; pr < npairs; pr += groups) {
     const int tx = (pr % tiles_x) * 8, ty = (pr / tiles_x) * 8;
-    acc += eval_half_tile8_pair<WS>(h0, h3, h6, h1, h4, h7, tx, ty, pg.dxB, pg.dyB, half, s_orgp, pg.pw, wc);
+    acc += eval_half_tile8_pair<WS, DXP>(h0, h3, h6, h1, h4, h7, tx, ty, pg.dxB, pg.dyB, half, s_orgp, pg.pw, wc);
   }
   if (half == 0) atomicAdd(&sh.dist[pb][c], acc);   // both lanes hold the tile sums, count once
 }
@@ -644,6 +655,7 @@ template <> struct GtCfg<2> { static constexpr int T = 448, B = 1; };
 template <> struct GtCfg<3> { static constexpr int T = 224, B = 3; };
 template <> struct GtCfg<4> { static constexpr int T = 448, B = 2; };
 template <> struct GtCfg<5> { static constexpr int T = 224, B = 4; };
+template <> struct GtCfg<6> { static constexpr int T = 896, B = 1; };
 
 // Start vector b of the diamond search in integer pels (TEncSearch.cpp:5106-5153); false = the reference skips it.
 __device__ __forceinline__ bool gt_start_vector(const HopGtJob& job, int b, int* Hx, int* Hy)
@@ -676,8 +688,19 @@ __device__ __forceinline__ uint32_t gt_window_word(int v, int max_val)
 }
 template <int WS>
 __device__ __forceinline__ void gt_stage_window(const HopGtJob& job, const int16_t* __restrict__ ref_buf, RefBounds rb,
-                                                int Hx, int Hy, int w, int win_w, int win_h, int max_val, uint32_t* win)
+                                                int Hx, int Hy, int w, int win_w, int win_h, int max_val, uint32_t* win,
+                                                bool with_dx = false)
 {
+  if (with_dx) {     // sample rows interleaved with rows of horizontal differences (warp_sample<WS, true>)
+    for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
+      const int wy = i / win_w, wx = i - wy * win_w;
+      const int v0 = min(max((int)ref_buf[gt_window_offset(job.ref_off, job.ref_stride, rb, Hx, Hy, w, wx, wy)], 0), max_val);
+      const int v1 = wx + 1 < win_w ? min(max((int)ref_buf[gt_window_offset(job.ref_off, job.ref_stride, rb, Hx, Hy, w, wx + 1, wy)], 0), max_val) : v0;
+      win[wy * 2 * WS + wx] = (uint32_t)__double2hiint((double)v0);
+      win[wy * 2 * WS + WS + wx] = (uint32_t)__double2hiint((double)(v1 - v0));
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < win_w * win_h; i += blockDim.x) {
     const int wy = i / win_w, wx = i - wy * win_w;
     win[wy * WS + wx] = gt_window_word(ref_buf[gt_window_offset(job.ref_off, job.ref_stride, rb, Hx, Hy, w, wx, wy)], max_val);
@@ -721,8 +744,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   // batched kernel, Hadamard cost, 8x8 tiles that pair up: the original block is staged packed, two tiles per word
   // (eval_half_tile8_pair); it takes the place of the int32 copy, which nothing else reads in that kernel
   const PairGeom pg = gt_pair_geom(cols, rows);
-  const bool packed = PAIR && !org_staged && pg.on && job.use_had &&
-                      !((int)gridDim.x == 1 && (cols / 8) * (rows / 8) * 8 * GT_CANDS <= (int)blockDim.x);   // not the row-per-lane form (`fine` below)
+  const bool packed = PAIR && !org_staged && pg.on && job.use_had && (int)gridDim.x > 1;   // a batch: the launch sized the window for it
   if (packed) {
     unsigned* s_orgp = reinterpret_cast<unsigned*>(s_org);
     for (int i = threadIdx.x; i < pg.ph * pg.pw; i += blockDim.x) {
@@ -773,7 +795,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
     uint32_t* const win_b = win_slots ? win_slots + (size_t)b * slot_words : s_win;
     if (!((pre_mask >> b) & 1u)) {
       if (!win_slots) __syncthreads();   // previous start done with the slot
-      gt_stage_window<WS>(job, ref_buf, rb, Hx, Hy, w, win_w, win_h, max_val, win_b);
+      gt_stage_window<WS>(job, ref_buf, rb, Hx, Hy, w, win_w, win_h, max_val, win_b, PAIR && packed);
     }
     const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);        // :5345
     HOP_STAMP(g_trace_k2, 8 + b * 16);   // window loads of start b issued
@@ -830,7 +852,7 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
       }
       __syncthreads();
       HOP_STAMP(g_trace_k2, 9 + b * 16 + 2 * pass);    // candidate table of the pass built
-      if (PAIR && packed) run_tasks8_pair<WS>(sh, reinterpret_cast<const unsigned*>(s_org), win_b, pg, w, cols, rows, cols >> 1, rows >> 1, pb);
+      if (PAIR && packed) run_tasks8_pair<WS, true>(sh, reinterpret_cast<const unsigned*>(s_org), win_b, pg, w, cols, rows, cols >> 1, rows >> 1, pb);
       else run_tasks<WS>(sh, s_org, win_b, w, cols, rows, cols >> 1, rows >> 1, tile_n, job.use_had, crank, csize, pb, fine);
       if (CL) cg::this_cluster().sync(); else __syncthreads();
       HOP_STAMP(g_trace_k2, 10 + b * 16 + 2 * pass);   // tiles of the pass evaluated
@@ -997,6 +1019,7 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
 
   const PairGeom pg = gt_pair_geom(cols, rows);
   const bool packed = pg.on && job.use_had;                     // two tiles per register tile (eval_half_tile8_pair)
+  constexpr bool SWEEP_DX = WS != WS_D;                         // difference rows: not for the 64-wide class (two CTAs per SM stay resident)
   if (packed) {
     unsigned* s_orgp = reinterpret_cast<unsigned*>(s_org);
     for (int i = threadIdx.x; i < pg.ph * pg.pw; i += blockDim.x) {
@@ -1013,7 +1036,14 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
     o = o < rb.lo ? rb.lo : (o > rb.hi ? rb.hi : o);
     int v = ref_buf[o];
     v = min(max(v, 0), max_val);
-    s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
+    if (packed && SWEEP_DX) {                                   // with the row of horizontal differences (warp_sample<WS, true>)
+      long long o1 = job.ref_off + (long long)(mvy - w + wy) * job.ref_stride + (mvx - w + wx + 1);
+      o1 = o1 < rb.lo ? rb.lo : (o1 > rb.hi ? rb.hi : o1);
+      const int v1 = wx + 1 < win_w ? min(max((int)ref_buf[o1], 0), max_val) : v;
+      s_win[wy * 2 * WS + wx] = (uint32_t)__double2hiint((double)v);
+      s_win[wy * 2 * WS + WS + wx] = (uint32_t)__double2hiint((double)(v1 - v));
+    } else
+      s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
   }
   const uint32_t mv_add = mv_cost(job.cost, Hor, Ver);          // :5035
   unsigned long long best = ~0ull;
@@ -1060,7 +1090,7 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
       sh.dist[0][c] = 0;
     }
     __syncthreads();
-    if (packed) run_tasks8_pair<WS>(sh, reinterpret_cast<const unsigned*>(s_org), s_win, pg, w, cols, rows, 0, 0, 0);
+    if (packed) run_tasks8_pair<WS, SWEEP_DX>(sh, reinterpret_cast<const unsigned*>(s_org), s_win, pg, w, cols, rows, 0, 0, 0);
     else run_tasks<WS>(sh, s_org, s_win, w, cols, rows, 0, 0, tile_n, job.use_had);
     __syncthreads();
     if (threadIdx.x < 64) {
@@ -1185,11 +1215,12 @@ __global__ void k2_sweep_finalize_x(int n, const HopGtJob* __restrict__ jobs, un
   if (s_timed_out) { out[i].gt_flag = -1; out[i].best_index = -2; }    // incomplete exchange: never a silent partial result
 }
 
-static size_t gt_smem_bytes(int ws, int max_cols, int max_rows)
+static size_t gt_smem_bytes(int ws, int max_cols, int max_rows, bool with_dx = false)
 {
   const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
   const size_t org = ((size_t)max_cols * max_rows + 3) & ~(size_t)3;
-  return GT_SHARED_BYTES + gt_div_bytes(max_cols, max_rows) + sizeof(int) * org + sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w);
+  return GT_SHARED_BYTES + gt_div_bytes(max_cols, max_rows) + sizeof(int) * org +
+         sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w) * (with_dx ? 2 : 1);
 }
 
 template <int WS, int CFG>
@@ -1199,7 +1230,7 @@ static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d
 {
   static SmemOptIn opt_in;
   {
-    cudaError_t e = opt_in.ensure(k2_gt_search<WS, CFG>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+    cudaError_t e = opt_in.ensure(k2_gt_search<WS, CFG>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU, true));
     if (e != cudaSuccess) return e;
   }
   // CTA = 56 candidates x `groups` tile groups x (2 lanes per 8x8 tile | 1 lane per 4x4 tile)
@@ -1214,7 +1245,7 @@ static cudaError_t gt_launch_cfg(int n, const HopGtJob* d_jobs, const int16_t* d
   int threads = per_group * groups;
   if (threads < 64) threads = 64;   // set-up and argmin use the first 64 threads
   if (n == 1) threads = GtCfg<CFG>::T;   // single PU: all lanes, for the row-per-lane tiles (gt_search_cta: fine)
-  k2_gt_search<WS, CFG><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq, rb);
+  k2_gt_search<WS, CFG><<<n, threads, gt_smem_bytes(WS, max_cols, max_rows, n > 1), stream>>>(n, d_jobs, d_org, d_ref, d_out, done_flag, seq, rb);
   return cudaGetLastError();
 }
 
@@ -1229,8 +1260,9 @@ static cudaError_t gt_launch_class(int n, const HopGtJob* d_jobs, const int16_t*
   static int env_cfg = -2;
   if (env_cfg == -2) { const char* e = getenv("HOP_K2_CFG"); env_cfg = e ? atoi(e) : -1; }
   // a single PU (latency path) takes the widest CTA: all of its tiles at once
-  const int cfg = env_cfg >= 0 ? env_cfg : ((WS == WS_D || n == 1) ? 4 : 5);
+  const int cfg = env_cfg >= 0 ? env_cfg : (n == 1 ? 4 : (WS == WS_D ? 6 : 5));
   switch (cfg) {
+    case 6:  return gt_launch_cfg<WS, 6>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 1:  return gt_launch_cfg<WS, 1>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 2:  return gt_launch_cfg<WS, 2>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
     case 3:  return gt_launch_cfg<WS, 3>(n, d_jobs, d_org, d_ref, d_out, max_cols, max_rows, stream, done_flag, seq, rb);
@@ -1262,7 +1294,7 @@ static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16
 {
   static SmemOptIn opt_in;
   {
-    cudaError_t e = opt_in.ensure(k2_gt_sweep<WS>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU));
+    cudaError_t e = opt_in.ensure(k2_gt_sweep<WS>, (int)gt_smem_bytes(WS, HOP_MAX_PU, HOP_MAX_PU, WS != WS_D));
     if (e != cudaSuccess) return e;
   }
   const int tile = ((max_rows % 8 == 0) && (max_cols % 8 == 0)) ? 8 : 4;
@@ -1274,7 +1306,7 @@ static cudaError_t sweep_launch_class(int n, const HopGtJob* d_jobs, const int16
     if ((ntiles + g - 1) / g <= (ntiles + groups - 1) / groups) groups = g;
   int threads = per_group * groups;
   if (threads < 64) threads = 64;
-  k2_gt_sweep<WS><<<dim3(n, chunks), threads, gt_smem_bytes(WS, max_cols, max_rows), stream>>>(
+  k2_gt_sweep<WS><<<dim3(n, chunks), threads, gt_smem_bytes(WS, max_cols, max_rows, WS != WS_D), stream>>>(
       n, d_jobs, d_org, d_ref, cand_begin, cand_end, d_keys, d_counts, rb, xc);
   return cudaGetLastError();
 }

@@ -44,6 +44,12 @@ def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=
     if launcher:                      # e.g. ["taskset", "-c", "3"]
         cmd = list(launcher) + cmd
     env = dict(os.environ, HOP_DEVICE=str(device))
+    if os.environ.get("HOP_ENC_PIN", "1") != "0":
+        # the encoder process sees only ITS GPU: CUDA start-up enumerates and maps every visible device, and on an
+        # 8-GPU box that is most of the 1-2 s a process spends before its first kernel (multi-GPU encode)
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v != ""]
+        env["CUDA_VISIBLE_DEVICES"] = vis[device] if device < len(vis) else str(device)
+        env["HOP_DEVICE"] = "0"
     env.update(env_extra or {})
     t0 = time.perf_counter()
     p = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

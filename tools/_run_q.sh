@@ -1,12 +1,5 @@
-set -x
-O=gpurun_out/r2q
+O=gpurun_out/r2t
 mkdir -p $O
-(time python -m pytest tests/test_gpu_parity.py tests/test_sweep.py tests/test_frac_motion.py -m gpu -x -q) > $O/pytest.txt 2>&1
-tail -3 $O/pytest.txt
-python bench.py --steps 10 --no-cpu-baseline --encode-size 0 --k1-pus 0 > $O/bench.json 2> $O/bench.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2q/bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['per_shape_ms'], d['parity_spot_check'], d['e2e_results_equal_resident'])
-print(d['sweep']['ms'], d['sweep']['candidates_per_s'], d['sweep']['parity_spot_check'])
-PY
+python tools/ctx_create_probe.py 1,4,16 --mps > $O/ctx_probe_1gpu.txt 2>&1
+cat $O/ctx_probe_1gpu.txt
+python -m pytest tests/test_encoder_integration.py -m gpu -x -q -k "identical_to_reference or speculative" 2>&1 | tail -3
