@@ -194,7 +194,7 @@ struct WarpCtx {
 template <int WS, bool DXP = false>
 __device__ __forceinline__ int warp_sample(const WarpCtx& wc, double Fx, double Fy)
 {
-  constexpr int RS = DXP ? 2 * WS : WS;          // row stride of the window in words
+  constexpr int RS = DXP ? 2 * WS + 1 : WS;      // row stride of the window in words: odd (== 7 mod 32) either way
   const int wox = wc.wox, woy = wc.woy, lim_xw = wc.lim_xw, lim_yw = wc.lim_yw;
   const int Yt = __double2int_rz(Fy);            // C truncation toward zero
   const int Xt = __double2int_rz(Fx);
@@ -696,8 +696,8 @@ __device__ __forceinline__ void gt_stage_window(const HopGtJob& job, const int16
       const int wy = i / win_w, wx = i - wy * win_w;
       const int v0 = min(max((int)ref_buf[gt_window_offset(job.ref_off, job.ref_stride, rb, Hx, Hy, w, wx, wy)], 0), max_val);
       const int v1 = wx + 1 < win_w ? min(max((int)ref_buf[gt_window_offset(job.ref_off, job.ref_stride, rb, Hx, Hy, w, wx + 1, wy)], 0), max_val) : v0;
-      win[wy * 2 * WS + wx] = (uint32_t)__double2hiint((double)v0);
-      win[wy * 2 * WS + WS + wx] = (uint32_t)__double2hiint((double)(v1 - v0));
+      win[wy * (2 * WS + 1) + wx] = (uint32_t)__double2hiint((double)v0);
+      win[wy * (2 * WS + 1) + WS + wx] = (uint32_t)__double2hiint((double)(v1 - v0));
     }
     return;
   }
@@ -1040,8 +1040,8 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
       long long o1 = job.ref_off + (long long)(mvy - w + wy) * job.ref_stride + (mvx - w + wx + 1);
       o1 = o1 < rb.lo ? rb.lo : (o1 > rb.hi ? rb.hi : o1);
       const int v1 = wx + 1 < win_w ? min(max((int)ref_buf[o1], 0), max_val) : v;
-      s_win[wy * 2 * WS + wx] = (uint32_t)__double2hiint((double)v);
-      s_win[wy * 2 * WS + WS + wx] = (uint32_t)__double2hiint((double)(v1 - v));
+      s_win[wy * (2 * WS + 1) + wx] = (uint32_t)__double2hiint((double)v);
+      s_win[wy * (2 * WS + 1) + WS + wx] = (uint32_t)__double2hiint((double)(v1 - v));
     } else
       s_win[wy * WS + wx] = (uint32_t)__double2hiint((double)v);
   }
@@ -1220,7 +1220,7 @@ static size_t gt_smem_bytes(int ws, int max_cols, int max_rows, bool with_dx = f
   const int w = (max_cols < max_rows ? max_cols : max_rows) >> 1;
   const size_t org = ((size_t)max_cols * max_rows + 3) & ~(size_t)3;
   return GT_SHARED_BYTES + gt_div_bytes(max_cols, max_rows) + sizeof(int) * org +
-         sizeof(uint32_t) * (size_t)ws * (max_rows + 2 * w) * (with_dx ? 2 : 1);
+         sizeof(uint32_t) * (size_t)(with_dx ? 2 * ws + 1 : ws) * (max_rows + 2 * w);
 }
 
 template <int WS, int CFG>

@@ -55,7 +55,12 @@ def source_report(path):
     f = gzip.open(path, "rt") if path.endswith(".gz") else open(path)
     rows = list(csv.reader(f))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    seen = set()
     for a, b in zip(starts[:-1], starts[1:]):
+        sig = (rows[a][1], tuple(tuple(r[:8]) for r in rows[a + 2:a + 40]))
+        if sig in seen:          # the export repeats every launch's listing
+            continue
+        seen.add(sig)
         name = re.sub(r"\(int, const Hop.*", "", rows[a][1]).replace("void hop::", "")
         h = rows[a + 1]
         si, ei, smp = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
