@@ -353,6 +353,41 @@ def test_randomised_content_and_parameters(ctx):
         assert got.tobytes() == want.tobytes(), it
 
 
+def test_packed_tile_pairs_equal_single_calls(ctx):
+    """A batch evaluates two 8x8 tiles of a candidate in one register tile (16-bit lanes) on a window that carries rows
+    of horizontal differences; a single-PU call takes the one-tile forms (row per lane, half tiles).  Two
+    independent GPU paths, same answers -- at full PU sizes, both bit depths, extreme content (0 / max checkerboards
+    drive the Hadamard coefficients to their bound, 32 x 1023 inside a half tile) and in one mixed-shape batch."""
+    from hevc_hop_b200.workload import GtBatch
+    rng = np.random.default_rng(8)
+    mixed_jobs = []
+    for (c, r) in [(64, 64), (32, 32), (16, 16), (64, 16), (16, 64), (32, 24), (64, 48), (48, 64), (16, 8), (8, 16), (32, 8), (8, 8)]:
+        for bd in (8, 10):
+            n = 4 if c * r >= 2048 else 8
+            maxv = (1 << bd) - 1
+            b = GtBatch(c, r, n, seed=700 + c + 3 * r + bd, bit_depth=bd)
+            org, ref = b.org.copy(), b.ref.copy()
+            half = org.size // 2                  # second half of the PUs: checkerboard blocks against a noise window
+            org[half:] = ((np.arange(org.size - half) // 3) % 2) * maxv
+            ref[ref.size // 2:] = rng.integers(0, maxv + 1, size=ref.size - ref.size // 2)
+            gj = b.gt_jobs.copy()
+            gj["threshold"] = rng.choice([0xFFFFFFFE, 200000, 20000], size=n)
+            got = ctx.pattern_search_gt(gj, org, ref)
+            single = np.concatenate([ctx.pattern_search_gt(gj[k:k + 1], org, ref) for k in range(n)])
+            assert got.tobytes() == single.tobytes(), (c, r, bd)
+            if bd == 8:
+                mixed_jobs.append((gj[:2].copy(), org, ref, got[:2].copy()))
+    # one batch of every 8-bit shape (two PUs each): per-job shapes differ, the launch is sized for 64x64
+    jobs, orgs, refs, want = [], [], [], []
+    for (gj, org, ref, res) in mixed_jobs:
+        j = gj.copy()
+        j["org_off"] += sum(o.size for o in orgs)
+        j["ref_off"] += sum(x.size for x in refs)
+        jobs.append(j); orgs.append(org); refs.append(ref); want.append(res)
+    got = ctx.pattern_search_gt(np.concatenate(jobs), np.concatenate(orgs), np.concatenate(refs))
+    assert got.tobytes() == np.concatenate(want).tobytes()
+
+
 def test_three_lerp_blend_equals_reference_operation_sequence_at_full_size(ctx):
     """DESIGN.md "warp rounding": K2 blends with three lerps; libhopgpu_refops.so is the same library with the
     reference's literal binary64 operation sequence (-DHOP_WARP_REFERENCE_OPS).  The oracle pins both at sizes
