@@ -623,9 +623,20 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_step")
         except Exception:
             traffic = None
+    pipes = None
+    pp = os.path.join(ROOT, "profiles", "k2_pipes.json")
+    if os.path.exists(pp):
+        try:
+            pipes = json.load(open(pp))
+        except Exception:
+            pipes = None
     roofline = {
         "kernel": "k2_gt_search", "bound": "fp64-alu", "achieved": achieved, "peak": fp64_peak, "unit": "Gop/s",
         "frac": achieved / fp64_peak, "traffic": traffic,
+        # what the pipes really do (ncu capture of the same kernels, profiles/): `frac` counts the REFERENCE's 24 fp64
+        # operations per warped pixel, the kernel executes about half as many
+        "fp64_pipe_busy": pipes.get("fp64_pipe_busy") if pipes else None,
+        "pipes_ncu": pipes,
         "peak_source": "hop_probe_alu DADD/DMUL loop, measured in this run (MEASURED_PEAKS.json has no fp64/int32 figure)",
         "algorithmic": {"fp64_ops_per_pixel_candidate": FP64_OPS_PER_PIXEL, "int32_ops_per_pixel_candidate": INT_OPS_PER_PIXEL,
                         "pixel_candidates_per_step": pix_per_step},
