@@ -744,7 +744,8 @@ __device__ __forceinline__ void gt_search_cta(const HopGtJob& job, const int16_t
   // batched kernel, Hadamard cost, 8x8 tiles that pair up: the original block is staged packed, two tiles per word
   // (eval_half_tile8_pair); it takes the place of the int32 copy, which nothing else reads in that kernel
   const PairGeom pg = gt_pair_geom(cols, rows);
-  const bool packed = PAIR && !org_staged && pg.on && job.use_had && (int)gridDim.x > 1;   // a batch: the launch sized the window for it
+  // a batch (the launch sized the window for the difference rows); <= 10-bit residuals keep every lane below 2^15
+  const bool packed = PAIR && !org_staged && pg.on && job.use_had && job.bit_depth <= 10 && (int)gridDim.x > 1;
   if (packed) {
     unsigned* s_orgp = reinterpret_cast<unsigned*>(s_org);
     for (int i = threadIdx.x; i < pg.ph * pg.pw; i += blockDim.x) {
@@ -1018,7 +1019,7 @@ k2_gt_sweep(int n_jobs, const HopGtJob* __restrict__ jobs, const int16_t* __rest
   const int Hor = (int16_t)(mvx << 2), Ver = (int16_t)(mvy << 2);   // :4713-4724 with half = quarter = 0
 
   const PairGeom pg = gt_pair_geom(cols, rows);
-  const bool packed = pg.on && job.use_had;                     // two tiles per register tile (eval_half_tile8_pair)
+  const bool packed = pg.on && job.use_had && job.bit_depth <= 10;   // two tiles per register tile (eval_half_tile8_pair)
   constexpr bool SWEEP_DX = WS != WS_D;                         // difference rows: not for the 64-wide class (two CTAs per SM stay resident)
   if (packed) {
     unsigned* s_orgp = reinterpret_cast<unsigned*>(s_org);
