@@ -1,5 +1,5 @@
 """One launch series per kernel family, small enough for `ncu --set full` (40 replays per launch):
-    python tools/ncu_targets.py [k2] [k1] [sweep] [tail] [pred] [intra]      (default: all)
+    python tools/ncu_targets.py [k2] [k1] [sweep] [tail] [pred] [intra] [dist] [ref]      (default: all)
 Every family runs `WARM` untimed launches first, then the launches ncu should capture; prints CUDA-event times."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
@@ -10,7 +10,7 @@ from hevc_hop_b200.workload import PuBatch, GtBatch
 from hevc_hop_b200.lenslet import lenslet_luma
 
 WARM = int(os.environ.get("NCU_WARM", "1"))
-what = set(sys.argv[1:]) or {"k2", "k1", "sweep", "tail", "pred", "intra"}
+what = set(sys.argv[1:]) or {"k2", "k1", "sweep", "tail", "pred", "intra", "dist", "ref"}
 ctx = hop.HopContext(0)
 dev = torch.device("cuda", 0)
 ts = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -77,3 +77,19 @@ if "intra" in what:
     from hevc_hop_b200.workload import intra_jobs
     ij, io, ir = intra_jobs([4, 8, 16, 32, 64], 64, seed=12)
     timed("k7 intra x%d" % len(ij), lambda: ctx.intra_prescreen(ij, io, ir))
+
+if "dist" in what:
+    from hevc_hop_b200.workload import dist_jobs
+    dj, dorg, dcur = dist_jobs(16, 16, 4096, func=hop.HOP_DF_HADS)
+    timed("k3 dist x%d (16x16 HADs)" % len(dj), lambda: ctx.dist(dj, dorg, dcur))
+
+if "ref" in what:
+    # K4: the SS mirror of a 1024x1024 picture -- fill, then one 64x64 CU patch with its incremental border extension
+    ctx.ref_create(1024, 1024, 80)
+    blk = np.full((64, 64), 77, dtype=np.int16)
+    def run():
+        ctx.ref_reset(-1)
+        ctx.ref_update(0, 0, blk)
+        ctx.ref_update(960, 960, blk)
+        ctx.sync()
+    timed("k4 reset + 2 CU updates", run)
