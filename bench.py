@@ -225,7 +225,12 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
     # where an encoder process spends its wall clock (HOP_STATS lines of the shim): search calls on the GPU path, SS-mirror
     # updates, CUDA context creation; the rest is the reference's own host code (RDO, transforms, CABAC)
     split = np.zeros(3)
+    startup = [r.get("worker_startup_s", 0.0) for r in res if "error" not in r]
     for r in res:
+        if r.get("stats"):          # long-lived workers report per job; their CUDA start-up is `worker_startup_s`
+            st = r["stats"]
+            split += np.array([st["gpu_search_calls"], st["ss_mirror_updates"], st["context_and_mirror_create"]])
+            continue
         for ln in (r.get("log") or "").splitlines():
             f = ln.split()
             if len(f) >= 5 and f[0] == "hopshim:" and f[3] == "calls":
@@ -241,7 +246,7 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
     pp = [subprocess.Popen([sys.executable, "-c", probe_src], stdout=subprocess.PIPE, text=True) for _ in range(procs)]
     probe = [float(p_.communicate()[0].strip() or 0) for p_ in pp]
     t = torch.tensor([makespan, sum(secs), len(secs), max(secs) if secs else 0.0, len(errors)] + list(split) +
-                     [sum(probe), len(probe)], dtype=torch.float64, device=dev)
+                     [sum(probe), len(probe), sum(startup), sum(1 for x in startup if x > 0)], dtype=torch.float64, device=dev)
     tmax = t.clone()
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -258,7 +263,12 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
            "gpus": world, "encoder_processes_per_gpu": procs, "mps": bool(mps), "host_cores": cores,
            "makespan_s": mk, "images_per_s": total / mk if mk > 0 else None,
            "s_per_image": float(t[1].item()) / max(1, total), "s_per_image_max": float(tmax[3].item()),
+           "s_per_image_incl_worker_startup": (float(t[1].item()) + float(t[10].item())) / max(1, total),
            "ctus_per_image": ctus, "s_per_ctu": float(t[1].item()) / max(1, total) / ctus, "errors": int(t[4].item()),
+           "workers": {"long_lived": bool(t[11].item() > 0), "count": int(t[11].item()),
+                       "mean_startup_s": float(t[10].item()) / max(1.0, float(t[11].item())),
+                       "what": "encoder processes that stay alive for their share of the queue (integration/hop_batch_main.cpp): "
+                               "CUDA start-up once per worker, inside the makespan, not inside s_per_image"},
            "host_probe": {"seconds": float(t[8].item()) / max(1.0, float(t[9].item())), "processes": int(t[9].item()),
                           "what": "a fixed single-threaded numpy job run in as many concurrent processes as encoders, all ranks at once: "
                                   "its growth with the GPU count is the host's share of any per-image slowdown"},
@@ -267,8 +277,9 @@ def measure_encode(args, rank, world, local, dist, torch, dev):
                                  "host_rdo_and_rest": (float(t[1].item()) - float(t[5].item() + t[6].item() + t[7].item())) / max(1, total),
                                  "what": "mean over all images of all ranks, from the shim's HOP_STATS timers; host = the reference's own "
                                          "untouched code (RDO, transform/quant, CABAC, YUV I/O)"},
-           "note": "s_per_image = mean wall clock of an encoder process incl. CUDA start-up, over all images of all ranks; "
-                   "makespan = slowest rank; images are independent (no collective)"}
+           "note": "s_per_image = mean wall clock of one image's encode over all images of all ranks (a process per image: incl. its "
+                   "CUDA start-up; long-lived workers: start-up is paid once per worker and reported in `workers`, inside the "
+                   "makespan); makespan = slowest rank; images are independent (no collective)"}
     gpath = os.path.join(ROOT, "tests", "golden", "encode_golden.json")
     if n == 1024 and os.path.exists(gpath) and "error" not in res[0]:
         g = json.load(open(gpath)).get("c0_1024x1024_qp32")

@@ -63,9 +63,18 @@ def mps_stop():
     shutil.rmtree(MPS_DIR, ignore_errors=True)
 
 
-def encode_batch(tasks, device=0, procs=1, use_mps=False, binary=None, keep_outputs=False, stats=False):
+def encode_batch(tasks, device=0, procs=1, use_mps=False, binary=None, keep_outputs=False, stats=False, persistent=None):
     """Encode `tasks` (dicts of encoder.encode keyword arguments incl. width/height) with `procs` concurrent
-    encoder processes on GPU `device`.  Returns (results in task order, makespan seconds)."""
+    encoder processes on GPU `device`.  Returns (results in task order, makespan seconds).
+
+    persistent (default: when the batch front end is built and no other binary is asked for): every worker is ONE
+    long-lived process (encoder.EncoderWorker, integration/hop_batch_main.cpp) that encodes its share of the queue, so
+    the CUDA start-up -- serialised machine-wide by the driver, DESIGN.md section 4 -- is paid once per worker and not
+    once per image; results carry `worker_startup_s`."""
+    if persistent is None:
+        persistent = binary is None and os.path.exists(encoder.HOP_ENCODER_BATCH) and os.environ.get("HOP_BATCH_WORKERS", "1") != "0"
+    if persistent:
+        return _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats)
     binary = binary or encoder.HOP_ENCODER
     q = queue.Queue()
     for i, t in enumerate(tasks):
@@ -98,6 +107,63 @@ def encode_batch(tasks, device=0, procs=1, use_mps=False, binary=None, keep_outp
         th.start()
     for th in threads:
         th.join()
+    return out, time.perf_counter() - t0
+
+
+def _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats):
+    q = queue.Queue()
+    for i, t in enumerate(tasks):
+        q.put((i, t))
+    out = [None] * len(tasks)
+    env_extra = dict(mps_env()) if use_mps else {}
+    if stats:
+        env_extra["HOP_STATS"] = "1"
+
+    def worker():
+        t_start = time.perf_counter()
+        try:
+            w = encoder.EncoderWorker(device=device, env_extra=env_extra)
+        except Exception as e:
+            while True:                                  # a worker that cannot start fails its share loudly
+                try:
+                    i, _ = q.get_nowait()
+                except queue.Empty:
+                    return
+                out[i] = {"error": "worker start: " + str(e)[:300], "seconds": time.perf_counter() - t_start}
+        first = True
+        while True:
+            try:
+                i, t = q.get_nowait()
+            except queue.Empty:
+                break
+            kw = dict(t)
+            wd, ht = kw.pop("width"), kw.pop("height")
+            t0 = time.perf_counter()
+            try:
+                r = w.encode(wd, ht, keep=keep_outputs, **kw)
+                out[i] = {"seconds": r["seconds"], "bytes": len(r["bitstream"]), "md5": hashlib.md5(r["bitstream"]).hexdigest(),
+                          "rec_md5": hashlib.md5(r["rec"]).hexdigest(), "dir": r["dir"] if keep_outputs else None,
+                          "log": r["log"] if stats else None, "start": t0, "stats": r["stats"],
+                          "worker_startup_s": w.startup_seconds if first else 0.0}
+            except Exception as e:                       # an encoder failure is reported, never hidden
+                out[i] = {"error": str(e)[:400], "seconds": time.perf_counter() - t0}
+                try:
+                    w.close()
+                    w = encoder.EncoderWorker(device=device, env_extra=env_extra)
+                except Exception:
+                    break
+            first = False
+        w.close()
+
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=worker) for _ in range(max(1, min(procs, len(tasks))))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for i, o in enumerate(out):
+        if o is None:
+            out[i] = {"error": "not encoded (its worker died)", "seconds": 0.0}
     return out, time.perf_counter() - t0
 
 

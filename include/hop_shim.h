@@ -96,11 +96,16 @@ inline HopCtx* ctx()
 /* TEncTop::create (TEncTop.cpp:89-110): one context per encoder instance = per GPU (HOP_DEVICE selects it). */
 inline void create() { ctx(); }
 
+/* A front end that runs several encodes in one process (integration/hop_batch_main.cpp) keeps the context -- its
+ * stream, pinned result slots and scratch buffers -- across TEncTop::destroy / create; only the mirror is detached. */
+inline bool& keepContext() { static bool keep = false; return keep; }
+
 /* TEncTop::destroy (TEncTop.cpp:204-213): release the context; HOP_STATS=1 prints what the single-PU path did. */
-inline void destroy()
+inline void destroy(bool force = false)
 {
   State& s = state();
   if (!s.ctx) return;
+  if (keepContext() && !force) { s.origin = NULL; s.buf_lo = NULL; s.buf_hi = NULL; s.recording = false; return; }
   if (stats().on) {
     HopCtxStats cs;
     if (hop_ctx_stats(s.ctx, &cs) == HOP_OK) {

@@ -98,3 +98,34 @@ def test_speculative_first_pu_searches_are_used_and_change_nothing():
     assert _stat(noamp["log"], "cache hits") <= hits
     cand = _stat(on["log"], "HOP candidates scored for the encoder")
     assert cand == _stat(off["log"], "HOP candidates scored for the encoder") and cand > 0
+
+
+@pytest.mark.skipif(not os.path.exists(encoder.HOP_ENCODER_BATCH), reason="TAppEncoderHopBatch not built")
+def test_long_lived_worker_writes_the_same_bytes():
+    """integration/hop_batch_main.cpp: the reference's TAppEncTop run once per job inside one process that keeps the CUDA
+    context (BASELINE configs[3]: a queue of images per GPU).  Every job must write exactly what a process of its own
+    writes -- also the second time the same image comes by, and across bit depths / cfgs / sizes."""
+    cases = [dict(width=128, height=128, seed=1, qp=32), dict(width=128, height=64, seed=3, qp=22),
+             dict(width=64, height=64, seed=1, qp=32, bit_depth=10), dict(width=128, height=128, seed=1, qp=32),
+             dict(width=128, height=64, seed=4, frames=2, cfg=encoder.CFG_LOWDELAY_P), dict(width=136, height=104, seed=1, qp=37)]
+    w = encoder.EncoderWorker(env_extra={"HOP_STATS": "1"})
+    try:
+        outs = [w.encode(**c) for c in cases]
+    finally:
+        w.close()
+    assert outs[0]["bitstream"] == outs[3]["bitstream"] and outs[0]["rec"] == outs[3]["rec"]
+    for c, o in zip(cases, outs):
+        one = encoder.encode(encoder.HOP_ENCODER, c["width"], c["height"], **{k: v for k, v in c.items() if k not in ("width", "height")})
+        assert o["bitstream"] == one["bitstream"] and o["rec"] == one["rec"] and o["trace"] == one["trace"], c
+        assert o["stats"] is not None and o["stats"]["gpu_search_calls"] > 0
+
+
+@pytest.mark.skipif(not os.path.exists(encoder.HOP_ENCODER_BATCH), reason="TAppEncoderHopBatch not built")
+def test_batch_driver_workers_and_processes_agree():
+    from hevc_hop_b200 import batch
+    tasks = [dict(width=128, height=64, seed=20 + i) for i in range(5)]
+    a, _ = batch.encode_batch(tasks, procs=2, persistent=True)
+    b, _ = batch.encode_batch(tasks, procs=2, persistent=False)
+    assert all("error" not in r for r in a + b), (a, b)
+    assert [r["md5"] for r in a] == [r["md5"] for r in b] and [r["rec_md5"] for r in a] == [r["rec_md5"] for r in b]
+    assert sum(1 for r in a if r["worker_startup_s"] > 0) == 2
