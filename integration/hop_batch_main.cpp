@@ -67,6 +67,7 @@ int main(int, char**)
 #ifndef HOP_BATCH_NO_GPU
   hopshim::keepContext() = true;        // TEncTop::destroy of a job leaves the context (stream, pinned slots, scratch) alone
   hopshim::create();
+  { hopshim::Stats& st = hopshim::stats(); for (int i = 0; i < 6; i++) { st.sec[i] = 0; st.calls[i] = 0; } }   // start-up is reported by "ready", not by the first job
 #endif
   printf("@@HOPBATCH ready %.3f\n", now_s() - t0);
   fflush(stdout);

@@ -1,10 +1,18 @@
-O=gpurun_out/r2x
-mkdir -p $O
-python -m pytest tests/test_encoder_integration.py -m gpu -x -q -k "long_lived or batch_driver" 2>&1 | tail -4 | cut -c1-300
-python bench.py --steps 3 --no-cpu-baseline --sweep-pus 0 --k1-pus 0 --encode-images 4 > $O/bench_workers.json 2> $O/bench_workers.err
 python - <<'PY'
-import json
-for f in ("workers",):
-    d=json.loads(open('gpurun_out/r2x/bench_%s.json'%f).read().strip().splitlines()[-1])
-    e=d['encode']; print(f, {k:e.get(k) for k in ('images','encoder_processes_per_gpu','makespan_s','images_per_s','s_per_image','bitstream_identical','errors','workers','s_per_image_split')})
+import sys, time, threading
+sys.path.insert(0,'tests'); import conftest
+from hevc_hop_b200 import encoder, batch
+mps = batch.mps_start()
+env = dict(batch.mps_env()) if mps else {}
+env["HOP_STATS"]="1"
+def run(k):
+    w = encoder.EncoderWorker(env_extra=env)
+    print(k, 'startup', round(w.startup_seconds,2), w.ready_line, flush=True)
+    for j in range(2):
+        r = w.encode(512, 512, seed=10*k+j)
+        print(k, j, 'seconds', round(r['seconds'],2), r['stats'], [l for l in r['log'].splitlines() if 'HOPBATCH' in l or 'Total Time' in l], flush=True)
+    w.close()
+th=[threading.Thread(target=run,args=(k,)) for k in range(4)]
+[t.start() for t in th]; [t.join() for t in th]
+batch.mps_stop()
 PY
