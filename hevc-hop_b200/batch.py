@@ -73,6 +73,9 @@ def encode_batch(tasks, device=0, procs=1, use_mps=False, binary=None, keep_outp
     once per image; results carry `worker_startup_s`."""
     if persistent is None:
         persistent = binary is None and os.path.exists(encoder.HOP_ENCODER_BATCH) and os.environ.get("HOP_BATCH_WORKERS", "1") != "0"
+    worker_args = {"width", "height", "seed", "qp", "bit_depth", "crop_of", "cfg", "frames", "extra_args", "input_yuv"}
+    if persistent and any(set(t) - worker_args for t in tasks):
+        persistent = False                     # a task asks for something only the one-process-per-image path offers
     if persistent:
         return _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats)
     binary = binary or encoder.HOP_ENCODER

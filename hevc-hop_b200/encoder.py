@@ -113,10 +113,11 @@ class EncoderWorker:
                 return "".join(log), line.strip()
             log.append(line)
 
-    def encode(self, width, height, seed=0, qp=32, bit_depth=8, crop_of=None, cfg=None, frames=1, extra_args=(), keep=False):
+    def encode(self, width, height, seed=0, qp=32, bit_depth=8, crop_of=None, cfg=None, frames=1, extra_args=(), keep=False,
+               input_yuv=None):
         tmp = tempfile.mkdtemp(prefix="hopenc_")
-        yuv = os.path.join(tmp, "in.yuv")
-        for k in range(frames):
+        yuv = input_yuv or os.path.join(tmp, "in.yuv")
+        for k in range(0 if input_yuv else frames):
             write_yuv420(yuv, lenslet_luma(width, height, seed=seed + k, bit_depth=bit_depth, crop_of=crop_of), bit_depth=bit_depth,
                          append=k > 0)
         args = ["-c", cfg or CFG, "-i", yuv, "-wdt", str(width), "-hgt", str(height), "-fr", "30", "-f", str(frames),

@@ -35,7 +35,7 @@ for q, r in zip(qps, res):
         report["per_qp"][str(q)] = r
         continue
     ok, msg = batch.decoder_round_trip(_oracle.REF_DECODER, r["dir"]) if os.path.exists(_oracle.REF_DECODER) else (None, "decoder not built")
-    stats = [l for l in r["log"].splitlines() if l.startswith("hopshim:") and "x" not in l.split()[2][:3]][:9]
+    stats = [l for l in (r["log"] or "").splitlines() if (l.startswith("hopshim:") and "x" not in l.split()[2][:3]) or l.startswith("@@HOPBATCH stats")][:9]
     report["per_qp"][str(q)] = {"s_per_image": r["seconds"], "s_per_ctu": r["seconds"] / ctus, "bytes": r["bytes"], "md5": r["md5"],
                                 "decoder_round_trip_identical": ok, "decoder_msg": msg, "shim_stats": stats}
 os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
