@@ -268,3 +268,24 @@ def test_host_incremental_border_equals_full_extension(tmp_path):
             lib.border_extend_patch(origin, stride, pic_w, pic_h, m, bx, by, size, size)
             _oracle.extend_border_oracle(full, pic_w, pic_h, m)
             assert (inc == full).all(), (pic_w, pic_h, bx, by, size)
+
+
+def test_batch_front_end_over_the_unpatched_reference(tmp_path):
+    """integration/hop_batch_main.cpp runs the reference's TAppEncTop once per job inside ONE process (the GPU build keeps
+    its CUDA context that way).  Built over the UNPATCHED reference objects (oracle/_ref/TAppEncoderRefBatch,
+    -DHOP_BATCH_NO_GPU) it must write, job after job, what a process per image writes -- bitstream, reconstruction and
+    syntax trace -- also when an image comes by a second time and when the bit depth changes between jobs."""
+    from hevc_hop_b200 import encoder
+    exe = os.path.join(os.path.dirname(_oracle.REF_ENCODER), "TAppEncoderRefBatch")
+    if not (os.path.exists(exe) and os.path.exists(_oracle.REF_ENCODER)):
+        pytest.skip("reference encoders not built")
+    cases = [dict(width=64, height=64, seed=1), dict(width=72, height=64, seed=2, qp=27),
+             dict(width=64, height=64, seed=1), dict(width=64, height=64, seed=5, bit_depth=10)]
+    w = encoder.EncoderWorker(binary=exe)
+    try:
+        outs = [w.encode(**c) for c in cases]
+    finally:
+        w.close()
+    for c, o in zip(cases, outs):
+        ref = _oracle.encode_reference(**c)
+        assert o["bitstream"] == ref["bitstream"] and o["rec"] == ref["rec"] and o["trace"] == ref["trace"], c
