@@ -44,14 +44,7 @@ def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=
     cmd += list(extra_args)
     if launcher:                      # e.g. ["taskset", "-c", "3"]
         cmd = list(launcher) + cmd
-    env = dict(os.environ, HOP_DEVICE=str(device))
-    if os.environ.get("HOP_ENC_PIN", "1") != "0":
-        # the encoder process sees only ITS GPU: CUDA start-up enumerates and maps every visible device, and on an
-        # 8-GPU box that is most of the 1-2 s a process spends before its first kernel (multi-GPU encode)
-        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v != ""]
-        env["CUDA_VISIBLE_DEVICES"] = vis[device] if device < len(vis) else str(device)
-        env["HOP_DEVICE"] = "0"
-    env.update(env_extra or {})
+    env = _child_env(device, env_extra)
     t0 = time.perf_counter()
     p = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     dt = time.perf_counter() - t0
@@ -76,6 +69,9 @@ def encode(binary, width, height, seed=0, qp=32, bit_depth=8, device=0, workdir=
 
 
 def _child_env(device, env_extra):
+    """Environment of an encoder process on GPU `device`.  The process sees only ITS GPU (HOP_ENC_PIN=0 turns that off):
+    CUDA start-up enumerates and maps every visible device -- 7.1 s against 2.1 s for a lone start on a 4-GPU box
+    (profiles/r02_ctx_create_probe_4gpu_box.txt)."""
     env = dict(os.environ, HOP_DEVICE=str(device))
     if os.environ.get("HOP_ENC_PIN", "1") != "0":
         vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v != ""]
