@@ -493,15 +493,15 @@ def run_ours(args):
                                       d["out"].data_ptr(), b.cols, b.rows, stream)
 
     # host calls of one end-to-end step: one hop_pattern_search_gt_batch_async call per shape, except that a
-    # shape with more than 64 MB of input goes in chunks of 1184 PUs (4 waves of the 296 CTAs resident for the
+    # shape with more than 16 MB of input (32x32, 64x64) goes in chunks of 1184 PUs (8 waves of the 148 SMs for the
     # 64x64 class; each chunk a complete call on its own slice of the pinned host buffers, offsets rebased), so
     # that its copy pipelines with its own kernels instead of preceding them.  Small shapes first: their copies
-    # are short and their kernels cover the first big copy.
+    # are short and their kernels cover the copy of the next, larger call.
     e2e_calls = []
     for d in dbat:
         b = d["b"]
         org_per, ref_per = b.org.size // b.n, b.ref.size // b.n
-        chunk = 1184 if 2 * b.n * (org_per + ref_per) > (64 << 20) else b.n
+        chunk = 1184 if 2 * b.n * (org_per + ref_per) > (16 << 20) else b.n
         for k0 in range(0, b.n, chunk):
             k1 = min(b.n, k0 + chunk)
             jobs = b.gt_jobs[k0:k1].copy()
@@ -671,7 +671,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (%.0f MB per step per GPU)" % (in_bytes / 1e6),
                    "candidates_per_step_per_gpu": cands_per_step},
         "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": e2e_ms, "api": "hop_pattern_search_gt_batch_async x%d (64x64 shape in chunks of 1184 PUs) + hop_ctx_sync (host buffers, pinned)" % len(e2e_calls)},
+                "ms_per_step": e2e_ms, "api": "hop_pattern_search_gt_batch_async x%d (32x32 and 64x64 shapes in chunks of 1184 PUs) + hop_ctx_sync (host buffers, pinned)" % len(e2e_calls)},
         "e2e_results_equal_resident": e2e_same,
         "gpu_launches": int(launches),
         "clocks": clocks,
