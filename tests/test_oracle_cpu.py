@@ -289,3 +289,55 @@ def test_batch_front_end_over_the_unpatched_reference(tmp_path):
     for c, o in zip(cases, outs):
         ref = _oracle.encode_reference(**c)
         assert o["bitstream"] == ref["bitstream"] and o["rec"] == ref["rec"] and o["trace"] == ref["trace"], c
+
+
+def test_packed_lane_hadamard_model():
+    """The arithmetic claim behind K2's two-tiles-per-register-tile form (k2_gt.cu, eval_half_tile8_pair), modelled in
+    numpy uint32: two 8x8 residual tiles ride in the 16-bit lanes of one word with a bias of 0x8000 per lane;
+    a + b - 0x80008000 / a - b + 0x80008000 are the lane-wise butterflies with no carry or borrow between the lanes for
+    every residual of <= 10-bit content, |x| + 0x8000 = max(lane, 0x10000 - lane), and the rounded SATDs equal the
+    plain 8x8 Hadamard SATD of each tile -- including the all-extreme tiles that drive a coefficient to 32 x 1023."""
+    rng = np.random.default_rng(3)
+    BIAS = np.uint32(0x80008000)
+
+    def satd_plain(d):                       # xCalcHADs8x8 (TComRdCost.cpp:1478-1575): sum |H d H| with (sum + 2) >> 2
+        h = np.array([[1]], dtype=np.int64)
+        for _ in range(3):
+            h = np.block([[h, h], [h, -h]])
+        return (int(np.abs(h @ d.astype(np.int64) @ h).sum()) + 2) >> 2
+
+    def satd_packed(da, db):
+        w = ((da.astype(np.int64) + 0x8000) | ((db.astype(np.int64) + 0x8000) << 16)).astype(np.uint32)   # (8, 8) words
+        halves = []
+        for half in (0, 1):                  # the two lanes of a pair: rows 4*half .. 4*half+3
+            t = w[4 * half:4 * half + 4].copy()
+            for ln in (1, 2, 4):             # horizontal 8-point
+                for i in range(0, 8, 2 * ln):
+                    for j in range(i, i + ln):
+                        a, b = t[:, j].copy(), t[:, j + ln].copy()
+                        t[:, j], t[:, j + ln] = a + b - BIAS, a - b + BIAS
+            for ln in (1, 2):                # vertical 4-point inside the half
+                for i in range(0, 4, 2 * ln):
+                    for j in range(i, i + ln):
+                        a, b = t[j].copy(), t[j + ln].copy()
+                        t[j], t[j + ln] = a + b - BIAS, a - b + BIAS
+            assert ((t & 0xffff) != 0).all() and ((t >> 16) != 0).all()        # lanes never reach 0: negation below is exact
+            halves.append(t)
+        s = np.zeros(2, dtype=np.int64)
+        for (mine, other) in ((halves[0][:2], halves[1][:2]), (halves[1][2:], halves[0][2:])):   # last vertical stage, folded
+            for m, r in zip(mine.reshape(-1), other.reshape(-1)):
+                cand = [np.uint32(m), np.uint32(0x00010000) - np.uint32(m), np.uint32(r), np.uint32(0x00010000) - np.uint32(r)]
+                lo = max(int(c) & 0xffff for c in cand) - 0x8000
+                hi = max(int(c) >> 16 for c in cand) - 0x8000
+                s += (lo, hi)
+        return ((int(s[0]) + 1) >> 1), ((int(s[1]) + 1) >> 1)
+
+    with np.errstate(over="ignore"):
+        for it in range(60):
+            maxv = 1023 if it % 2 else 255
+            if it < 8:                       # extreme tiles: every residual +-maxv in Hadamard-aligned sign patterns
+                sign = np.where((np.add.outer(np.arange(8) * (it & 3), np.arange(8) * (it >> 1)) & 1) == 0, 1, -1)
+                da, db = sign * maxv, -sign * maxv if it & 1 else np.full((8, 8), maxv)
+            else:
+                da, db = rng.integers(-maxv, maxv + 1, size=(8, 8)), rng.integers(-maxv, maxv + 1, size=(8, 8))
+            assert satd_packed(np.asarray(da), np.asarray(db)) == (satd_plain(np.asarray(da)), satd_plain(np.asarray(db))), it
