@@ -441,6 +441,31 @@ def measure_k1(hop, ctx, torch, dev, tstream, pus, peaks):
     return res
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Several ranks on one host: run this rank -- and with it the first touch of its pinned host buffers -- on the CPUs
+    of the NUMA node its GPU hangs off, so that the end-to-end copies do not cross the socket interconnect.  Returns a
+    short description, or None when the topology is not visible (then nothing is changed).  HOP_BENCH_NUMA=0: off."""
+    if os.environ.get("HOP_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "gpu %s: no NUMA node reported" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "gpu %s: node %d has no CPU this process may use" % (bdf, node)
+        os.sched_setaffinity(0, cpus)
+        return "gpu %s on NUMA node %d: rank bound to %d CPUs" % (bdf, node, len(cpus))
+    except Exception as e:
+        return "topology not visible (%s)" % str(e)[:80]
+
+
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
@@ -458,6 +483,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    cpus_before = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     hop = graft.load_package()
     ctx = hop.HopContext(local)
     batches = make_batches(hop, args.pus, seed=rank + 1)
@@ -512,6 +539,8 @@ def run_ours(args):
             e2e_calls.append((k1 - k0, hj, d["h_org"].data_ptr() + 2 * k0 * org_per, (k1 - k0) * org_per,
                               d["h_ref"].data_ptr() + 2 * k0 * ref_per, (k1 - k0) * ref_per,
                               d["h_out"].data_ptr() + k0 * hop.GT_RES_DT.itemsize))
+
+    os.sched_setaffinity(0, cpus_before)      # the pinned buffers exist (first touch done): the later legs use every core again
 
     def step_e2e():
         # the reference-facing host call: pinned HOST buffers in, results back on the host; the calls of a step
@@ -673,6 +702,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_ms, "api": "hop_pattern_search_gt_batch_async x%d (32x32 and 64x64 shapes in chunks of 1184 PUs) + hop_ctx_sync (host buffers, pinned)" % len(e2e_calls)},
         "e2e_results_equal_resident": e2e_same,
+        "numa_binding_rank0": numa,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
