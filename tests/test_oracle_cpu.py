@@ -341,3 +341,29 @@ def test_packed_lane_hadamard_model():
             else:
                 da, db = rng.integers(-maxv, maxv + 1, size=(8, 8)), rng.integers(-maxv, maxv + 1, size=(8, 8))
             assert satd_packed(np.asarray(da), np.asarray(db)) == (satd_plain(np.asarray(da)), satd_plain(np.asarray(db))), it
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs here (no GPU): one JSON line on stdout with the contract's keys, the same
+    `config.workload` string as the GPU arm, and a cpu_baseline block that describes the bounded sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if _oracle.ref() is None:
+        pytest.skip("oracle/_ref/libhopref.so not built")
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD % 4096
