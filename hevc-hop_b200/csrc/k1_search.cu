@@ -604,37 +604,57 @@ k1_batch(int n_jobs, const HopSearchJob* __restrict__ jobs, const int16_t* __res
     const int wpr = g.sw / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int k_first = (mis + 3) / 4, k_end = (g.st_cols + mis) / 4;      // groups [k_first, k_end) are complete
+    // what a lane does with its (up to three) groups of a row does not depend on the row: decided once.  The row loop
+    // is straight-line code -- loads, one test, one byte permute and one store per group through the 32-bit
+    // shared-memory address -- with ONE branch for the rare groups that hold NOT_VALID or out-of-range samples.
+    bool in_g[3], st_g[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int k = lane + 32 * t;
+      in_g[t] = vec && k >= k_first && k < k_end;
+      st_g[t] = k < wpr;
+    }
+    // opaque moves: the lane's shared-memory base and the row pitch stay in registers (the compiler would otherwise
+    // rebuild the shared-window address from the CTA's special registers in front of every store)
+    unsigned win_sa, sw_r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(win_sa) : "r"((unsigned)__cvta_generic_to_shared(s_win) + 4u * (unsigned)lane));
+    asm volatile("mov.b32 %0, %1;" : "=r"(sw_r) : "r"((unsigned)g.sw));
     for (int r = warp; r < g.st_rows; r += nwarp) {
-      const int16_t* prow = win0 + (long long)r * job.ref_stride - mis;
-      unsigned* srow = reinterpret_cast<unsigned*>(s_win + (size_t)r * g.sw);
+      const uint2* prow = reinterpret_cast<const uint2*>(win0 + (long long)r * job.ref_stride - mis) + lane;
       uint2 u[3];
 #pragma unroll
       for (int t = 0; t < 3; t++) {
-        const int k = lane + 32 * t;
-        if (vec && k >= k_first && k < k_end) u[t] = __ldg(reinterpret_cast<const uint2*>(prow + 4 * k));
+        u[t] = make_uint2(0u, 0u);
+        if (in_g[t]) u[t] = __ldg(prow + 32 * t);
       }
+      unsigned w[3];
+      bool slow = false;
 #pragma unroll
       for (int t = 0; t < 3; t++) {
-        const int k = lane + 32 * t;
-        if (k >= wpr) continue;
-        unsigned w = 0;
-        if (vec && k >= k_first && k < k_end) {
-          if (((u[t].x | u[t].y) & 0xff00ff00u) == 0) {
-            w = __byte_perm(u[t].x, u[t].y, 0x6420);
-          } else {
-            const unsigned e0 = __vcmpeq2(u[t].x, 0xffffffffu), e1 = __vcmpeq2(u[t].y, 0xffffffffu);   // 0xffff per NOT_VALID sample
-            bad |= (((u[t].x & ~e0) | (u[t].y & ~e1)) & 0xff00ff00u) != 0;
-            w = __byte_perm(u[t].x & ~e0, u[t].y & ~e1, 0x6420);
-            const int n_inv = __popc(e0 & 0x00010001u) + __popc(e1 & 0x00010001u);
-            if (n_inv) {
-              const int first = 4 * k - mis + ((e0 & 0xffffu) ? 0 : (e0 ? 1 : ((e1 & 0xffffu) ? 2 : 3)));
-              atomicMin(&s_first_invalid[r], first);
-              atomicAdd(&s_cnt_invalid[r], n_inv);
-            }
+        w[t] = __byte_perm(u[t].x, u[t].y, 0x6420);                      // four plain 8-bit samples (zeros where nothing was read)
+        slow |= ((u[t].x | u[t].y) & 0xff00ff00u) != 0;
+      }
+      if (slow) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          if (((u[t].x | u[t].y) & 0xff00ff00u) == 0) continue;
+          const int k = lane + 32 * t;
+          const unsigned e0 = __vcmpeq2(u[t].x, 0xffffffffu), e1 = __vcmpeq2(u[t].y, 0xffffffffu);   // 0xffff per NOT_VALID sample
+          bad |= (((u[t].x & ~e0) | (u[t].y & ~e1)) & 0xff00ff00u) != 0;
+          w[t] = __byte_perm(u[t].x & ~e0, u[t].y & ~e1, 0x6420);
+          const int n_inv = __popc(e0 & 0x00010001u) + __popc(e1 & 0x00010001u);
+          if (n_inv) {
+            const int first = 4 * k - mis + ((e0 & 0xffffu) ? 0 : (e0 ? 1 : ((e1 & 0xffffu) ? 2 : 3)));
+            atomicMin(&s_first_invalid[r], first);
+            atomicAdd(&s_cnt_invalid[r], n_inv);
           }
         }
-        srow[k] = w;                                                     // edge and outside groups: zero for now
       }
+      const unsigned row_sa = win_sa + (unsigned)r * sw_r;
+      // edge and outside groups: zero for now
+      if (st_g[0]) asm volatile("st.shared.u32 [%0], %1;" :: "r"(row_sa), "r"(w[0]) : "memory");
+      if (st_g[1]) asm volatile("st.shared.u32 [%0+128], %1;" :: "r"(row_sa), "r"(w[1]) : "memory");
+      if (st_g[2]) asm volatile("st.shared.u32 [%0+256], %1;" :: "r"(row_sa), "r"(w[2]) : "memory");
     }
     __syncthreads();
     {
