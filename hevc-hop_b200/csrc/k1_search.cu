@@ -426,9 +426,9 @@ __host__ __device__ inline size_t k1b_smem_bytes(const HopSearchJob& job, const 
 }
 
 template <int W>
-__device__ __forceinline__ void k1b_load_row(const unsigned char* col0, int sw, int srow, unsigned (&sh)[4][W])
+__device__ __forceinline__ void k1b_load_row(const unsigned char* row, unsigned (&sh)[4][W])
 {
-  const unsigned* rw = reinterpret_cast<const unsigned*>(col0 + (size_t)srow * sw);
+  const unsigned* rw = reinterpret_cast<const unsigned*>(row);
   unsigned w0 = rw[0];
 #pragma unroll
   for (int k = 0; k < W; k++) {
@@ -476,28 +476,34 @@ __device__ __forceinline__ unsigned long long k1b_scan(const HopSearchJob& job, 
     for (int j = 0; j < Q; j++)
 #pragma unroll
       for (int a = 0; a < 4; a++) acc[j][a] = 0;
-    const unsigned char* col0 = s_win + 4 * xg;
+    // running pointers: the reference row of step m and the block row that position row Q-1 meets at step m
+    const unsigned char* rowp = s_win + 4 * xg + (size_t)q0 * g.sw;
+    const size_t rstep = (size_t)S * g.sw;
+    const unsigned* op = s_org - (Q - 1) * W;
     unsigned sh[4][W];
     // reference row m serves block row m - j of position row j; rows past the staged window only feed padded positions
     // head: m = 0 .. Q-2, position rows j <= m
 #pragma unroll
     for (int m = 0; m < Q - 1; m++) {
-      k1b_load_row<W>(col0, g.sw, q0 + S * m, sh);
+      k1b_load_row<W>(rowp, sh);
 #pragma unroll
-      for (int j = 0; j <= m; j++) k1b_accum<W>(s_org + (m - j) * W, sh, acc[j]);
+      for (int j = 0; j <= m; j++) k1b_accum<W>(op + (Q - 1 - j) * W, sh, acc[j]);
+      rowp += rstep; op += W;
     }
     // steady state: every position row takes part
     for (int m = Q - 1; m < R; m++) {
-      k1b_load_row<W>(col0, g.sw, q0 + S * m, sh);
+      k1b_load_row<W>(rowp, sh);
 #pragma unroll
-      for (int j = 0; j < Q; j++) k1b_accum<W>(s_org + (m - j) * W, sh, acc[j]);
+      for (int j = 0; j < Q; j++) k1b_accum<W>(op + (Q - 1 - j) * W, sh, acc[j]);
+      rowp += rstep; op += W;
     }
     // tail: m = R .. R+Q-2, position rows j > m - R
 #pragma unroll
     for (int t = 0; t < Q - 1; t++) {
-      k1b_load_row<W>(col0, g.sw, q0 + S * (R + t), sh);
+      k1b_load_row<W>(rowp, sh);
 #pragma unroll
-      for (int j = t + 1; j < Q; j++) k1b_accum<W>(s_org + (R + t - j) * W, sh, acc[j]);
+      for (int j = t + 1; j < Q; j++) k1b_accum<W>(op + (Q - 1 - j) * W, sh, acc[j]);
+      rowp += rstep; op += W;
     }
     // epilogue.  (acc << sub) + (t >> 16) == hi32(t * 65536) + acc * (1 << sub) runs on the multiply-add pipe.
     // Inside a task the raster index grows with the row and with x, so "first strict minimum" is the minimum of
