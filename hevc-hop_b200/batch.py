@@ -77,7 +77,7 @@ def encode_batch(tasks, device=0, procs=1, use_mps=False, binary=None, keep_outp
     if persistent and any(set(t) - worker_args for t in tasks):
         persistent = False                     # a task asks for something only the one-process-per-image path offers
     if persistent:
-        return _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats)
+        return _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats, binary)
     binary = binary or encoder.HOP_ENCODER
     q = queue.Queue()
     for i, t in enumerate(tasks):
@@ -113,7 +113,7 @@ def encode_batch(tasks, device=0, procs=1, use_mps=False, binary=None, keep_outp
     return out, time.perf_counter() - t0
 
 
-def _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats):
+def _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats, binary=None):
     q = queue.Queue()
     for i, t in enumerate(tasks):
         q.put((i, t))
@@ -125,7 +125,7 @@ def _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats):
     def worker():
         t_start = time.perf_counter()
         try:
-            w = encoder.EncoderWorker(device=device, env_extra=env_extra)
+            w = encoder.EncoderWorker(binary=binary, device=device, env_extra=env_extra)
         except Exception as e:
             while True:                                  # a worker that cannot start fails its share loudly
                 try:
@@ -152,7 +152,7 @@ def _encode_batch_workers(tasks, device, procs, use_mps, keep_outputs, stats):
                 out[i] = {"error": str(e)[:400], "seconds": time.perf_counter() - t0}
                 try:
                     w.close()
-                    w = encoder.EncoderWorker(device=device, env_extra=env_extra)
+                    w = encoder.EncoderWorker(binary=binary, device=device, env_extra=env_extra)
                 except Exception:
                     break
             first = False

@@ -367,3 +367,22 @@ def test_bench_reference_arm_contract():
     sys.path.insert(0, root)
     import bench
     assert d["config"]["workload"] == bench.WORKLOAD % 4096
+
+
+def test_batch_driver_on_cpu_workers_and_processes_agree():
+    """hevc_hop_b200.batch.encode_batch over the CPU builds of the two front ends (unpatched reference): a pool of long-lived
+    workers pulling from a queue writes the same bitstreams as one process per image; a task the encoder rejects is
+    reported as an error and the rest of the queue is still encoded."""
+    from hevc_hop_b200 import batch
+    exe = os.path.join(os.path.dirname(_oracle.REF_ENCODER), "TAppEncoderRefBatch")
+    if not (os.path.exists(exe) and os.path.exists(_oracle.REF_ENCODER)):
+        pytest.skip("reference encoders not built")
+    tasks = [dict(width=64, height=64, seed=30 + i) for i in range(4)]
+    a, _ = batch.encode_batch(tasks, procs=2, persistent=True, binary=exe)
+    b, _ = batch.encode_batch(tasks, procs=2, persistent=False, binary=_oracle.REF_ENCODER)
+    assert all("error" not in r for r in a + b), (a, b)
+    assert [r["md5"] for r in a] == [r["md5"] for r in b] and [r["rec_md5"] for r in a] == [r["rec_md5"] for r in b]
+    assert sum(1 for r in a if r["worker_startup_s"] > 0) == 2
+    bad = [dict(width=64, height=64, seed=1), dict(width=64, height=64, seed=2, cfg="/nonexistent/hop.cfg"), dict(width=64, height=64, seed=3)]
+    c, _ = batch.encode_batch(bad, procs=1, persistent=True, binary=exe)
+    assert "error" in c[1] and "error" not in c[0] and "error" not in c[2]
